@@ -1,0 +1,257 @@
+// host_record.cpp -- host-side record helpers of the C ABI: BAM record -> pinned SoA staging
+// (hm_pack_record), CodecV1 (hm_codev1_*), and the MM/ML/MN writer (hm_build_mod_record).
+//
+// Reference behaviour mirrored here:
+//   acceptance rules     src/app/hifimeth/mod_main.cpp:189-196, src/corelib/bam_info.cpp:443-453,572-603
+//   CodecV1              src/corelib/bam_info.cpp:455-478 (encode), :562-570 (decode table)
+//   tag stripping + MM/ML/MN   src/corelib/build_mod_bam.cpp:87-109,125-247
+#include <cstring>
+#include <vector>
+
+#include "../../include/hm_engine.h"
+
+namespace {
+
+struct AuxField {
+    size_t tag_off;  // offset of tag[0]
+    size_t end_off;  // one past the field
+};
+
+// Walks the aux area.  Returns false when a field is truncated or has an unknown type.
+bool next_aux(const uint8_t* b, size_t p, size_t len, AuxField& f)
+{
+    if (p + 3 > len) return false;
+    size_t q = p + 3;
+    switch (b[p + 2]) {
+    case 'A': case 'c': case 'C': q += 1; break;
+    case 's': case 'S': q += 2; break;
+    case 'i': case 'I': case 'f': q += 4; break;
+    case 'd': q += 8; break;
+    case 'Z': case 'H':
+        while (q < len && b[q]) ++q;
+        q += 1;
+        break;
+    case 'B': {
+        if (q + 5 > len) return false;
+        size_t es;
+        switch (b[q]) {
+        case 'c': case 'C': es = 1; break;
+        case 's': case 'S': es = 2; break;
+        case 'i': case 'I': case 'f': es = 4; break;
+        default: return false;
+        }
+        uint32_t n;
+        memcpy(&n, b + q + 1, 4);
+        q += 5 + es * (size_t)n;
+        break;
+    }
+    default: return false;
+    }
+    if (q > len) return false;
+    f.tag_off = p;
+    f.end_off = q;
+    return true;
+}
+
+struct RecLayout {
+    uint16_t flag;
+    int32_t l_seq;
+    size_t seq_off, aux_off;
+};
+
+bool layout_of(const uint8_t* body, size_t len, RecLayout& r)
+{
+    if (len < 32) return false;
+    uint8_t l_read_name = body[8];
+    uint16_t n_cigar;
+    memcpy(&n_cigar, body + 12, 2);
+    memcpy(&r.flag, body + 14, 2);
+    memcpy(&r.l_seq, body + 16, 4);
+    if (r.l_seq < 0) return false;
+    r.seq_off = 32 + (size_t)l_read_name + 4u * (size_t)n_cigar;
+    r.aux_off = r.seq_off + (size_t)((r.l_seq + 1) >> 1) + (size_t)r.l_seq;
+    return r.aux_off <= len;
+}
+
+size_t put_decimal(uint8_t* dst, uint32_t v)
+{
+    uint8_t tmp[12];
+    size_t n = 0;
+    do { tmp[n++] = (uint8_t)('0' + v % 10); v /= 10; } while (v);
+    for (size_t i = 0; i < n; ++i) dst[i] = tmp[n - 1 - i];
+    return n;
+}
+
+size_t put_mn(uint8_t* dst, int32_t l_seq)
+{
+    // bam_aux_update_int stores the smallest integer type that fits (src/htslib/sam.h:1844-1866)
+    dst[0] = 'M'; dst[1] = 'N';
+    if (l_seq <= 0xff) { dst[2] = 'C'; dst[3] = (uint8_t)l_seq; return 4; }
+    if (l_seq <= 0xffff) { dst[2] = 'S'; uint16_t v = (uint16_t)l_seq; memcpy(dst + 3, &v, 2); return 5; }
+    dst[2] = 'I'; uint32_t v = (uint32_t)l_seq; memcpy(dst + 3, &v, 4); return 7;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint8_t hm_codev1_encode(uint32_t frames)
+{
+    uint32_t s = frames < 952u ? frames : 952u;
+    if (s >= 448) return (uint8_t)((s - 448) / 8 + 192);
+    if (s >= 192) return (uint8_t)((s - 192) / 4 + 128);
+    if (s >= 64) return (uint8_t)((s - 64) / 2 + 64);
+    return (uint8_t)s;
+}
+
+uint16_t hm_codev1_decode(uint8_t code)
+{
+    uint32_t c = code;
+    if (c < 64) return (uint16_t)c;
+    if (c < 128) return (uint16_t)((c - 64) * 2 + 64);
+    if (c < 192) return (uint16_t)((c - 128) * 4 + 192);
+    return (uint16_t)((c - 192) * 8 + 448);
+}
+
+int hm_pack_record(hm_read_batch* b, uint32_t* n_reads, const uint8_t* body, size_t len, int32_t min_read_len)
+{
+    if (!b || !n_reads || !body) return HM_ERR_ARG;
+    RecLayout r;
+    if (!layout_of(body, len, r)) return HM_ERR_FORMAT;
+    uint32_t i = *n_reads;
+    uint32_t l = (uint32_t)r.l_seq;
+    if (i >= b->max_reads) return HM_ERR_ARG;
+    uint32_t b0 = i ? b->base_off[i] : 0, s0 = i ? b->seq_off[i] : 0;
+    if ((uint64_t)b0 + l > b->max_bases) return HM_ERR_ARG;
+    if (i == 0) { b->base_off[0] = 0; b->seq_off[0] = 0; }
+
+    // locate the four kinetics tags (first occurrence wins, as bam_aux_get does)
+    const uint8_t* tag[4] = {nullptr, nullptr, nullptr, nullptr};
+    static const char names[4][2] = {{'f', 'i'}, {'f', 'p'}, {'r', 'i'}, {'r', 'p'}};
+    size_t p = r.aux_off;
+    AuxField f;
+    while (p < len && next_aux(body, p, len, f)) {
+        for (int k = 0; k < 4; ++k)
+            if (!tag[k] && body[p] == (uint8_t)names[k][0] && body[p + 1] == (uint8_t)names[k][1]) tag[k] = body + p + 2;
+        p = f.end_off;
+    }
+    bool ok = r.l_seq >= min_read_len;
+    for (int k = 0; k < 4 && ok; ++k) {
+        const uint8_t* t = tag[k];
+        if (!t || t[0] != 'B' || (t[1] != 'C' && t[1] != 'S')) { ok = false; break; }
+        uint32_t n;
+        memcpy(&n, t + 2, 4);
+        if (n != l) ok = false;
+    }
+    uint8_t* planes[4] = {b->fi + b0, b->fp + b0, b->ri + b0, b->rp + b0};
+    if (ok) {
+        for (int k = 0; k < 4; ++k) {
+            const uint8_t* t = tag[k];
+            if (t[1] == 'C') memcpy(planes[k], t + 6, l);
+            else
+                for (uint32_t j = 0; j < l; ++j) {
+                    uint16_t v;
+                    memcpy(&v, t + 6 + 2 * (size_t)j, 2);
+                    planes[k][j] = hm_codev1_encode(v);
+                }
+        }
+    } else {
+        for (int k = 0; k < 4; ++k) memset(planes[k], 0, l);
+    }
+    memcpy(b->seq4 + s0, body + r.seq_off, (l + 1) >> 1);
+    b->flag[i] = r.flag;
+    b->valid[i] = ok ? 1 : 0;
+    b->base_off[i + 1] = b0 + l;
+    b->seq_off[i + 1] = s0 + ((l + 1) >> 1);
+    *n_reads = i + 1;
+    return HM_OK;
+}
+
+size_t hm_mod_record_bound(size_t len, uint32_t n_calls) { return len + 64 + 12 * (size_t)n_calls; }
+
+int hm_build_mod_record(const uint8_t* body, size_t len, int keep_kinetics, const int32_t* fwd_qoff,
+                        const uint8_t* fwd_ml, uint32_t n_fwd, const int32_t* rev_qoff, const uint8_t* rev_ml,
+                        uint32_t n_rev, uint8_t* out, size_t* out_len)
+{
+    RecLayout r;
+    if (!body || !out || !out_len || !layout_of(body, len, r)) return HM_ERR_FORMAT;
+    const bool have_calls = (n_fwd + n_rev) > 0;
+    memcpy(out, body, r.aux_off);
+    size_t o = r.aux_off;
+
+    // One filtering pass == the reference's delete-by-name sequence: first fi/ri/fp/rp (unless -k),
+    // then the first ML and the first MM; an existing integer MN is rewritten in place.
+    bool dropped[6] = {false, false, false, false, false, false};
+    static const char names[6][2] = {{'f', 'i'}, {'r', 'i'}, {'f', 'p'}, {'r', 'p'}, {'M', 'L'}, {'M', 'M'}};
+    bool mn_written = false;
+    size_t p = r.aux_off;
+    AuxField f;
+    while (p < len) {
+        if (!next_aux(body, p, len, f)) {  // corrupt tail: keep bytes as they are
+            memcpy(out + o, body + p, len - p);
+            o += len - p;
+            break;
+        }
+        bool drop = false;
+        for (int k = 0; k < 6; ++k) {
+            if (dropped[k] || body[p] != (uint8_t)names[k][0] || body[p + 1] != (uint8_t)names[k][1]) continue;
+            if (k < 4 && keep_kinetics) continue;
+            dropped[k] = true;
+            drop = true;
+        }
+        if (!drop && have_calls && !mn_written && body[p] == 'M' && body[p + 1] == 'N' && strchr("cCsSiI", body[p + 2])) {
+            o += put_mn(out + o, r.l_seq);
+            mn_written = true;
+            drop = true;
+        }
+        if (!drop) {
+            memcpy(out + o, body + p, f.end_off - p);
+            o += f.end_off - p;
+        }
+        p = f.end_off;
+    }
+    if (!have_calls) { *out_len = o; return HM_OK; }
+
+    // forward-strand base at original-read offset k: get_bam_fwd_strand_base (bam_info.cpp:224-232)
+    const uint8_t* seq = body + r.seq_off;
+    const bool is_rev = (r.flag & 16) != 0;
+    const int32_t L = r.l_seq;
+    auto fwd_nib = [&](int32_t k) -> int {
+        int32_t i = is_rev ? L - 1 - k : k;
+        int nib = (seq[i >> 1] >> ((~i & 1) << 2)) & 0xf;
+        if (!is_rev) return nib;
+        switch (nib) { case 1: return 8; case 2: return 4; case 4: return 2; case 8: return 1; default: return nib; }
+    };
+    out[o++] = 'M'; out[o++] = 'M'; out[o++] = 'Z';
+    for (int pass = 0; pass < 2; ++pass) {
+        const int32_t* qoff = pass ? rev_qoff : fwd_qoff;
+        const uint32_t n = pass ? n_rev : n_fwd;
+        const int target = pass ? 4 : 2;  // G : C
+        out[o++] = pass ? 'G' : 'C';
+        out[o++] = pass ? '-' : '+';
+        out[o++] = 'm';
+        int32_t last = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            if (qoff[i] < last || qoff[i] >= L || fwd_nib(qoff[i]) != target) return HM_ERR_ARG;
+            uint32_t delta = 0;
+            for (int32_t k = last; k < qoff[i]; ++k) delta += (fwd_nib(k) == target);
+            out[o++] = ',';
+            o += put_decimal(out + o, delta);
+            last = qoff[i] + 1;
+        }
+        out[o++] = ';';
+    }
+    out[o++] = 0;
+    out[o++] = 'M'; out[o++] = 'L'; out[o++] = 'B'; out[o++] = 'C';
+    uint32_t cnt = n_fwd + n_rev;
+    memcpy(out + o, &cnt, 4); o += 4;
+    if (n_fwd) memcpy(out + o, fwd_ml, n_fwd);
+    o += n_fwd;
+    if (n_rev) memcpy(out + o, rev_ml, n_rev);
+    o += n_rev;
+    if (!mn_written) o += put_mn(out + o, r.l_seq);
+    *out_len = o;
+    return HM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,33 @@
+// onnx_weights.h -- loads models/{CpG,CHG,CHH}.onnx into plain host arrays.
+//
+// Replaces ov::Core::read_model + the input-shape checks of ModModels::s_load_one_model
+// (reference: src/app/hifimeth/mod_main.cpp:32-67).  Both ONNX dialects that ship are handled
+// (SURVEY.md appendix A): opset 17 with named initializers and Gemm(transB=1) (CpG, CHG), and opset 11
+// with every weight in a Constant node and MatMul+Add with pre-transposed FC weights (CHH).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace hm {
+
+struct ConvLayer {
+    int cout = 0, cin = 0, k = 0;
+    std::vector<float> w;  // [cout][cin][k] as stored in the file
+    std::vector<float> b;  // [cout]
+};
+
+struct CnnModel {
+    int kmer = 0, features = 0;            // from the graph input shape [batch, kmer, features]
+    float bn_eps = 1e-5f;
+    std::vector<float> bn_w, bn_b, bn_mean, bn_var;  // [features]
+    std::vector<ConvLayer> convs;          // 8 layers, stride 2, pad 1
+    std::vector<float> fc1_w, fc1_b;       // [256][128] (out, in), [256]
+    std::vector<float> fc2_w, fc2_b;       // [2][256], [2]
+    int fc1_out = 0, fc1_in = 0, fc2_out = 0;
+};
+
+// Returns true on success; on failure err holds a one-line reason.
+bool load_onnx_model(const std::string& path, CnnModel& out, std::string& err);
+
+}  // namespace hm

@@ -88,7 +88,11 @@ def soa_from_reads(reads, min_read_len: int = 1000) -> ReadBatch:
     seq_off = np.zeros(n + 1, dtype=np.uint32)
     seq_off[1:] = np.cumsum(seq_bytes)
     seq4 = np.concatenate([pack_seq(r["seq"]) for r in reads]) if n else np.zeros(0, np.uint8)
-    cat = lambda k: (np.concatenate([r[k] for r in reads]) if n else np.zeros(0, np.uint8)).astype(np.uint8)
+
+    def cat(k):  # a missing or wrong-length plane is staged as zeros (the read is invalid anyway)
+        parts = [r[k] if (r.get(k) is not None and len(r[k]) == len(r["seq"])) else np.zeros(len(r["seq"]), np.uint8) for r in reads]
+        return (np.concatenate(parts) if n else np.zeros(0, np.uint8)).astype(np.uint8)
+
     valid = np.array([1 if (len(r["seq"]) >= min_read_len and all(r.get(k) is not None and len(r[k]) == len(r["seq"])
                                                                  for k in ("fi", "ri", "fp", "rp"))) else 0
                       for r in reads], dtype=np.uint8)
@@ -113,7 +117,9 @@ def record_body(r, *, kinetics_as_u16: bool = False, extra_mm: bool = False) -> 
         if v is None:
             continue
         if kinetics_as_u16:
-            frames = codev1_decode_table()[v].astype("<u2")
+            # raw frames that re-encode (src/corelib/bam_info.cpp:455-478) to the same code: table value plus the
+            # largest remainder the code's step size absorbs
+            frames = (codev1_decode_table()[v] + (1 << (v >> 6)) - 1).astype("<u2")
             out.append(tag.encode() + b"BS" + struct.pack("<I", len(v)) + frames.tobytes())
         else:
             out.append(tag.encode() + b"BC" + struct.pack("<I", len(v)) + v.astype(np.uint8).tobytes())

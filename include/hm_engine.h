@@ -1,0 +1,173 @@
+/*
+ * hm_engine.h -- C ABI of the B200-native engine for the read-level `hifimeth call` hot path.
+ *
+ * This is the drop-in boundary.  It replaces, inside the reference's worker thread
+ * (src/app/hifimeth/mod_main.cpp:145-262), everything between SAM_Batch::get_next_sam
+ * (src/corelib/sam_batch.hpp:38) and build_one_mod_bam (src/corelib/build_mod_bam.hpp:8-10):
+ *
+ *   reference interface                                         replaced by
+ *   ----------------------------------------------------------  -------------------------------------
+ *   ModModels ctor: read_model(.onnx) / reshape / compile_model  hm_engine_create
+ *     src/app/hifimeth/mod_main.cpp:32-98
+ *   EvalKmerFeaturesGenerator::init(bam1_t*)                     hm_batch_acquire + hm_pack_record
+ *     src/app/hifimeth/eval_kmer_features.hpp:17-22                (record -> pinned SoA staging)
+ *   extract_{cpg,chg,chh}_samples + ModBatch::call_mods_for_     hm_batch_submit
+ *     one_read + ModBatch::call_current_batch + infer()
+ *     src/app/hifimeth/eval_kmer_features.cpp:67-136,
+ *     src/app/hifimeth/mod_batch.cpp:66-93
+ *   per-read regroup of MolMethyCall (sort by qid, split by      hm_batch_collect
+ *     strand, sort by qoff)  src/app/hifimeth/mod_main.cpp:217-251   (fwd/rev qoff[] + ml[] per read =
+ *                                                                  the argument lists of build_one_mod_bam)
+ *   build_one_mod_bam  src/corelib/build_mod_bam.cpp:125-248      hm_build_mod_record (host helper)
+ *
+ * Conventions: every function returns 0 on success or a negative hm_status; hm_last_error() gives the
+ * message.  Nothing throws or aborts across this boundary (the reference aborts: src/corelib/hbn_aux.hpp:
+ * 100-101,146-154).  No torch types, plain pointers and sizes only.  There is no CPU fallback: creation
+ * fails with HM_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Threading: one feeder thread per slot may call acquire/submit/collect for that slot; different slots
+ * may be driven from different threads.  Each slot owns a CUDA stream; H2D, kernels and D2H of different
+ * slots overlap.  Buffers handed out by acquire/collect stay valid until the next acquire of the slot.
+ */
+#ifndef HM_ENGINE_H
+#define HM_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HM_KMER 401            /* window, from the ONNX input shape [batch,401,8] (mod_main.cpp:41-57) */
+#define HM_FEATURES_PER_BASE 8
+#define HM_CTX_CPG 1
+#define HM_CTX_CHG 2
+#define HM_CTX_CHH 4
+
+typedef enum hm_status {
+    HM_OK = 0,
+    HM_ERR_ARG = -1,      /* bad argument / capacity exceeded */
+    HM_ERR_MODEL = -2,    /* model file missing or not the expected graph */
+    HM_ERR_CUDA = -3,     /* CUDA runtime error (message names the stage) */
+    HM_ERR_STATE = -4,    /* call sequence error (collect without submit, ...) */
+    HM_ERR_FORMAT = -5    /* malformed BAM record */
+} hm_status;
+
+/* CNN arithmetic.  TENSOR is the product path: bf16 split-precision (hi*hi + lo*hi + hi*lo, fp32
+ * accumulate) on tcgen05 tensor cores.  FP32_SIMT evaluates the same graph with fp32 FMAs on the CUDA
+ * cores; it exists as an on-device cross-check for the validation hooks, not as a fallback. */
+typedef enum hm_cnn_mode { HM_CNN_TENSOR = 0, HM_CNN_FP32_SIMT = 1 } hm_cnn_mode;
+
+typedef struct hm_config {
+    const char* model_dir;   /* directory holding CpG.onnx, CHG.onnx, CHH.onnx (-m) */
+    int32_t ctx_mask;        /* HM_CTX_* bits (-c); 0 means all three */
+    int32_t min_read_len;    /* -l, default 1000 (src/app/hifimeth/mod_options.cpp:10) */
+    int32_t device;          /* CUDA device ordinal */
+    int32_t n_slots;         /* staging slots, 1..4 (2 = double buffered) */
+    uint32_t max_reads;      /* capacity of one batch */
+    uint32_t max_bases;      /* capacity of one batch, sum of l_qseq (< 2^31) */
+    int32_t cnn_mode;        /* hm_cnn_mode */
+    int32_t keep_debug;      /* 1 = keep intermediates for the hm_debug_* hooks (costs memory) */
+} hm_config;
+
+/* Engine-owned PINNED staging buffers of one slot, struct-of-arrays.  The caller fills them
+ * (hm_pack_record does it from a BAM record) and then calls hm_batch_submit. */
+typedef struct hm_read_batch {
+    uint32_t max_reads, max_bases;
+    uint32_t* base_off;  /* [n_reads+1] prefix sum of l_qseq; base_off[0] = 0 */
+    uint32_t* seq_off;   /* [n_reads+1] byte offset of each read's packed SEQ in seq4 */
+    uint8_t* seq4;       /* packed 4-bit SEQ exactly as BAM stores it; capacity max_bases/2 + max_reads */
+    uint16_t* flag;      /* [n_reads] BAM flag (only 0x10 is looked at) */
+    uint8_t* valid;      /* [n_reads] 1 = call; 0 = pass through (short read / kinetics missing) */
+    uint8_t* fi;         /* [n_bases] CodecV1 codes, forward IPD, forward-read coordinates */
+    uint8_t* fp;         /* [n_bases] forward PW */
+    uint8_t* ri;         /* [n_bases] reverse IPD, reverse-strand coordinates */
+    uint8_t* rp;         /* [n_bases] reverse PW */
+} hm_read_batch;
+
+/* Result of one batch, in engine-owned pinned memory.  For read r the calls are
+ * [call_off[r], call_off[r+1]): first n_fwd[r] forward-strand calls (C on the read) with ascending qoff,
+ * then the reverse-strand calls (G on the read) with ascending qoff -- exactly the two arrays
+ * build_one_mod_bam takes.  qoff is in forward-strand coordinates of BamQuerySequence. */
+typedef struct hm_call_batch {
+    uint32_t n_reads;
+    uint32_t n_calls;
+    const uint32_t* call_off; /* [n_reads+1] */
+    const uint32_t* n_fwd;    /* [n_reads] */
+    const int32_t* qoff;      /* [n_calls] */
+    const uint8_t* ml;        /* [n_calls] scaled_prob = min(255,(int)(255*p1)) (mod_batch.cpp:46-64) */
+    uint64_t n_sites[3];      /* CpG, CHG, CHH samples in this batch (mod_main.cpp:364-407 statistics) */
+} hm_call_batch;
+
+/* Device-side timing of the last submit of a slot (CUDA events on the slot's stream). */
+typedef struct hm_timing {
+    float h2d_ms, decode_ms, scan_ms, cnn_ms, d2h_ms, total_ms;
+    uint64_t h2d_bytes, d2h_bytes;
+    uint32_t kernel_launches;   /* kernels of this library launched by the submit */
+    float top_kernel_ms;        /* summed duration of the dominant kernel family (CNN GEMM tiles) */
+    uint32_t top_kernel_launches;
+} hm_timing;
+
+#define HM_SUBMIT_SKIP_H2D 1u   /* inputs of this slot are already resident in HBM (re-run) */
+#define HM_SUBMIT_SKIP_D2H 2u   /* leave results on the device (kernel-only timing) */
+
+typedef struct hm_engine hm_engine;
+
+int hm_engine_create(const hm_config* cfg, hm_engine** out);
+void hm_engine_destroy(hm_engine* e);
+const char* hm_last_error(const hm_engine* e); /* e may be NULL: error of the last failed create */
+const char* hm_version(void);
+
+int hm_batch_acquire(hm_engine* e, int slot, hm_read_batch* out);
+int hm_batch_submit(hm_engine* e, int slot, uint32_t n_reads, uint32_t flags);
+int hm_batch_collect(hm_engine* e, int slot, hm_call_batch* out);
+int hm_batch_timing(hm_engine* e, int slot, hm_timing* out);
+
+/* ---- host helpers on the record path (A2 re-encode, record -> SoA, A8 tag construction) ---------------- */
+
+/* s_encode_signal_value, src/corelib/bam_info.cpp:455-478: raw frames (B:S tags) -> CodecV1 code. */
+uint8_t hm_codev1_encode(uint32_t frames);
+/* The decode table of src/corelib/bam_info.cpp:562-570. */
+uint16_t hm_codev1_decode(uint8_t code);
+
+/* Append one BAM alignment record body (SAMv1 s4.2 without block_size) to a staging batch at index
+ * *n_reads.  Applies the reference's acceptance rules: valid = l_seq >= min_read_len and fi, ri, fp, rp all
+ * present as B:C or B:S with count == l_seq (src/app/hifimeth/mod_main.cpp:189-196,
+ * src/corelib/bam_info.cpp:443-453).  Returns HM_ERR_ARG (and appends nothing) when the batch is full. */
+int hm_pack_record(hm_read_batch* b, uint32_t* n_reads, const uint8_t* body, size_t len, int32_t min_read_len);
+
+/* build_one_mod_bam, src/corelib/build_mod_bam.cpp:125-248, on a record body: strips fi/ri/fp/rp unless
+ * keep_kinetics, strips old ML/MM, appends MM:Z ML:B:C MN when there are calls.  out needs
+ * hm_mod_record_bound(len, n_calls) bytes.  Returns the new body length in *out_len. */
+size_t hm_mod_record_bound(size_t len, uint32_t n_calls);
+int hm_build_mod_record(const uint8_t* body, size_t len, int keep_kinetics, const int32_t* fwd_qoff,
+                        const uint8_t* fwd_ml, uint32_t n_fwd, const int32_t* rev_qoff, const uint8_t* rev_ml,
+                        uint32_t n_rev, uint8_t* out, size_t* out_len);
+
+/* ---- validation hooks (parity tests; need cfg.keep_debug = 1, call after hm_batch_collect) ------------ */
+
+/* Decoded kinetics as frames, u16, each [n_bases]: fi, fp in forward coordinates, ri, rp in reverse-strand
+ * coordinates (= BamKinetics::decoded_ipd/pw(strand, offset), src/corelib/bam_info.cpp:550-560), plus the
+ * two strands' base codes (A0 C1 G2 T3 N14, BamQuerySequence::fwd_qs / rev_qs). */
+int hm_debug_dump_decode(hm_engine* e, int slot, uint16_t* fi, uint16_t* fp, uint16_t* ri, uint16_t* rp,
+                         uint8_t* fwd_qs, uint8_t* rev_qs);
+/* Context (0 CpG, 1 CHG, 2 CHH) of every call, [n_calls], in hm_call_batch order. */
+int hm_debug_dump_ctx(hm_engine* e, int slot, uint8_t* ctx);
+/* Feature tensors [count][401][8] f32 of calls [first, first+count) in hm_call_batch order
+ * (s_extract_kmer_features, src/app/hifimeth/eval_kmer_features.cpp:9-65). */
+int hm_debug_dump_features(hm_engine* e, int slot, uint32_t first, uint32_t count, float* out);
+/* Logits [n_calls][2] f32 in hm_call_batch order. */
+int hm_debug_dump_logits(hm_engine* e, int slot, float* out);
+
+/* ---- kernel microbenchmarks (BASELINE.json config 5) --------------------------------------------------- */
+/* Runs one named kernel family `iters` times on the slot's resident inputs and returns the mean device
+ * time per launch (CUDA events) and the algorithmic bytes / flops one launch processes.
+ * name: "decode", "scan", "gather", "cnn". */
+int hm_microbench(hm_engine* e, int slot, const char* name, uint32_t n_sites, int iters, float* ms_per_launch,
+                  double* algo_bytes, double* algo_flops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HM_ENGINE_H */

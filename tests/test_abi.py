@@ -1,0 +1,113 @@
+"""CPU tests of the C-ABI library: it builds for sm_100a, loads, exports every symbol include/hm_engine.h
+declares, its host helpers agree with the oracle / golden vectors, and engine creation FAILS LOUDLY without a
+GPU (no CPU fallback).  No device compute is exercised here."""
+import ctypes as C
+import re
+
+import numpy as np
+import pytest
+
+from hifimeth_b200 import engine as hme
+from hifimeth_b200 import synth
+from oracle import hmoracle
+from oracle.make_golden import golden_bodies, golden_reads
+
+from conftest import ROOT
+
+
+def _declared_functions():
+    text = (ROOT / "include" / "hm_engine.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(hm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib_built):
+    lib = hme.load_library()
+    declared = _declared_functions()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/hm_engine.h but not exported"
+    assert sorted(hme.ABI_SYMBOLS) == declared
+    assert b"sm_100a" in lib.hm_version()
+
+
+def test_library_is_sm100a_only(lib_built):
+    import subprocess
+
+    out = subprocess.run(["cuobjdump", "-lelf", str(hme.LIB_PATH)], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_engine_create_fails_loudly_without_gpu(lib_built):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(hme.HmError) as ei:
+        hme.Engine(max_reads=4, max_bases=1 << 16)
+    assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_codev1_helpers(lib_built):
+    lib = hme.load_library()
+    lut = synth.codev1_decode_table()
+    for c in range(256):
+        assert lib.hm_codev1_decode(c) == lut[c]
+    O = hmoracle.oracle()
+    for s in list(range(0, 1100)) + [5000, 65535]:
+        assert lib.hm_codev1_encode(s) == O.lib.hmo_codev1_encode(s)
+
+
+def test_pack_record_matches_soa_and_acceptance_rules(lib_built):
+    reads = golden_reads()
+    bodies = golden_bodies(reads)
+    packed = hme.pack_records_host(bodies, min_read_len=1000)
+    want = synth.soa_from_reads(reads, min_read_len=1000)
+    assert packed.n_reads == want.n_reads
+    assert (packed.base_off == want.base_off).all() and (packed.seq_off == want.seq_off).all()
+    assert (packed.seq4 == want.seq4).all() and (packed.flag == want.flag).all()
+    # read 5 lacks rp, read 6 is shorter than -l: both passed through (src/app/hifimeth/mod_main.cpp:189-196)
+    assert list(packed.valid) == [1, 1, 1, 1, 1, 0, 0, 1]
+    assert (packed.valid == want.valid).all()
+    for r in range(want.n_reads):
+        if not want.valid[r]:
+            continue
+        a, b = int(want.base_off[r]), int(want.base_off[r + 1])
+        for k in ("fi", "fp", "ri", "rp"):  # read 1 carries B:S raw frames that must re-encode to the same codes
+            assert (getattr(packed, k)[a:b] == getattr(want, k)[a:b]).all(), (r, k)
+
+
+def test_pack_record_rejects_overflow_and_garbage(lib_built):
+    reads = golden_reads()
+    body = golden_bodies(reads)[0]
+    with pytest.raises(hme.HmError):
+        hme.pack_records_host([body, body], max_bases=len(reads[0]["seq"]) + 10)
+    lib = hme.load_library()
+    b = hme.hm_read_batch()
+    n = C.c_uint32(0)
+    junk = np.zeros(8, np.uint8)
+    assert lib.hm_pack_record(C.byref(b), C.byref(n), junk.ctypes.data_as(C.POINTER(C.c_uint8)), 8, 1000) != 0
+
+
+def test_build_mod_record_vs_golden(lib_built, golden):
+    for i in range(int(golden["n_reads"])):
+        body = golden[f"body{i}"].tobytes()
+        if not golden[f"ok{i}"]:
+            assert hme.build_mod_record(body, False, [], [], [], []) == golden[f"mod{i}"].tobytes()
+            continue
+        fq, rq, fml, rml = (golden[f"{k}{i}"] for k in ("fq", "rq", "fml", "rml"))
+        assert hme.build_mod_record(body, False, fq, fml, rq, rml) == golden[f"mod{i}"].tobytes()
+        assert hme.build_mod_record(body, True, fq, fml, rq, rml) == golden[f"modkeep{i}"].tobytes()
+
+
+def test_build_mod_record_rejects_bad_calls(lib_built, golden):
+    body = golden["body0"].tobytes()
+    fq = golden["fq0"]
+    bad = fq.copy()
+    bad[1], bad[0] = fq[0], fq[1]  # not ascending: the reference aborts (build_mod_bam.cpp:138), we return an error
+    with pytest.raises(hme.HmError):
+        hme.build_mod_record(body, False, bad, np.zeros(len(bad), np.uint8), [], [])
+    with pytest.raises(hme.HmError):
+        not_c = int(np.nonzero(golden["fwd0"] != 1)[0][0])  # a call on a base that is not C (build_mod_bam.cpp:139-140)
+        hme.build_mod_record(body, False, [not_c], [1], [], [])
