@@ -1,14 +1,712 @@
-// cnn_tensor.cu -- tensor-core CNN path (placeholder until the tcgen05 kernels land in this file).
+// cnn_tensor.cu -- tensor-core CNN path: the dilated dense plan, its packed weights, and the batch orchestration.
+//
+// Network (training/model_cnn.py:31-85 as exported in models/*.onnx): bn0 -> 8 x (conv1d stride 2, pad 1, +bias, ReLU)
+// -> flatten -> fc1 + ReLU -> fc2.  The reference runs it once per site on a [401,8] window
+// (src/app/hifimeth/mod_batch.cpp:66-75).  Windows of neighbouring sites overlap almost completely, so here every
+// layer is evaluated ONCE per strand position as a dilated convolution over the whole read ("track"):
+//
+//     Y_l[i] = relu(b_l + sum_j W_l[j] . Y_{l-1}[i + j * 2^(l-1)])          l = 1..6,  Y_0 = X (raw features)
+//
+// Output v of layer l of the site whose window starts at row s + 1 (s = o - 201, o = the site's strand offset) is
+// Y_l[s + v * 2^l - (2^l - 2)], except the first and last output of each layer, which see the zero padding.  Those
+// depend on s alone and are dense maps as well (F_l, G_l); layers 7, 8 and the FC head are evaluated per row s
+// (T7_v, T8_w, head).  bn0 is folded into conv1; the pad columns bn0 never touches are corrected in F_1 / G_1.
+// tests/dense_emulator.py restates this plan in numpy and checks it against the per-site oracle (max |dlogit| 4e-6).
+//
+// Every op of the plan is one launch of dense_gemm_kernel.  Tracks of a batch are processed in sub-batches that fit
+// the activation workspace; the final logits of all rows of a batch are kept (8 B/row) and a lookup kernel turns
+// them into per-site logits + ML bytes in hm_call_batch order.
 #include "cnn_tensor.cuh"
 
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <string>
+#include <vector>
+
+#include "dense_gemm.cuh"
+#include "postprocess.cuh"
 
 namespace hm {
-namespace { std::string g_err = "tensor-core CNN path not built yet"; }
+namespace {
+
+std::string g_err = "";
+int tfail(const std::string& s) { g_err = s; return -1; }
+#define TCUDA(stage, call)                                                                   \
+    do {                                                                                     \
+        cudaError_t _st = (call);                                                            \
+        if (_st != cudaSuccess) return tfail(std::string(stage) + ": " + cudaGetErrorString(_st)); \
+    } while (0)
+
+constexpr int kHaloL = 208;   // rows before strand position 0 (>= 201, multiple of 16)
+constexpr int kHaloR = 200;   // zero-feature rows after the last strand position
+constexpr int kSlackRows = 1024;  // rows past the sub-batch every plane keeps allocated (shifted reads of the last tile)
+constexpr size_t kSmemMax = 232448;
+
+enum MapId { MAP_X = 0, MAP_Y = 1, MAP_F = 7, MAP_G = 13, MAP_T7 = 19, MAP_T8 = 23, N_MAPS = 25 };
+const int kLayerCout[6] = {128, 128, 128, 96, 96, 96};
+
+int map_channels(int id)
+{
+    if (id == MAP_X) return 8;
+    if (id < MAP_F) return kLayerCout[id - MAP_Y];
+    if (id < MAP_G) return kLayerCout[id - MAP_F];
+    if (id < MAP_T7) return kLayerCout[id - MAP_G];
+    return 64;
+}
+
+// ---- host plan ---------------------------------------------------------------------------------------------------
+struct HostTerm {
+    int src = 0, shift = 0;
+    std::vector<float> w;  // [cin][cout]; conv1 form: [taps][8][cout]
+};
+struct HostOp {
+    int out = -1;
+    int cin = 0, cout = 0;
+    std::vector<float> bias;
+    std::vector<HostTerm> terms;
+    int conv1_taps = 0;  // > 0: conv1 form (one term, weights [taps][8][cout], rows shift .. shift + taps - 1)
+    bool head = false;
+    std::vector<float> w2, b2;
+};
+
+uint16_t f2bf(float f)
+{
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+float bf2f(uint16_t h)
+{
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+bool build_plan(const CnnModel& m, std::vector<HostOp>& ops, std::string& err)
+{
+    if (m.features != 8 || m.kmer != 401 || m.convs.size() != 8) { err = "unsupported model geometry"; return false; }
+    const int k1 = m.convs[0].k;
+    int lens[9];
+    lens[0] = 401;
+    for (int l = 0; l < 8; ++l) lens[l + 1] = (lens[l] + 2 - m.convs[l].k) / 2 + 1;
+    if (lens[8] != 2 || 2 * (lens[1] - 1) + k1 - 1 != 402) { err = "unsupported conv geometry"; return false; }
+    for (int l = 0; l < 6; ++l)
+        if (m.convs[l].cout != kLayerCout[l]) { err = "unsupported channel counts"; return false; }
+    if (m.convs[6].cout != 64 || m.convs[7].cout != 64 || m.fc1_in != 128 || m.fc1_out != 256) { err = "unsupported head"; return false; }
+
+    double scale[8], shift[8];
+    for (int c = 0; c < 8; ++c) {
+        scale[c] = (double)m.bn_w[c] / std::sqrt((double)m.bn_var[c] + (double)m.bn_eps);
+        shift[c] = (double)m.bn_b[c] - (double)m.bn_mean[c] * scale[c];
+    }
+    // ---- layer 1 (conv1 form; bn0 folded) ----------------------------------------------------------------------
+    const ConvLayer& c1 = m.convs[0];
+    auto w1 = [&](int o, int c, int j) { return (double)c1.w[((size_t)o * 8 + c) * k1 + j]; };
+    std::vector<double> b1f(128);
+    for (int o = 0; o < 128; ++o) {
+        double s = c1.b[o];
+        for (int c = 0; c < 8; ++c)
+            for (int j = 0; j < k1; ++j) s += w1(o, c, j) * shift[c];
+        b1f[o] = s;
+    }
+    auto conv1_op = [&](int out, int base_shift, int skip_tap) {
+        HostOp op;
+        op.out = out; op.cin = 8; op.cout = 128; op.conv1_taps = k1;
+        op.bias.resize(128);
+        HostTerm t;
+        t.src = MAP_X; t.shift = base_shift;
+        t.w.assign((size_t)k1 * 8 * 128, 0.f);
+        for (int o = 0; o < 128; ++o) {
+            double b = b1f[o];
+            for (int c = 0; c < 8; ++c) {
+                for (int j = 0; j < k1; ++j)
+                    if (j != skip_tap) t.w[((size_t)j * 8 + c) * 128 + o] = (float)(w1(o, c, j) * scale[c]);
+                // the skipped tap is a conv zero-pad column: bn0 never saw it, so its folded shift goes away too
+                if (skip_tap >= 0) b -= w1(o, c, skip_tap) * shift[c];
+            }
+            op.bias[o] = (float)b;
+        }
+        op.terms.push_back(std::move(t));
+        ops.push_back(std::move(op));
+    };
+    conv1_op(MAP_Y + 0, 0, -1);
+    conv1_op(MAP_F + 0, 0, 0);
+    conv1_op(MAP_G + 0, 2 * (lens[1] - 1), k1 - 1);
+
+    auto off = [](int l) { return -((1 << l) - 2); };
+    // site-level element q of layer l's output -> (map, shift) relative to row s; false = zero pad
+    auto src = [&](int l, int q, int& map, int& sh) {
+        const int n = lens[l];
+        if (q < 0 || q >= n) return false;
+        if (l <= 6) {
+            if (q == 0) { map = MAP_F + l - 1; sh = 0; }
+            else if (q == n - 1) { map = MAP_G + l - 1; sh = 0; }
+            else { map = MAP_Y + l - 1; sh = off(l) + q * (1 << l); }
+        } else { map = MAP_T7 + q; sh = 0; }
+        return true;
+    };
+    for (int l = 2; l <= 8; ++l) {
+        const ConvLayer& cv = m.convs[l - 1];
+        if (cv.k != 3) { err = "unsupported kernel size"; return false; }
+        auto tap = [&](int j) {
+            std::vector<float> w((size_t)cv.cin * cv.cout);
+            for (int o = 0; o < cv.cout; ++o)
+                for (int c = 0; c < cv.cin; ++c) w[(size_t)c * cv.cout + o] = cv.w[((size_t)o * cv.cin + c) * 3 + j];
+            return w;
+        };
+        auto new_op = [&](int out) {
+            HostOp op;
+            op.out = out; op.cin = cv.cin; op.cout = cv.cout; op.bias = cv.b;
+            return op;
+        };
+        std::vector<std::pair<int, int>> outs;  // (map, site-level output index)
+        if (l <= 6) {
+            HostOp op = new_op(MAP_Y + l - 1);
+            for (int j = 0; j < 3; ++j) {
+                HostTerm t; t.src = MAP_Y + l - 2; t.shift = j * (1 << (l - 1)); t.w = tap(j);
+                op.terms.push_back(std::move(t));
+            }
+            ops.push_back(std::move(op));
+            outs = {{MAP_F + l - 1, 0}, {MAP_G + l - 1, lens[l] - 1}};
+        } else {
+            for (int v = 0; v < lens[l]; ++v) outs.push_back({(l == 7 ? MAP_T7 : MAP_T8) + v, v});
+        }
+        for (auto& ov : outs) {
+            HostOp op = new_op(ov.first);
+            for (int j = 0; j < 3; ++j) {
+                int mp, sh;
+                if (!src(l - 1, 2 * ov.second - 1 + j, mp, sh)) continue;
+                if (sh < 0) { err = "negative shift in plan"; return false; }
+                HostTerm t; t.src = mp; t.shift = sh; t.w = tap(j);
+                op.terms.push_back(std::move(t));
+            }
+            ops.push_back(std::move(op));
+        }
+    }
+    // ---- head: flatten index = c * 2 + t; fc1 + ReLU on the tensor cores, fc2 in the epilogue ---------------------
+    HostOp h;
+    h.head = true; h.cin = 64; h.cout = 256; h.bias = m.fc1_b; h.w2 = m.fc2_w; h.b2 = m.fc2_b;
+    for (int t = 0; t < 2; ++t) {
+        HostTerm tm; tm.src = MAP_T8 + t; tm.shift = 0;
+        tm.w.resize((size_t)64 * 256);
+        for (int o = 0; o < 256; ++o)
+            for (int c = 0; c < 64; ++c) tm.w[(size_t)c * 256 + o] = m.fc1_w[(size_t)o * 128 + c * 2 + t];
+        h.terms.push_back(std::move(tm));
+    }
+    ops.push_back(std::move(h));
+    return true;
+}
+
+// ---- device op: DenseOp template + the map ids its pointers are patched from ---------------------------------------
+struct DevOp {
+    DenseOp p{};
+    int seg_map[kMaxSegs] = {0, 0, 0};
+    int out_map = -1;
+    size_t smem = 0;
+    size_t w_off = 0, bias_off = 0, w2_off = 0, b2_off = 0;  // offsets into the model blob
+    double macs_per_row = 0;  // executed MACs per output row, one precision pass
+};
+
+bool lower_op(const HostOp& h, DevOp& d, std::vector<uint8_t>& blob, std::string& err)
+{
+    DenseOp& p = d.p;
+    const int n = h.cout;
+    if (n % 16 || n > 256 || h.terms.empty() || (int)h.terms.size() > kMaxTerms) { err = "op shape not supported"; return false; }
+    p.n = n;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < (uint32_t)(2 * n)) p.tmem_cols <<= 1;
+    p.n_terms = (int)h.terms.size();
+    p.mode = h.head ? 1 : 0;
+    d.out_map = h.out;
+    uint32_t stage = 0;
+    if (h.conv1_taps > 0) {
+        p.n_segs = 1; p.n_stages = 1; p.ksteps = (h.conv1_taps + 1) / 2; p.a_q_off = 32; p.planes_per_seg = 2;
+        DenseSeg& sg = p.seg[0];
+        sg.row_off = h.terms[0].shift; sg.nrows = kTileRows + 16; sg.groups = 1; sg.smem_off = 0;
+        d.seg_map[0] = h.terms[0].src;
+        p.term[0] = DenseTerm{0u, sg.nrows * 16u, 16u};
+        stage = 2 * sg.nrows * 16u;
+        d.macs_per_row = (double)p.ksteps * 16 * n;
+    } else {
+        if (h.cin % 16) { err = "cin must be a multiple of 16"; return false; }
+        p.n_stages = h.cin / 16; p.ksteps = 1; p.a_q_off = 0; p.planes_per_seg = 4; p.n_segs = 0;
+        for (size_t k = 0; k < h.terms.size(); ++k) {
+            int s = -1;
+            for (int i = 0; i < p.n_segs; ++i)
+                if (d.seg_map[i] == h.terms[k].src) s = i;
+            if (s < 0) {
+                if (p.n_segs == kMaxSegs) { err = "too many segments"; return false; }
+                s = p.n_segs++;
+                d.seg_map[s] = h.terms[k].src;
+                p.seg[s].row_off = h.terms[k].shift;
+                p.seg[s].nrows = 0;  // holds max shift until finalised
+                p.seg[s].groups = (uint32_t)h.cin / 8;
+            }
+            p.seg[s].row_off = std::min(p.seg[s].row_off, h.terms[k].shift);
+            p.seg[s].nrows = std::max<uint32_t>(p.seg[s].nrows, (uint32_t)h.terms[k].shift);
+        }
+        for (int s = 0; s < p.n_segs; ++s) {
+            p.seg[s].nrows = kTileRows + (p.seg[s].nrows - (uint32_t)p.seg[s].row_off);
+            p.seg[s].smem_off = stage;
+            stage += 4 * p.seg[s].nrows * 16u;
+        }
+        for (size_t k = 0; k < h.terms.size(); ++k) {
+            int s = 0;
+            for (int i = 0; i < p.n_segs; ++i)
+                if (d.seg_map[i] == h.terms[k].src) s = i;
+            const uint32_t pl = p.seg[s].nrows * 16u;
+            p.term[k] = DenseTerm{p.seg[s].smem_off + (uint32_t)(h.terms[k].shift - p.seg[s].row_off) * 16u, 2 * pl, pl};
+        }
+        d.macs_per_row = (double)h.cin * n * h.terms.size();
+    }
+    p.stage_bytes = (stage + 127u) & ~127u;
+    // ---- weight image: tiles [stage][kstep][term][hl], each [2][n][8] bf16 ------------------------------------------
+    const uint32_t tile_elems = 2u * n * 8u;
+    const size_t n_tiles = (size_t)p.n_stages * p.ksteps * p.n_terms * 2;
+    std::vector<uint16_t> img(n_tiles * tile_elems, 0);
+    for (int st = 0; st < p.n_stages; ++st)
+        for (int q = 0; q < p.ksteps; ++q)
+            for (int k = 0; k < p.n_terms; ++k) {
+                uint16_t* hi = &img[(((size_t)(st * p.ksteps + q) * p.n_terms + k) * 2) * tile_elems];
+                uint16_t* lo = hi + tile_elems;
+                for (int c = 0; c < 2; ++c)
+                    for (int o = 0; o < n; ++o)
+                        for (int e = 0; e < 8; ++e) {
+                            float w = 0.f;
+                            if (h.conv1_taps > 0) {
+                                int tap = 2 * q + c;
+                                if (tap < h.conv1_taps) w = h.terms[0].w[((size_t)tap * 8 + e) * n + o];
+                            } else {
+                                w = h.terms[k].w[(size_t)(16 * st + 8 * c + e) * n + o];
+                            }
+                            uint16_t wh = f2bf(w);
+                            hi[((size_t)c * n + o) * 8 + e] = wh;
+                            lo[((size_t)c * n + o) * 8 + e] = f2bf(w - bf2f(wh));
+                        }
+            }
+    p.w_bytes = (uint32_t)(img.size() * 2);
+    const size_t w_al = (p.w_bytes + 127u) & ~127u;
+    if (w_al + 2 * (size_t)p.stage_bytes + 256 > kSmemMax) { err = "op does not fit shared memory"; return false; }
+    p.ring = (int)std::min<size_t>(8, (kSmemMax - 256 - w_al) / p.stage_bytes);
+    d.smem = dense_smem_bytes(p);
+    auto append = [&](const void* src, size_t bytes) {
+        size_t o = (blob.size() + 255) & ~(size_t)255;
+        blob.resize(o + bytes);
+        memcpy(blob.data() + o, src, bytes);
+        return o;
+    };
+    d.w_off = append(img.data(), img.size() * 2);
+    d.bias_off = append(h.bias.data(), h.bias.size() * 4);
+    if (h.head) {
+        d.w2_off = append(h.w2.data(), h.w2.size() * 4);
+        d.b2_off = append(h.b2.data(), h.b2.size() * 4);
+    }
+    return true;
+}
+
+void bind_blob(DevOp& d, const uint8_t* blob)
+{
+    d.p.w_img = blob + d.w_off;
+    d.p.bias = reinterpret_cast<const float*>(blob + d.bias_off);
+    if (d.p.mode == 1) {
+        d.p.w2 = reinterpret_cast<const float*>(blob + d.w2_off);
+        d.p.b2 = reinterpret_cast<const float*>(blob + d.b2_off);
+    }
+}
+
+bool g_attr_set = false;
+int ensure_kernel_attr()
+{
+    if (g_attr_set) return 0;
+    TCUDA("dense kernel attribute", cudaFuncSetAttribute(dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    g_attr_set = true;
+    return 0;
+}
+
+// ---- small kernels around the plan ------------------------------------------------------------------------------------
+
+// X map of one sub-batch: one block per 128-row tile.  Row of track position i holds the 8 features of
+// s_extract_kmer_features (src/app/hifimeth/eval_kmer_features.cpp:42-64) for that strand position, split hi/lo.
+__global__ void __launch_bounds__(128)
+track_features_kernel(const uint8_t* __restrict__ bcode, const ushort4* __restrict__ kinf, const uint32_t* __restrict__ base_off,
+                      const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_first, uint32_t gtile0,
+                      uint8_t* __restrict__ x_hi, uint8_t* __restrict__ x_lo)
+{
+    const uint32_t gt = gtile0 + blockIdx.x;
+    const uint32_t rs = tile_read[gt];
+    const uint32_t r = rs & 0x7fffffffu;
+    const bool rev = (rs >> 31) != 0;
+    const uint32_t B = base_off[r];
+    const int L = (int)(base_off[r + 1] - B);
+    const int i = (int)((gt - tile_first[gt]) * kTileRows + threadIdx.x) - kHaloL;
+    uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+    if (i >= 0 && i < L) {
+        const int p = rev ? L - 1 - i : i;
+        uint32_t c = bcode[B + p];
+        if (rev && c < 4) c = 3u - c;
+        const ushort4 k = kinf[B + p];
+        const float f0 = __fdiv_rn((float)k.x, 952.0f), f1 = __fdiv_rn((float)k.y, 952.0f);
+        const float f2 = __fdiv_rn((float)k.z, 952.0f), f3 = __fdiv_rn((float)k.w, 952.0f);
+        const float own_i = rev ? f2 : f0, own_p = rev ? f3 : f1, opp_i = rev ? f0 : f2, opp_p = rev ? f1 : f3;
+        const uint32_t one = 0x3f80u;  // bf16 1.0
+        hi.x = (c == 0 ? one : 0u) | ((c == 1 ? one : 0u) << 16);
+        hi.y = (c == 2 ? one : 0u) | ((c == 3 ? one : 0u) << 16);
+        __nv_bfloat16 h0 = __float2bfloat16_rn(own_i), h1 = __float2bfloat16_rn(own_p);
+        __nv_bfloat16 h2 = __float2bfloat16_rn(opp_i), h3 = __float2bfloat16_rn(opp_p);
+        hi.z = pack_bf16x2(h0, h1);
+        hi.w = pack_bf16x2(h2, h3);
+        lo.z = pack_bf16x2(__float2bfloat16_rn(own_i - __bfloat162float(h0)), __float2bfloat16_rn(own_p - __bfloat162float(h1)));
+        lo.w = pack_bf16x2(__float2bfloat16_rn(opp_i - __bfloat162float(h2)), __float2bfloat16_rn(opp_p - __bfloat162float(h3)));
+    }
+    const size_t row = (size_t)blockIdx.x * kTileRows + threadIdx.x;
+    reinterpret_cast<uint4*>(x_hi)[row] = hi;
+    reinterpret_cast<uint4*>(x_lo)[row] = lo;
+}
+
+// Per-site lookup of one class region: row (o - 201) of the site's track -> logits, probability, ML byte
+// (s_logits_to_methy_probs, src/app/hifimeth/mod_batch.cpp:46-64).
+__global__ void __launch_bounds__(256)
+site_lookup_kernel(const float2* __restrict__ logit_rows, const uint32_t* __restrict__ track_row_fwd,
+                   const uint32_t* __restrict__ track_row_rev, const uint32_t* __restrict__ base_off,
+                   const uint32_t* __restrict__ site_read, const uint32_t* __restrict__ site_pos,
+                   const uint32_t* __restrict__ site_out, uint32_t first, uint32_t count, float* __restrict__ logits,
+                   uint8_t* __restrict__ ml)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const uint32_t r = site_read[first + k];
+    const uint32_t sp = site_pos[first + k];
+    const bool rev = (sp >> 31) != 0;
+    const int p = (int)(sp & 0x7fffffffu);
+    const int L = (int)(base_off[r + 1] - base_off[r]);
+    const int o = rev ? L - 1 - p : p;
+    const size_t row = (size_t)(rev ? track_row_rev[r] : track_row_fwd[r]) + (size_t)(kHaloL + o - 201);
+    const float2 lg = logit_rows[row];
+    const uint32_t out = site_out[first + k];
+    logits[2 * (size_t)out] = lg.x;
+    logits[2 * (size_t)out + 1] = lg.y;
+    ml[out] = prob_to_ml(softmax_p1(lg.x, lg.y));
+}
+
+}  // namespace
+
+// ---- model ---------------------------------------------------------------------------------------------------------------
+struct TensorModel {
+    std::vector<DevOp> ops;
+    uint8_t* d_blob = nullptr;
+    double macs_per_row = 0;  // executed, one precision pass, all ops
+};
+
 const char* tensor_last_error() { return g_err.c_str(); }
-int tensor_model_build(TensorModelHandle&, const CnnModel&) { return -1; }
-void tensor_model_free(TensorModelHandle&) {}
-int tensor_workspace_alloc(TensorWorkspace&, uint32_t, uint32_t) { return -1; }
-void tensor_workspace_free(TensorWorkspace&) {}
-int tensor_cnn_run(const TensorModelHandle&, TensorWorkspace&, const TensorInputs&, uint32_t, uint32_t, cudaStream_t, uint32_t*, hm_timing*) { return -1; }
+
+int tensor_model_build(TensorModelHandle& m, const CnnModel& host)
+{
+    std::vector<HostOp> plan;
+    std::string err;
+    if (!build_plan(host, plan, err)) return tfail("dense plan: " + err);
+    TensorModel* t = new TensorModel();
+    std::vector<uint8_t> blob;
+    for (const HostOp& h : plan) {
+        DevOp d;
+        if (!lower_op(h, d, blob, err)) { delete t; return tfail("dense plan lowering: " + err); }
+        t->macs_per_row += d.macs_per_row;
+        t->ops.push_back(d);
+    }
+    cudaError_t st = cudaMalloc((void**)&t->d_blob, blob.size());
+    if (st == cudaSuccess) st = cudaMemcpy(t->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+    if (st != cudaSuccess) { cudaFree(t->d_blob); delete t; return tfail(std::string("weight upload: ") + cudaGetErrorString(st)); }
+    for (DevOp& d : t->ops) bind_blob(d, t->d_blob);
+    m.p = t;
+    return ensure_kernel_attr();
+}
+
+void tensor_model_free(TensorModelHandle& m)
+{
+    if (!m.p) return;
+    cudaFree(m.p->d_blob);
+    delete m.p;
+    m.p = nullptr;
+}
+
+// ---- workspace ---------------------------------------------------------------------------------------------------------------
+struct TensorWorkspaceImpl {
+    uint32_t rows_cap = 0;            // dense rows of one sub-batch
+    unsigned long long plane_stride = 0;
+    uint8_t* d_maps = nullptr;
+    uint8_t* map[N_MAPS] = {};
+    size_t logit_rows_cap = 0;
+    float* d_logit[3] = {};
+    uint32_t tiles_cap = 0, reads_cap = 0;
+    uint32_t *h_tile_read = nullptr, *h_tile_first = nullptr, *d_tile_read = nullptr, *d_tile_first = nullptr;
+    uint32_t *h_track_row = nullptr, *d_track_row = nullptr;  // [2][reads_cap]
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+int tensor_workspace_alloc(TensorWorkspace& w, uint32_t max_bases, uint32_t max_reads, uint32_t max_rows)
+{
+    TensorWorkspaceImpl* s = new TensorWorkspaceImpl();
+    w.impl = s;
+    const size_t total_rows = 2 * (size_t)max_bases + (size_t)1070 * max_reads + 256;  // every track: L + 408 rounded up to 128, x2
+    size_t cap = max_rows;
+    if (!cap) {
+        const char* env = getenv("HM_DENSE_ROWS");
+        cap = env ? (size_t)atoll(env) : ((size_t)1 << 19);
+    }
+    cap = std::min(cap, total_rows);
+    cap = ((cap + kTileRows - 1) / kTileRows) * kTileRows;
+    s->rows_cap = (uint32_t)cap;
+    s->plane_stride = (unsigned long long)(cap + kSlackRows) * 16ull;
+    size_t planes = 0;
+    for (int i = 0; i < N_MAPS; ++i) planes += 2 * (size_t)map_channels(i) / 8;
+    const size_t bytes = planes * s->plane_stride;
+    TCUDA("activation workspace", cudaMalloc((void**)&s->d_maps, bytes));
+    TCUDA("activation workspace", cudaMemset(s->d_maps, 0, bytes));
+    size_t pl = 0;
+    for (int i = 0; i < N_MAPS; ++i) {
+        s->map[i] = s->d_maps + pl * s->plane_stride;
+        pl += 2 * (size_t)map_channels(i) / 8;
+    }
+    s->logit_rows_cap = total_rows;
+    for (int c = 0; c < 3; ++c) TCUDA("logit rows", cudaMalloc((void**)&s->d_logit[c], total_rows * 2 * sizeof(float)));
+    s->tiles_cap = (uint32_t)(total_rows / kTileRows + 1);
+    s->reads_cap = max_reads;
+    TCUDA("track tables", cudaMallocHost((void**)&s->h_tile_read, (size_t)s->tiles_cap * 4));
+    TCUDA("track tables", cudaMallocHost((void**)&s->h_tile_first, (size_t)s->tiles_cap * 4));
+    TCUDA("track tables", cudaMalloc((void**)&s->d_tile_read, (size_t)s->tiles_cap * 4));
+    TCUDA("track tables", cudaMalloc((void**)&s->d_tile_first, (size_t)s->tiles_cap * 4));
+    TCUDA("track tables", cudaMallocHost((void**)&s->h_track_row, (size_t)2 * std::max(max_reads, 1u) * 4));
+    TCUDA("track tables", cudaMalloc((void**)&s->d_track_row, (size_t)2 * std::max(max_reads, 1u) * 4));
+    TCUDA("events", cudaEventCreate(&s->ev0));
+    TCUDA("events", cudaEventCreate(&s->ev1));
+    return 0;
+}
+
+void tensor_workspace_free(TensorWorkspace& w)
+{
+    TensorWorkspaceImpl* s = w.impl;
+    if (!s) return;
+    cudaFree(s->d_maps);
+    for (float* p : s->d_logit) cudaFree(p);
+    cudaFreeHost(s->h_tile_read); cudaFreeHost(s->h_tile_first); cudaFree(s->d_tile_read); cudaFree(s->d_tile_first);
+    cudaFreeHost(s->h_track_row); cudaFree(s->d_track_row);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    delete s;
+    w.impl = nullptr;
+}
+
+namespace {
+
+int launch_op(const DevOp& d, const TensorWorkspaceImpl& s, uint32_t n_tiles, float* logit_out, int sm_count, cudaStream_t stream)
+{
+    DenseOp p = d.p;
+    for (int i = 0; i < p.n_segs; ++i) {
+        p.seg[i].src = s.map[d.seg_map[i]];
+        p.seg[i].plane_stride = s.plane_stride;
+    }
+    p.n_tiles = n_tiles;
+    if (p.mode == 0) {
+        p.out = s.map[d.out_map];
+        p.out_plane_stride = s.plane_stride;
+    } else {
+        p.logits = logit_out;
+    }
+    const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)sm_count);
+    dense_gemm_kernel<<<grid, kDenseThreads, d.smem, stream>>>(p);
+    return 0;
+}
+
+struct SubBatch {
+    uint32_t gtile0, fwd_tiles, tiles;
+};
+
+}  // namespace
+
+int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorWorkspace& w, const TensorBatch& b, cudaStream_t stream,
+                     int sm_count, uint32_t* launches, hm_timing* timing)
+{
+    TensorWorkspaceImpl* s = w.impl;
+    if (!s) return tfail("tensor workspace not allocated");
+    if (b.n_reads > s->reads_cap) return tfail("batch exceeds the workspace read capacity");
+    const bool want_rev = (ctx_mask & 4u) != 0;
+    // ---- tracks -> sub-batches: [forward tracks | reverse tracks] per sub-batch ---------------------------------------------
+    std::vector<SubBatch> subs;
+    uint32_t* trk_f = s->h_track_row;
+    uint32_t* trk_r = s->h_track_row + s->reads_cap;
+    uint32_t gtile = 0;
+    uint32_t r = 0;
+    while (r < b.n_reads) {
+        uint32_t r1 = r, rows = 0;
+        while (r1 < b.n_reads) {
+            if (b.h_valid[r1]) {
+                const uint32_t L = b.h_base_off[r1 + 1] - b.h_base_off[r1];
+                const uint32_t tr = ((L + kHaloL + kHaloR + kTileRows - 1) / kTileRows) * kTileRows;
+                const uint32_t need = tr * (want_rev ? 2u : 1u);
+                if (need > s->rows_cap) return tfail("a read is longer than the dense workspace (raise HM_DENSE_ROWS)");
+                if (rows + need > s->rows_cap) break;
+                rows += need;
+            }
+            ++r1;
+        }
+        if (rows) {
+            SubBatch sb{gtile, 0, 0};
+            for (int strand = 0; strand < (want_rev ? 2 : 1); ++strand) {
+                for (uint32_t q = r; q < r1; ++q) {
+                    if (!b.h_valid[q]) continue;
+                    const uint32_t L = b.h_base_off[q + 1] - b.h_base_off[q];
+                    const uint32_t nt = (L + kHaloL + kHaloR + kTileRows - 1) / kTileRows;
+                    if (gtile + nt > s->tiles_cap) return tfail("internal: tile table overflow");
+                    (strand ? trk_r : trk_f)[q] = gtile * kTileRows;
+                    for (uint32_t t = 0; t < nt; ++t) {
+                        s->h_tile_read[gtile + t] = q | ((uint32_t)strand << 31);
+                        s->h_tile_first[gtile + t] = gtile;
+                    }
+                    gtile += nt;
+                }
+                if (strand == 0) sb.fwd_tiles = gtile - sb.gtile0;
+            }
+            sb.tiles = gtile - sb.gtile0;
+            subs.push_back(sb);
+        }
+        r = r1;
+    }
+    if (gtile) {
+        TCUDA("track tables", cudaMemcpyAsync(s->d_tile_read, s->h_tile_read, (size_t)gtile * 4, cudaMemcpyHostToDevice, stream));
+        TCUDA("track tables", cudaMemcpyAsync(s->d_tile_first, s->h_tile_first, (size_t)gtile * 4, cudaMemcpyHostToDevice, stream));
+        TCUDA("track tables", cudaMemcpyAsync(s->d_track_row, s->h_track_row, (size_t)2 * s->reads_cap * 4, cudaMemcpyHostToDevice, stream));
+    }
+    // ---- the plan, sub-batch by sub-batch -------------------------------------------------------------------------------------
+    TCUDA("dense plan", cudaEventRecord(s->ev0, stream));
+    uint32_t dense_launches = 0;
+    for (const SubBatch& sb : subs) {
+        track_features_kernel<<<sb.tiles, 128, 0, stream>>>(b.d_bcode, b.d_kinf, b.d_base_off, s->d_tile_read, s->d_tile_first, sb.gtile0,
+                                                          s->map[MAP_X], s->map[MAP_X] + s->plane_stride);
+        ++*launches;
+        for (int c = 0; c < 3; ++c) {
+            const uint32_t n_sites_c = b.class_count[c] + (c == 2 ? b.class_count[3] : 0u);
+            if (!(ctx_mask & (1u << c)) || !n_sites_c) continue;
+            if (!models[c].p) return tfail("model of an enabled context is missing");
+            const uint32_t nt = (c == 2) ? sb.tiles : sb.fwd_tiles;
+            if (!nt) continue;
+            float* lg = s->d_logit[c] + (size_t)sb.gtile0 * kTileRows * 2;
+            for (const DevOp& d : models[c].p->ops) {
+                launch_op(d, *s, nt, lg, sm_count, stream);
+                ++dense_launches;
+            }
+        }
+        TCUDA("dense plan", cudaGetLastError());
+    }
+    TCUDA("dense plan", cudaEventRecord(s->ev1, stream));
+    *launches += dense_launches;
+    // ---- per-site lookup ---------------------------------------------------------------------------------------------------------
+    const uint32_t first[4] = {0, b.class_count[0], b.class_count[0] + b.class_count[1], b.class_count[0] + b.class_count[1] + b.class_count[2]};
+    for (int k = 0; k < 4; ++k) {
+        if (!b.class_count[k]) continue;
+        const int c = k < 3 ? k : 2;
+        site_lookup_kernel<<<(b.class_count[k] + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const float2*>(s->d_logit[c]), s->d_track_row,
+                                                                               s->d_track_row + s->reads_cap, b.d_base_off, b.d_site_read,
+                                                                               b.d_site_pos, b.d_site_out, first[k], b.class_count[k], b.d_logits,
+                                                                               b.d_ml);
+        ++*launches;
+    }
+    TCUDA("site lookup", cudaGetLastError());
+    if (timing) timing->top_kernel_launches = dense_launches;
+    return 0;
+}
+
+// Device time of the dense plan of the last batch (ms); valid after the stream has been synchronised.
+float tensor_last_dense_ms(TensorWorkspace& w)
+{
+    float ms = 0.f;
+    if (w.impl && cudaEventElapsedTime(&ms, w.impl->ev0, w.impl->ev1) != cudaSuccess) ms = 0.f;
+    return ms;
+}
+
+// ---- unit-test hook: one op on caller-provided fp32 maps ------------------------------------------------------------------------
+int tensor_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int cin, int cout, int n_src, const float* const* src, int n_terms,
+                          const int32_t* term_src, const int32_t* term_shift, const float* weights, const float* bias, int conv1_taps,
+                          const float* w2, const float* b2, float* out)
+{
+    if (rows == 0 || rows % kTileRows || rows_alloc < rows || n_src < 1 || n_src > kMaxSegs || n_terms < 1 || n_terms > kMaxTerms)
+        return tfail("hm_debug_dense_op: bad shape");
+    TCUDA("debug op", cudaSetDevice(device));
+    if (ensure_kernel_attr()) return -1;
+    HostOp h;
+    h.out = 0; h.cin = cin; h.cout = cout; h.conv1_taps = conv1_taps; h.head = (w2 != nullptr);
+    h.bias.assign(bias, bias + cout);
+    if (h.head) { h.w2.assign(w2, w2 + 2 * (size_t)cout); h.b2.assign(b2, b2 + 2); }
+    const size_t wsz = conv1_taps > 0 ? (size_t)conv1_taps * 8 * cout : (size_t)cin * cout;
+    for (int k = 0; k < n_terms; ++k) {
+        HostTerm t;
+        if (term_src[k] < 0 || term_src[k] >= n_src || term_shift[k] < 0) return tfail("hm_debug_dense_op: bad term");
+        t.src = term_src[k]; t.shift = term_shift[k];
+        t.w.assign(weights + k * wsz, weights + (k + 1) * wsz);
+        h.terms.push_back(std::move(t));
+    }
+    DevOp d;
+    std::vector<uint8_t> blob;
+    std::string err;
+    if (!lower_op(h, d, blob, err)) return tfail("hm_debug_dense_op: " + err);
+    for (int i = 0; i < d.p.n_segs; ++i)
+        if ((size_t)rows + d.p.seg[i].row_off + d.p.seg[i].nrows - kTileRows > rows_alloc) return tfail("hm_debug_dense_op: shifts run past rows_alloc");
+    const int groups = cin / 8;
+    const unsigned long long ps = (unsigned long long)rows_alloc * 16ull;
+    uint8_t *d_blob = nullptr, *d_in = nullptr, *d_out = nullptr;
+    float* d_logit = nullptr;
+    const size_t in_bytes = (size_t)n_src * 2 * groups * ps;
+    std::vector<uint16_t> img(in_bytes / 2, 0);
+    for (int sidx = 0; sidx < n_src; ++sidx)
+        for (uint32_t r = 0; r < rows_alloc; ++r)
+            for (int c = 0; c < cin; ++c) {
+                const float v = src[sidx][(size_t)r * cin + c];
+                const uint16_t hi = f2bf(v);
+                const size_t base = (size_t)sidx * 2 * groups * (ps / 2);
+                img[base + ((size_t)(c / 8) * rows_alloc + r) * 8 + c % 8] = hi;
+                img[base + ((size_t)(groups + c / 8) * rows_alloc + r) * 8 + c % 8] = f2bf(v - bf2f(hi));
+            }
+    const int ogroups = cout / 8;
+    const unsigned long long ops_ = (unsigned long long)rows * 16ull;
+    const size_t out_bytes = h.head ? 0 : (size_t)2 * ogroups * ops_;
+    TCUDA("debug op", cudaMalloc((void**)&d_blob, blob.size()));
+    TCUDA("debug op", cudaMalloc((void**)&d_in, in_bytes));
+    TCUDA("debug op", cudaMalloc((void**)&d_out, std::max<size_t>(out_bytes, 16)));
+    TCUDA("debug op", cudaMalloc((void**)&d_logit, (size_t)rows * 2 * sizeof(float)));
+    TCUDA("debug op", cudaMemcpy(d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    TCUDA("debug op", cudaMemcpy(d_in, img.data(), in_bytes, cudaMemcpyHostToDevice));
+    bind_blob(d, d_blob);
+    DenseOp p = d.p;
+    for (int i = 0; i < p.n_segs; ++i) {
+        p.seg[i].src = d_in + (size_t)d.seg_map[i] * 2 * groups * ps;
+        p.seg[i].plane_stride = ps;
+    }
+    p.n_tiles = rows / kTileRows;
+    p.out = d_out;
+    p.out_plane_stride = ops_;
+    p.logits = d_logit;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    dense_gemm_kernel<<<std::min<uint32_t>(p.n_tiles, (uint32_t)sms), kDenseThreads, d.smem>>>(p);
+    TCUDA("debug op launch", cudaGetLastError());
+    TCUDA("debug op run", cudaDeviceSynchronize());
+    if (h.head) {
+        TCUDA("debug op", cudaMemcpy(out, d_logit, (size_t)rows * 2 * sizeof(float), cudaMemcpyDeviceToHost));
+    } else {
+        std::vector<uint16_t> o(out_bytes / 2);
+        TCUDA("debug op", cudaMemcpy(o.data(), d_out, out_bytes, cudaMemcpyDeviceToHost));
+        for (uint32_t r = 0; r < rows; ++r)
+            for (int c = 0; c < cout; ++c) {
+                const float hi = bf2f(o[((size_t)(c / 8) * rows + r) * 8 + c % 8]);
+                const float lo = bf2f(o[((size_t)(ogroups + c / 8) * rows + r) * 8 + c % 8]);
+                out[(size_t)r * cout + c] = hi + lo;
+            }
+    }
+    cudaFree(d_blob); cudaFree(d_in); cudaFree(d_out); cudaFree(d_logit);
+    return 0;
+}
+
 }  // namespace hm

@@ -1,4 +1,8 @@
 // cnn_tensor.cuh -- interface of the tensor-core (tcgen05, bf16 split precision) CNN path.
+//
+// The reference evaluates the network once per site on a 401-wide window (src/app/hifimeth/mod_batch.cpp:66-75).
+// This path evaluates it as a *dilated dense plan* over strand positions (see cnn_tensor.cu), every layer being one
+// launch of dense_gemm_kernel (dense_gemm.cuh); a site's logits are row (o - 201) of the final map.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -8,35 +12,52 @@
 
 namespace hm {
 
-struct TensorModel;      // packed bf16 hi/lo weights of one context, device resident
-struct TensorWorkspaceImpl;
+struct TensorModel;          // plan + packed bf16 hi/lo weights of one context, device resident
+struct TensorWorkspaceImpl;  // activation maps of one sub-batch, logits of one batch, track tables
 
 struct TensorWorkspace {
     TensorWorkspaceImpl* impl = nullptr;
 };
-
-struct TensorInputs {
-    const uint8_t* bcode;
-    const ushort4* kinf;
-    const uint32_t* base_off;
-    const uint32_t* site_read;
-    const uint32_t* site_pos;
-    const uint32_t* site_out;
-    float* logits;
-    uint8_t* ml;
-};
-
 struct TensorModelHandle {
     TensorModel* p = nullptr;
+};
+
+// One submitted read batch as the CNN stage sees it.
+struct TensorBatch {
+    // device: outputs of decode_kernel / scan_write_kernel
+    const uint8_t* d_bcode;
+    const ushort4* d_kinf;
+    const uint32_t* d_base_off;
+    const uint32_t* d_site_read;
+    const uint32_t* d_site_pos;
+    const uint32_t* d_site_out;
+    // host (pinned staging of the slot)
+    const uint32_t* h_base_off;
+    const uint8_t* h_valid;
+    uint32_t n_reads;
+    // class regions of the site list: CpG | CHG | CHH fwd | CHH rev
+    uint32_t class_count[4];
+    // results, indexed by site_out
+    float* d_logits;
+    uint8_t* d_ml;
 };
 
 const char* tensor_last_error();
 int tensor_model_build(TensorModelHandle& m, const CnnModel& host);
 void tensor_model_free(TensorModelHandle& m);
-int tensor_workspace_alloc(TensorWorkspace& w, uint32_t max_bases, uint32_t max_reads);
+// max_rows: dense rows (128-row tiles) of one sub-batch; 0 = default
+int tensor_workspace_alloc(TensorWorkspace& w, uint32_t max_bases, uint32_t max_reads, uint32_t max_rows);
 void tensor_workspace_free(TensorWorkspace& w);
-// Runs the CNN of one context over site-list entries [first, first+count); writes logits / ml at site_out.
-int tensor_cnn_run(const TensorModelHandle& m, TensorWorkspace& w, const TensorInputs& in, uint32_t first, uint32_t count,
-                   cudaStream_t stream, uint32_t* launches, hm_timing* timing);
+// Runs the CNN of every enabled context over one batch: features -> dense plan -> per-site logits + ML byte.
+int tensor_batch_run(const TensorModelHandle* models /*[3]*/, uint32_t ctx_mask, TensorWorkspace& w, const TensorBatch& b,
+                     cudaStream_t stream, int sm_count, uint32_t* launches, hm_timing* timing);
+
+// Device time (ms) of the dense plan of the last batch run on this workspace; call after the stream is synchronised.
+float tensor_last_dense_ms(TensorWorkspace& w);
+
+// Unit-test hook behind hm_debug_dense_op (include/hm_engine.h).
+int tensor_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int cin, int cout, int n_src, const float* const* src,
+                          int n_terms, const int32_t* term_src, const int32_t* term_shift, const float* weights, const float* bias,
+                          int conv1_taps, const float* w2, const float* b2, float* out);
 
 }  // namespace hm

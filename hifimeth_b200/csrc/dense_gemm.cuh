@@ -1,0 +1,258 @@
+// dense_gemm.cuh -- the one tensor-core kernel of the CNN path.
+//
+//   out[r][0..N) = act( bias + sum_k  In_k[r + shift_k][0..Cin) . W_k[Cin x N] )        r = tile rows (128 per tile)
+//
+// Every layer of the dilated dense plan (see cnn_tensor.cu) is an instance of this: a few row-shifted views of
+// channel-plane activation maps, multiplied by small weight blocks.  bf16 split precision: activations and
+// weights are stored as hi + lo bf16 pairs and every product is evaluated as hi*hi + lo*hi + hi*lo on the tcgen05
+// tensor cores with fp32 accumulation in TMEM (max probability error 6e-5 vs fp32, tests/test_dense_plan.py).
+//
+// Activation map layout in HBM ("plane layout"):  [hl][g][row][8] bf16,  hl in {hi, lo}, g = channel / 8.
+// A 16-byte unit is 8 consecutive channels of one row; a plane is all rows of one 8-channel group.  Loaded into
+// shared memory plane by plane (1-D bulk copies on the TMA engine), a plane IS a column of UMMA core matrices
+// (8 rows x 16 B, SWIZZLE_NONE, K-major), so a convolution tap is a descriptor whose start address is advanced by
+// shift * 16 bytes -- no im2col, no re-load per tap.
+//
+// CTA = 6 warps, persistent over tiles (grid = #SMs):
+//   warp 0    producer: weights once (resident for the whole launch), then the activation ring
+//   warp 1    MMA issuer (one elected lane): 3 tcgen05.mma per term and k-step, commit -> ring slot free
+//   warps 2-5 epilogue: tcgen05.ld the fp32 accumulator (double buffered in TMEM), bias + ReLU, split to hi/lo
+//             bf16, coalesced 16-byte stores in plane layout (or the fc2 head -> logits)
+#pragma once
+#include <cstdint>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "umma.cuh"
+
+namespace hm {
+
+constexpr int kTileRows = 128;
+constexpr int kMaxTerms = 3;
+constexpr int kMaxSegs = 3;
+constexpr int kDenseThreads = 192;
+
+struct DenseSeg {
+    const uint8_t* src;           // plane 0 (hi, g = 0), row 0 of the input map
+    unsigned long long plane_stride;  // bytes between consecutive planes in HBM
+    int32_t row_off;              // rows [tile*128 + row_off, +nrows) are staged
+    uint32_t nrows;               // rows staged per plane (128 + span of the shifts using this segment)
+    uint32_t groups;              // Cin / 8 of the source map (lo planes start at plane index `groups`)
+    uint32_t smem_off;            // byte offset of this segment inside a ring stage
+};
+
+struct DenseTerm {
+    uint32_t a_off;     // byte offset of the term's hi view inside a ring stage (segment + row shift * 16)
+    uint32_t a_hl_off;  // distance from the hi planes to the lo planes of that segment
+    uint32_t a_lbo;     // byte distance between the two 8-channel halves of a k-step
+};
+
+struct DenseOp {
+    DenseSeg seg[kMaxSegs];
+    DenseTerm term[kMaxTerms];
+    int32_t n_segs, n_terms;
+    int32_t n_stages;        // ring stages per tile (Cin / 16; 1 for the conv1 form)
+    int32_t ksteps;          // k16 steps per stage and term (1; conv1 form: ceil(taps / 2))
+    uint32_t a_q_off;        // byte advance of the A view per k-step inside a stage (conv1 form: 32)
+    int32_t planes_per_seg;  // planes copied per segment and stage (4 = {hi,lo} x 2 groups; conv1 form: 2)
+    uint32_t stage_bytes;    // bytes of one ring stage
+    int32_t ring;            // ring depth
+    const uint8_t* w_img;    // packed weights: tiles [stage][kstep][term][hl], each [2][N][8] bf16 (N*32 bytes)
+    uint32_t w_bytes;
+    const float* bias;       // [N]
+    int32_t n;               // output channels (multiple of 16, <= 256)
+    uint32_t tmem_cols;      // power of two >= 2 * n
+    uint32_t n_tiles;
+    int32_t mode;            // 0: ReLU -> hi/lo plane map;  1: ReLU -> fc2 -> logits
+    uint8_t* out;            // mode 0: plane 0 row 0 of the output map
+    unsigned long long out_plane_stride;
+    const float* w2;         // mode 1: [2][n]
+    const float* b2;         // mode 1: [2]
+    float* logits;           // mode 1: [rows][2]
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b)
+{
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// Shared memory: [weights image][ring stages][barriers]
+__global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel(const __grid_constant__ DenseOp op)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* s_w = smem;
+    uint8_t* s_ring = smem + ((op.w_bytes + 127u) & ~127u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + (size_t)op.ring * op.stage_bytes);
+    uint64_t* full = bars;                  // [ring]
+    uint64_t* empty = bars + op.ring;       // [ring]
+    uint64_t* w_full = bars + 2 * op.ring;  // [1]
+    uint64_t* t_full = w_full + 1;          // [2]
+    uint64_t* t_empty = t_full + 2;         // [2]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < op.ring; ++i) {
+                umma::mbar_init(&full[i], 1);
+                umma::mbar_init(&empty[i], 1);
+            }
+            umma::mbar_init(w_full, 1);
+            for (int i = 0; i < 2; ++i) {
+                umma::mbar_init(&t_full[i], 1);
+                umma::mbar_init(&t_empty[i], 128);
+            }
+            umma::fence_barrier_init();
+        }
+        __syncwarp();
+        umma::tmem_alloc(s_tmem, op.tmem_cols);
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    const uint32_t acc_stride = op.tmem_cols >> 1;
+
+    if (warp == 0) {
+        // ===================================== producer =====================================================
+        if (lane == 0) {
+            umma::mbar_arrive_expect_tx(w_full, op.w_bytes);
+            for (uint32_t off = 0; off < op.w_bytes; off += 32768u) {
+                uint32_t n = min(32768u, op.w_bytes - off);
+                umma::bulk_g2s(s_w + off, op.w_img + off, n, w_full);
+            }
+        }
+        uint32_t slot = 0, phase = 0;
+        uint32_t stage_tx = 0;
+        for (int s = 0; s < op.n_segs; ++s) stage_tx += op.seg[s].nrows * 16u * op.planes_per_seg;
+        for (uint32_t tile = blockIdx.x; tile < op.n_tiles; tile += gridDim.x) {
+            const long long row0 = (long long)tile * kTileRows;
+            for (int st = 0; st < op.n_stages; ++st) {
+                umma::mbar_wait(&empty[slot], phase ^ 1u);
+                uint8_t* stage = s_ring + (size_t)slot * op.stage_bytes;
+                if (lane == 0) {
+                    umma::mbar_arrive_expect_tx(&full[slot], stage_tx);
+                    for (int s = 0; s < op.n_segs; ++s) {
+                    const DenseSeg& sg = op.seg[s];
+                    const uint32_t pl_bytes = sg.nrows * 16u;
+                    for (int p = 0; p < op.planes_per_seg; ++p) {
+                        // planes of a stage: normal form {hi g0, hi g1, lo g0, lo g1}; conv1 form {hi, lo}
+                        const uint32_t hl = (op.planes_per_seg == 4) ? (uint32_t)(p >> 1) : (uint32_t)p;
+                        const uint32_t g = (op.planes_per_seg == 4) ? (uint32_t)(2 * st + (p & 1)) : 0u;
+                        const uint8_t* plane = sg.src + (unsigned long long)(hl * sg.groups + g) * sg.plane_stride;
+                        uint8_t* dst = stage + sg.smem_off + p * pl_bytes;
+                        umma::bulk_g2s(dst, plane + (row0 + sg.row_off) * 16ll, pl_bytes, &full[slot]);
+                    }
+                    }
+                }
+                __syncwarp();
+                if (++slot == (uint32_t)op.ring) { slot = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer ===================================================
+        const uint32_t idesc = umma::make_idesc_bf16_m128((uint32_t)op.n);
+        const uint32_t w_tile = (uint32_t)op.n * 32u;
+        const uint32_t b_lbo = (uint32_t)op.n * 16u;
+        const uint32_t s_w_addr = umma::smem_u32(s_w);
+        umma::mbar_wait(w_full, 0);
+        uint32_t slot = 0, phase = 0, it = 0;
+        for (uint32_t tile = blockIdx.x; tile < op.n_tiles; tile += gridDim.x, ++it) {
+            const uint32_t buf = it & 1u, use = it >> 1;
+            umma::mbar_wait(&t_empty[buf], (use & 1u) ^ 1u);
+            umma::tc_fence_after();
+            const uint32_t d_addr = tmem_base + buf * acc_stride;
+            uint32_t first = 1;
+            for (int st = 0; st < op.n_stages; ++st) {
+                umma::mbar_wait(&full[slot], phase);
+                umma::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t stage_addr = umma::smem_u32(s_ring + (size_t)slot * op.stage_bytes);
+                    for (int q = 0; q < op.ksteps; ++q) {
+                        for (int k = 0; k < op.n_terms; ++k) {
+                            const DenseTerm& tm = op.term[k];
+                            const uint32_t a_hi = stage_addr + tm.a_off + q * op.a_q_off;
+                            const uint32_t a_lo = a_hi + tm.a_hl_off;
+                            const uint32_t wt = s_w_addr + (uint32_t)(((st * op.ksteps + q) * op.n_terms + k) * 2) * w_tile;
+                            const uint64_t da_hi = umma::make_desc(a_hi, tm.a_lbo, 128);
+                            const uint64_t da_lo = umma::make_desc(a_lo, tm.a_lbo, 128);
+                            const uint64_t db_hi = umma::make_desc(wt, b_lbo, 128);
+                            const uint64_t db_lo = umma::make_desc(wt + w_tile, b_lbo, 128);
+                            umma::mma_bf16(d_addr, da_hi, db_hi, idesc, first ^ 1u);
+                            first = 0;
+                            umma::mma_bf16(d_addr, da_lo, db_hi, idesc, 1);
+                            umma::mma_bf16(d_addr, da_hi, db_lo, idesc, 1);
+                        }
+                    }
+                    umma::mma_commit(&empty[slot]);
+                }
+                __syncwarp();
+                if (++slot == (uint32_t)op.ring) { slot = 0; phase ^= 1u; }
+            }
+            if (lane == 0) umma::mma_commit(&t_full[buf]);
+            __syncwarp();
+        }
+    } else {
+        // ===================================== epilogue ======================================================
+        const uint32_t lane_grp = (warp & 3u) * 32u;  // TMEM lanes this warp may touch
+        const uint32_t m = lane_grp + lane;            // row of the tile
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < op.n_tiles; tile += gridDim.x, ++it) {
+            const uint32_t buf = it & 1u, use = it >> 1;
+            umma::mbar_wait(&t_full[buf], use & 1u);
+            umma::tc_fence_after();
+            const uint32_t t_addr = tmem_base + (lane_grp << 16) + buf * acc_stride;
+            const unsigned long long row = (unsigned long long)tile * kTileRows + m;
+            float l0 = 0.f, l1 = 0.f;
+            for (int c0 = 0; c0 < op.n; c0 += 16) {
+                uint32_t v[16];
+                umma::tmem_ld16(t_addr + (uint32_t)c0, v);
+                umma::tmem_ld_wait();
+                float f[16];
+                #pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = fmaxf(__uint_as_float(v[j]) + __ldg(op.bias + c0 + j), 0.f);
+                if (op.mode == 0) {
+                    uint32_t hi[8], lo[8];
+                    #pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * j]), h1 = __float2bfloat16_rn(f[2 * j + 1]);
+                        __nv_bfloat16 e0 = __float2bfloat16_rn(f[2 * j] - __bfloat162float(h0));
+                        __nv_bfloat16 e1 = __float2bfloat16_rn(f[2 * j + 1] - __bfloat162float(h1));
+                        hi[j] = pack_bf16x2(h0, h1);
+                        lo[j] = pack_bf16x2(e0, e1);
+                    }
+                    const uint32_t groups = (uint32_t)op.n >> 3, g = (uint32_t)c0 >> 3;
+                    uint8_t* p_hi = op.out + (unsigned long long)g * op.out_plane_stride + row * 16ull;
+                    uint8_t* p_lo = op.out + (unsigned long long)(groups + g) * op.out_plane_stride + row * 16ull;
+                    *reinterpret_cast<uint4*>(p_hi) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(p_hi + op.out_plane_stride) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                    *reinterpret_cast<uint4*>(p_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4*>(p_lo + op.out_plane_stride) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                } else {
+                    #pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        l0 = fmaf(f[j], __ldg(op.w2 + c0 + j), l0);
+                        l1 = fmaf(f[j], __ldg(op.w2 + op.n + c0 + j), l1);
+                    }
+                }
+            }
+            umma::tc_fence_before();
+            umma::mbar_arrive(&t_empty[buf]);
+            if (op.mode == 1) {
+                float2 o = make_float2(l0 + __ldg(op.b2), l1 + __ldg(op.b2 + 1));
+                *reinterpret_cast<float2*>(op.logits + row * 2ull) = o;
+            }
+        }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    if (warp == 0) umma::tmem_dealloc(tmem_base, op.tmem_cols);
+}
+
+inline size_t dense_smem_bytes(const DenseOp& op)
+{
+    return ((op.w_bytes + 127u) & ~127u) + (size_t)op.ring * op.stage_bytes + (2 * op.ring + 5) * sizeof(uint64_t) + 16;
+}
+
+}  // namespace hm

@@ -260,7 +260,7 @@ int alloc_slot(hm_engine* e, Slot& s)
         }
         for (int l = 0; l < 8; ++l) HM_CUDA(e, st, dmalloc(&s.d_act[l], S * (size_t)lmax[l] * cmax[l]));
     } else {
-        int rc = hm::tensor_workspace_alloc(s.tws, e->cfg.max_bases, e->cfg.max_reads);
+        int rc = hm::tensor_workspace_alloc(s.tws, e->cfg.max_bases, e->cfg.max_reads, 0);
         if (rc) return fail(e, HM_ERR_CUDA, "CUDA error in tensor workspace allocation: %s", hm::tensor_last_error());
     }
     return HM_OK;
@@ -353,15 +353,20 @@ int stage_cnn(hm_engine* e, Slot& s, uint32_t& launches)
     const uint32_t t0 = s.totals[0], t1 = s.totals[1], t23 = s.totals[2] + s.totals[3];
     const uint32_t first[3] = {0, t0, t0 + t1};
     const uint32_t cnt[3] = {t0, t1, t23};
+    if (e->cfg.cnn_mode != HM_CNN_FP32_SIMT) {
+        hm::TensorBatch tb{};
+        tb.d_bcode = s.d_bcode; tb.d_kinf = s.d_kinf; tb.d_base_off = s.d_base_off;
+        tb.d_site_read = s.d_site_read; tb.d_site_pos = s.d_site_pos; tb.d_site_out = s.d_site_out;
+        tb.h_base_off = s.host.base_off; tb.h_valid = s.host.valid; tb.n_reads = s.n_reads;
+        for (int k = 0; k < 4; ++k) tb.class_count[k] = s.totals[k];
+        tb.d_logits = s.d_logits; tb.d_ml = s.d_ml;
+        if (hm::tensor_batch_run(e->tensor, e->ctx_mask, s.tws, tb, s.stream, e->sm_count, &launches, &s.timing))
+            return fail(e, HM_ERR_CUDA, "CUDA error in tensor CNN: %s", hm::tensor_last_error());
+        return HM_OK;
+    }
     for (int c = 0; c < 3; ++c) {
         if (!cnt[c]) continue;
-        int rc;
-        if (e->cfg.cnn_mode == HM_CNN_FP32_SIMT) rc = run_cnn_fp32(e, s, c, first[c], cnt[c], launches);
-        else {
-            hm::TensorInputs in{s.d_bcode, s.d_kinf, s.d_base_off, s.d_site_read, s.d_site_pos, s.d_site_out, s.d_logits, s.d_ml};
-            rc = hm::tensor_cnn_run(e->tensor[c], s.tws, in, first[c], cnt[c], s.stream, &launches, &s.timing);
-            if (rc) return fail(e, HM_ERR_CUDA, "CUDA error in tensor CNN: %s", hm::tensor_last_error());
-        }
+        int rc = run_cnn_fp32(e, s, c, first[c], cnt[c], launches);
         if (rc) return rc;
     }
     return HM_OK;
@@ -541,6 +546,7 @@ int hm_batch_collect(hm_engine* e, int slot, hm_call_batch* out)
     cudaEventElapsedTime(&ms, s.ev[3], s.ev[4]); s.timing.cnn_ms = ms;
     cudaEventElapsedTime(&ms, s.ev[4], s.ev[5]); s.timing.d2h_ms = ms;
     cudaEventElapsedTime(&ms, s.ev[0], s.ev[5]); s.timing.total_ms = ms;
+    if (e->cfg.cnn_mode != HM_CNN_FP32_SIMT) s.timing.top_kernel_ms = hm::tensor_last_dense_ms(s.tws);
     out->n_reads = s.n_reads;
     out->n_calls = s.n_calls;
     out->call_off = s.h_call_off;
@@ -639,6 +645,18 @@ int hm_debug_dump_logits(hm_engine* e, int slot, float* out)
     if (!s.collected) return fail(e, HM_ERR_STATE, "hm_debug_dump_logits: collect slot %d first", slot);
     cudaSetDevice(e->cfg.device);
     HM_CUDA(e, "debug logits", cudaMemcpy(out, s.d_logits, (size_t)s.n_calls * 2 * sizeof(float), cudaMemcpyDeviceToHost));
+    return HM_OK;
+}
+
+int hm_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int cin, int cout, int n_src, const float* const* src, int n_terms,
+                      const int32_t* term_src, const int32_t* term_shift, const float* weights, const float* bias, int conv1_taps,
+                      const float* w2, const float* b2, float* out)
+{
+    if (!src || !term_src || !term_shift || !weights || !bias || !out) return fail(nullptr, HM_ERR_ARG, "hm_debug_dense_op: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(nullptr, HM_ERR_CUDA, "hm_debug_dense_op: no such CUDA device");
+    if (hm::tensor_debug_dense_op(device, rows, rows_alloc, cin, cout, n_src, src, n_terms, term_src, term_shift, weights, bias, conv1_taps, w2, b2, out))
+        return fail(nullptr, HM_ERR_CUDA, "%s", hm::tensor_last_error());
     return HM_OK;
 }
 

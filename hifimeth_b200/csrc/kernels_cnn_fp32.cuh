@@ -8,6 +8,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "postprocess.cuh"
+
 namespace hm {
 
 // Block = COUT threads, TP output positions of one site.  wt = [KW][CIN][COUT], bias [COUT].
@@ -58,19 +60,6 @@ conv_s2_fp32_kernel(const float* __restrict__ in, float* __restrict__ out, const
     #pragma unroll
     for (int t = 0; t < TP; ++t)
         if (t0 + t < lout) dst[(size_t)(t0 + t) * COUT + co] = fmaxf(acc[t], 0.f);
-}
-
-__device__ __forceinline__ float softmax_p1(float v0, float v1)
-{
-    float m = fmaxf(v0, v1);
-    float e0 = expf(v0 - m), e1 = expf(v1 - m);
-    return __fdiv_rn(e1, e0 + e1);
-}
-
-__device__ __forceinline__ uint8_t prob_to_ml(float p1)
-{
-    int v = (int)(255.0f * p1);  // truncation, mod_batch.cpp:59
-    return (uint8_t)(v > 255 ? 255 : v);
 }
 
 // fc1 + ReLU + fc2 + softmax + quantise.  a8 = [site][2][64] channels-last; flatten index = c*2 + t.

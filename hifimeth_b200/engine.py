@@ -57,7 +57,7 @@ class hm_timing(C.Structure):
 ABI_SYMBOLS = ["hm_engine_create", "hm_engine_destroy", "hm_last_error", "hm_version", "hm_batch_acquire", "hm_batch_submit",
                "hm_batch_collect", "hm_batch_timing", "hm_codev1_encode", "hm_codev1_decode", "hm_pack_record",
                "hm_mod_record_bound", "hm_build_mod_record", "hm_debug_dump_decode", "hm_debug_dump_ctx",
-               "hm_debug_dump_features", "hm_debug_dump_logits", "hm_microbench"]
+               "hm_debug_dump_features", "hm_debug_dump_logits", "hm_debug_dense_op", "hm_microbench"]
 
 _lib = None
 
@@ -93,6 +93,8 @@ def load_library() -> C.CDLL:
     L.hm_debug_dump_ctx.argtypes = [C.c_void_p, C.c_int, _u8p]
     L.hm_debug_dump_features.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, _f32p]
     L.hm_debug_dump_logits.argtypes = [C.c_void_p, C.c_int, _f32p]
+    L.hm_debug_dense_op.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(_f32p), C.c_int, _i32p, _i32p,
+                                    _f32p, _f32p, C.c_int, _f32p, _f32p, _f32p]
     L.hm_microbench.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_uint32, C.c_int, _f32p, C.POINTER(C.c_double),
                                 C.POINTER(C.c_double)]
     _lib = L
@@ -278,3 +280,31 @@ def pack_records_host(bodies, min_read_len: int = 1000, max_bases: int = None):
     ns = int(arr["seq_off"][n.value])
     return ReadBatch(n.value, arr["base_off"][:n.value + 1], arr["seq_off"][:n.value + 1], arr["seq4"][:ns], arr["flag"][:n.value],
                      arr["valid"][:n.value], arr["fi"][:nb], arr["fp"][:nb], arr["ri"][:nb], arr["rp"][:nb])
+
+
+def debug_dense_op(srcs, terms, bias, rows: int, conv1_taps: int = 0, w2=None, b2=None, device: int = 0) -> np.ndarray:
+    """hm_debug_dense_op: one op of the tensor-core dense plan on caller data (unit test of dense_gemm_kernel).
+
+    srcs: list of [rows_alloc, cin] f32 maps; terms: list of (src index, row shift, W) with W [cin, cout]
+    (conv1 form: one term, W [taps, 8, cout]); returns [rows, cout] f32, or [rows, 2] when w2/b2 select the head form."""
+    L = load_library()
+    srcs = [np.ascontiguousarray(a, np.float32) for a in srcs]
+    rows_alloc, cin = srcs[0].shape
+    w = np.ascontiguousarray(np.stack([np.asarray(t[2], np.float32) for t in terms]))
+    cout = w.shape[-1]
+    bias = np.ascontiguousarray(bias, np.float32)
+    tsrc = np.array([t[0] for t in terms], np.int32)
+    tsh = np.array([t[1] for t in terms], np.int32)
+    ptrs = (_f32p * len(srcs))(*[a.ctypes.data_as(_f32p) for a in srcs])
+    head = w2 is not None
+    out = np.empty((rows, 2 if head else cout), np.float32)
+    if head:
+        w2 = np.ascontiguousarray(w2, np.float32)
+        b2 = np.ascontiguousarray(b2, np.float32)
+    rc = L.hm_debug_dense_op(device, rows, rows_alloc, cin, cout, len(srcs), ptrs, len(terms), tsrc.ctypes.data_as(_i32p),
+                             tsh.ctypes.data_as(_i32p), w.ctypes.data_as(_f32p), bias.ctypes.data_as(_f32p), conv1_taps,
+                             w2.ctypes.data_as(_f32p) if head else None, b2.ctypes.data_as(_f32p) if head else None,
+                             out.ctypes.data_as(_f32p))
+    if rc != 0:
+        raise HmError(f"hm_debug_dense_op failed ({rc}): {L.hm_last_error(None).decode()}")
+    return out

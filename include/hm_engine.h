@@ -160,6 +160,15 @@ int hm_debug_dump_features(hm_engine* e, int slot, uint32_t first, uint32_t coun
 /* Logits [n_calls][2] f32 in hm_call_batch order. */
 int hm_debug_dump_logits(hm_engine* e, int slot, float* out);
 
+/* One op of the tensor-core dense plan on caller-provided fp32 data (unit test of dense_gemm_kernel; no engine needed):
+ *   out[r][:] = relu(bias + sum_k src[term_src[k]][r + term_shift[k]][:] . W_k),  r < rows (multiple of 128)
+ * src maps are [rows_alloc][cin] f32, W_k = weights + k*cin*cout as [cin][cout].  conv1_taps > 0 selects the conv1 form:
+ * cin = 8, one term, weights [taps][8][cout], rows r + shift .. r + shift + taps - 1.  w2 != NULL selects the head
+ * form: out = [rows][2] = relu(...) . w2^T + b2 with w2 [2][cout].  Arithmetic: bf16 hi/lo split, fp32 accumulate. */
+int hm_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int cin, int cout, int n_src, const float* const* src,
+                      int n_terms, const int32_t* term_src, const int32_t* term_shift, const float* weights, const float* bias,
+                      int conv1_taps, const float* w2, const float* b2, float* out);
+
 /* ---- kernel microbenchmarks (BASELINE.json config 5) --------------------------------------------------- */
 /* Runs one named kernel family `iters` times on the slot's resident inputs and returns the mean device
  * time per launch (CUDA events) and the algorithmic bytes / flops one launch processes.
