@@ -44,6 +44,14 @@ constexpr int kHaloR = 200;   // zero-feature rows after the last strand positio
 constexpr int kSlackRows = 1024;  // rows past the sub-batch every plane keeps allocated (shifted reads of the last tile)
 constexpr size_t kSmemMax = 232448;
 
+// Default: dense Y chain + F/G/tail ops evaluated at site rows only ("compact").  HM_DENSE_ALL=1 evaluates every op on
+// every row (the first version of this path; kept for A/B measurements).
+bool compact_mode()
+{
+    static const bool v = getenv("HM_DENSE_ALL") == nullptr;
+    return v;
+}
+
 enum MapId { MAP_X = 0, MAP_Y = 1, MAP_F = 7, MAP_G = 13, MAP_T7 = 19, MAP_T8 = 23, N_MAPS = 25 };
 const int kLayerCout[6] = {128, 128, 128, 96, 96, 96};
 
@@ -59,6 +67,7 @@ int map_channels(int id)
 // ---- host plan ---------------------------------------------------------------------------------------------------
 struct HostTerm {
     int src = 0, shift = 0;
+    bool gather = false;   // compact op: rows are picked through the site-row index (source is a dense map)
     std::vector<float> w;  // [cin][cout]; conv1 form: [taps][8][cout]
 };
 struct HostOp {
@@ -68,6 +77,7 @@ struct HostOp {
     std::vector<HostTerm> terms;
     int conv1_taps = 0;  // > 0: conv1 form (one term, weights [taps][8][cout], rows shift .. shift + taps - 1)
     bool head = false;
+    bool compact = false;  // evaluated at site rows only (one output row per site of the run)
     std::vector<float> w2, b2;
 };
 
@@ -87,7 +97,7 @@ float bf2f(uint16_t h)
     return f;
 }
 
-bool build_plan(const CnnModel& m, std::vector<HostOp>& ops, std::string& err)
+bool build_plan(const CnnModel& m, bool compact, std::vector<HostOp>& ops, std::string& err)
 {
     if (m.features != 8 || m.kmer != 401 || m.convs.size() != 8) { err = "unsupported model geometry"; return false; }
     const int k1 = m.convs[0].k;
@@ -117,9 +127,10 @@ bool build_plan(const CnnModel& m, std::vector<HostOp>& ops, std::string& err)
     auto conv1_op = [&](int out, int base_shift, int skip_tap) {
         HostOp op;
         op.out = out; op.cin = 8; op.cout = 128; op.conv1_taps = k1;
+        op.compact = compact && out != MAP_Y;
         op.bias.resize(128);
         HostTerm t;
-        t.src = MAP_X; t.shift = base_shift;
+        t.src = MAP_X; t.shift = base_shift; t.gather = op.compact;
         t.w.assign((size_t)k1 * 8 * 128, 0.f);
         for (int o = 0; o < 128; ++o) {
             double b = b1f[o];
@@ -178,11 +189,13 @@ bool build_plan(const CnnModel& m, std::vector<HostOp>& ops, std::string& err)
         }
         for (auto& ov : outs) {
             HostOp op = new_op(ov.first);
+            op.compact = compact;
             for (int j = 0; j < 3; ++j) {
                 int mp, sh;
                 if (!src(l - 1, 2 * ov.second - 1 + j, mp, sh)) continue;
                 if (sh < 0) { err = "negative shift in plan"; return false; }
                 HostTerm t; t.src = mp; t.shift = sh; t.w = tap(j);
+                t.gather = compact && mp >= MAP_Y && mp < MAP_F;  // dense Y maps are read through the site-row index
                 op.terms.push_back(std::move(t));
             }
             ops.push_back(std::move(op));
@@ -191,6 +204,7 @@ bool build_plan(const CnnModel& m, std::vector<HostOp>& ops, std::string& err)
     // ---- head: flatten index = c * 2 + t; fc1 + ReLU on the tensor cores, fc2 in the epilogue ---------------------
     HostOp h;
     h.head = true; h.cin = 64; h.cout = 256; h.bias = m.fc1_b; h.w2 = m.fc2_w; h.b2 = m.fc2_b;
+    h.compact = compact;
     for (int t = 0; t < 2; ++t) {
         HostTerm tm; tm.src = MAP_T8 + t; tm.shift = 0;
         tm.w.resize((size_t)64 * 256);
@@ -207,48 +221,73 @@ struct DevOp {
     DenseOp p{};
     int seg_map[kMaxSegs] = {0, 0, 0};
     int out_map = -1;
+    bool compact = false;
     size_t smem = 0;
     size_t w_off = 0, bias_off = 0, w2_off = 0, b2_off = 0;  // offsets into the model blob
     double macs_per_row = 0;  // executed MACs per output row, one precision pass
 };
 
-bool lower_op(const HostOp& h, DevOp& d, std::vector<uint8_t>& blob, std::string& err)
+// Lowers output channels [n0, n0 + n) of a plan op to kernel parameters + packed weights.  Returns false with
+// err = "fit" when the slice's resident weights leave no room for a 2-deep ring (the caller then splits it).
+bool lower_op(const HostOp& h, int n0, int n, DevOp& d, std::vector<uint8_t>& blob, std::string& err)
 {
     DenseOp& p = d.p;
-    const int n = h.cout;
+    p = DenseOp{};
+    const int nfull = h.cout;
     if (n % 16 || n > 256 || h.terms.empty() || (int)h.terms.size() > kMaxTerms) { err = "op shape not supported"; return false; }
     p.n = n;
+    p.out_groups = (uint32_t)nfull / 8;
+    p.out_g0 = (uint32_t)n0 / 8;
     p.tmem_cols = 32;
     while (p.tmem_cols < (uint32_t)(2 * n)) p.tmem_cols <<= 1;
     p.n_terms = (int)h.terms.size();
     p.mode = h.head ? 1 : 0;
     d.out_map = h.out;
     uint32_t stage = 0;
+    d.compact = h.compact;
+    p.gather_taps = 0;
+    p.gather_rows = nullptr;
     if (h.conv1_taps > 0) {
-        p.n_segs = 1; p.n_stages = 1; p.ksteps = (h.conv1_taps + 1) / 2; p.a_q_off = 32; p.planes_per_seg = 2;
+        p.n_segs = 1; p.n_stages = 1; p.ksteps = (h.conv1_taps + 1) / 2;
         DenseSeg& sg = p.seg[0];
-        sg.row_off = h.terms[0].shift; sg.nrows = kTileRows + 16; sg.groups = 1; sg.smem_off = 0;
+        sg.row_off = h.terms[0].shift; sg.groups = 1; sg.smem_off = 0;
         d.seg_map[0] = h.terms[0].src;
-        p.term[0] = DenseTerm{0u, sg.nrows * 16u, 16u};
-        stage = 2 * sg.nrows * 16u;
+        if (h.terms[0].gather) {
+            // explicit im2col in shared memory: one 128-row plane per tap, gathered through the site-row index
+            const uint32_t T = 2u * p.ksteps, pl = kTileRows * 16u;
+            sg.gather = 1; sg.nrows = kTileRows;
+            p.gather_taps = (int)T; p.planes_per_seg = (int)(2 * T); p.a_q_off = 2 * pl;
+            p.term[0] = DenseTerm{0u, T * pl, pl};
+            stage = 2 * T * pl;
+        } else {
+            // rows are consecutive positions: K-chunk c of row r is row r + c of the same plane (LBO = 16 bytes)
+            sg.gather = 0; sg.nrows = kTileRows + 16;
+            p.planes_per_seg = 2; p.a_q_off = 32;
+            p.term[0] = DenseTerm{0u, sg.nrows * 16u, 16u};
+            stage = 2 * sg.nrows * 16u;
+        }
         d.macs_per_row = (double)p.ksteps * 16 * n;
     } else {
         if (h.cin % 16) { err = "cin must be a multiple of 16"; return false; }
         p.n_stages = h.cin / 16; p.ksteps = 1; p.a_q_off = 0; p.planes_per_seg = 4; p.n_segs = 0;
+        int term_seg[kMaxTerms] = {0, 0, 0};
         for (size_t k = 0; k < h.terms.size(); ++k) {
             int s = -1;
-            for (int i = 0; i < p.n_segs; ++i)
-                if (d.seg_map[i] == h.terms[k].src) s = i;
+            if (!h.terms[k].gather)
+                for (int i = 0; i < p.n_segs; ++i)
+                    if (!p.seg[i].gather && d.seg_map[i] == h.terms[k].src) s = i;
             if (s < 0) {
                 if (p.n_segs == kMaxSegs) { err = "too many segments"; return false; }
                 s = p.n_segs++;
                 d.seg_map[s] = h.terms[k].src;
+                p.seg[s].gather = h.terms[k].gather ? 1u : 0u;
                 p.seg[s].row_off = h.terms[k].shift;
-                p.seg[s].nrows = 0;  // holds max shift until finalised
+                p.seg[s].nrows = (uint32_t)h.terms[k].shift;  // holds the max shift until finalised
                 p.seg[s].groups = (uint32_t)h.cin / 8;
             }
             p.seg[s].row_off = std::min(p.seg[s].row_off, h.terms[k].shift);
             p.seg[s].nrows = std::max<uint32_t>(p.seg[s].nrows, (uint32_t)h.terms[k].shift);
+            term_seg[k] = s;
         }
         for (int s = 0; s < p.n_segs; ++s) {
             p.seg[s].nrows = kTileRows + (p.seg[s].nrows - (uint32_t)p.seg[s].row_off);
@@ -256,9 +295,7 @@ bool lower_op(const HostOp& h, DevOp& d, std::vector<uint8_t>& blob, std::string
             stage += 4 * p.seg[s].nrows * 16u;
         }
         for (size_t k = 0; k < h.terms.size(); ++k) {
-            int s = 0;
-            for (int i = 0; i < p.n_segs; ++i)
-                if (d.seg_map[i] == h.terms[k].src) s = i;
+            const int s = term_seg[k];
             const uint32_t pl = p.seg[s].nrows * 16u;
             p.term[k] = DenseTerm{p.seg[s].smem_off + (uint32_t)(h.terms[k].shift - p.seg[s].row_off) * 16u, 2 * pl, pl};
         }
@@ -280,9 +317,9 @@ bool lower_op(const HostOp& h, DevOp& d, std::vector<uint8_t>& blob, std::string
                             float w = 0.f;
                             if (h.conv1_taps > 0) {
                                 int tap = 2 * q + c;
-                                if (tap < h.conv1_taps) w = h.terms[0].w[((size_t)tap * 8 + e) * n + o];
+                                if (tap < h.conv1_taps) w = h.terms[0].w[((size_t)tap * 8 + e) * nfull + n0 + o];
                             } else {
-                                w = h.terms[k].w[(size_t)(16 * st + 8 * c + e) * n + o];
+                                w = h.terms[k].w[(size_t)(16 * st + 8 * c + e) * nfull + n0 + o];
                             }
                             uint16_t wh = f2bf(w);
                             hi[((size_t)c * n + o) * 8 + e] = wh;
@@ -291,7 +328,7 @@ bool lower_op(const HostOp& h, DevOp& d, std::vector<uint8_t>& blob, std::string
             }
     p.w_bytes = (uint32_t)(img.size() * 2);
     const size_t w_al = (p.w_bytes + 127u) & ~127u;
-    if (w_al + 2 * (size_t)p.stage_bytes + 256 > kSmemMax) { err = "op does not fit shared memory"; return false; }
+    if (w_al + 2 * (size_t)p.stage_bytes + 256 > kSmemMax) { err = "fit"; return false; }
     p.ring = (int)std::min<size_t>(8, (kSmemMax - 256 - w_al) / p.stage_bytes);
     d.smem = dense_smem_bytes(p);
     auto append = [&](const void* src, size_t bytes) {
@@ -301,7 +338,7 @@ bool lower_op(const HostOp& h, DevOp& d, std::vector<uint8_t>& blob, std::string
         return o;
     };
     d.w_off = append(img.data(), img.size() * 2);
-    d.bias_off = append(h.bias.data(), h.bias.size() * 4);
+    d.bias_off = append(h.bias.data() + n0, (size_t)n * 4);
     if (h.head) {
         d.w2_off = append(h.w2.data(), h.w2.size() * 4);
         d.b2_off = append(h.b2.data(), h.b2.size() * 4);
@@ -393,6 +430,50 @@ site_lookup_kernel(const float2* __restrict__ logit_rows, const uint32_t* __rest
     ml[out] = prob_to_ml(softmax_p1(lg.x, lg.y));
 }
 
+// Compact runs: compact row m of a run is site (first_a + m) for m < n_a, else site (first_b + m - n_a) of the class-ordered
+// site list.  site_rows_kernel writes the dense row (local to the sub-batch) that holds s = o - 201 of every compact row.
+__device__ __forceinline__ uint32_t run_site(uint32_t m, uint32_t first_a, uint32_t n_a, uint32_t first_b)
+{
+    return m < n_a ? first_a + m : first_b + (m - n_a);
+}
+
+__global__ void __launch_bounds__(256)
+site_rows_kernel(const uint32_t* __restrict__ track_row_fwd, const uint32_t* __restrict__ track_row_rev,
+                 const uint32_t* __restrict__ base_off, const uint32_t* __restrict__ site_read, const uint32_t* __restrict__ site_pos,
+                 uint32_t first_a, uint32_t n_a, uint32_t first_b, uint32_t n, uint32_t n_pad, uint32_t row_base,
+                 uint32_t* __restrict__ rows)
+{
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_pad) return;
+    uint32_t row = 0;  // padding rows read row 0 (any valid row) and are never looked at
+    if (m < n) {
+        const uint32_t k = run_site(m, first_a, n_a, first_b);
+        const uint32_t r = site_read[k];
+        const uint32_t sp = site_pos[k];
+        const bool rev = (sp >> 31) != 0;
+        const int p = (int)(sp & 0x7fffffffu);
+        const int L = (int)(base_off[r + 1] - base_off[r]);
+        const int o = rev ? L - 1 - p : p;
+        row = (rev ? track_row_rev[r] : track_row_fwd[r]) - row_base + (uint32_t)(kHaloL + o - 201);
+    }
+    rows[m] = row;
+}
+
+// logits of the compact rows -> per-site logits + ML byte in hm_call_batch order
+// (s_logits_to_methy_probs, src/app/hifimeth/mod_batch.cpp:46-64).
+__global__ void __launch_bounds__(256)
+site_finish_kernel(const float2* __restrict__ clogit, const uint32_t* __restrict__ site_out, uint32_t first_a, uint32_t n_a,
+                   uint32_t first_b, uint32_t n, float* __restrict__ logits, uint8_t* __restrict__ ml)
+{
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    const float2 lg = clogit[m];
+    const uint32_t out = site_out[run_site(m, first_a, n_a, first_b)];
+    logits[2 * (size_t)out] = lg.x;
+    logits[2 * (size_t)out + 1] = lg.y;
+    ml[out] = prob_to_ml(softmax_p1(lg.x, lg.y));
+}
+
 }  // namespace
 
 // ---- model ---------------------------------------------------------------------------------------------------------------
@@ -408,14 +489,26 @@ int tensor_model_build(TensorModelHandle& m, const CnnModel& host)
 {
     std::vector<HostOp> plan;
     std::string err;
-    if (!build_plan(host, plan, err)) return tfail("dense plan: " + err);
+    if (!build_plan(host, compact_mode(), plan, err)) return tfail("dense plan: " + err);
     TensorModel* t = new TensorModel();
     std::vector<uint8_t> blob;
     for (const HostOp& h : plan) {
-        DevOp d;
-        if (!lower_op(h, d, blob, err)) { delete t; return tfail("dense plan lowering: " + err); }
-        t->macs_per_row += d.macs_per_row;
-        t->ops.push_back(d);
+        // an op whose resident weights leave no room for the activation ring is split over output channels
+        int parts = 1;
+        for (; parts <= 4; parts *= 2) {
+            if (h.cout % (16 * parts) || (h.head && parts > 1)) { parts = 8; break; }
+            std::vector<DevOp> ds(parts);
+            std::vector<uint8_t> trial = blob;
+            bool ok = true;
+            for (int i = 0; i < parts && ok; ++i) ok = lower_op(h, i * (h.cout / parts), h.cout / parts, ds[i], trial, err);
+            if (ok) {
+                blob.swap(trial);
+                for (DevOp& d : ds) { t->macs_per_row += d.macs_per_row; t->ops.push_back(d); }
+                break;
+            }
+            if (err != "fit") { parts = 8; break; }
+        }
+        if (parts > 4) { delete t; return tfail("dense plan lowering: " + (err == "fit" ? std::string("op does not fit shared memory") : err)); }
     }
     cudaError_t st = cudaMalloc((void**)&t->d_blob, blob.size());
     if (st == cudaSuccess) st = cudaMemcpy(t->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice);
@@ -444,6 +537,8 @@ struct TensorWorkspaceImpl {
     uint32_t tiles_cap = 0, reads_cap = 0;
     uint32_t *h_tile_read = nullptr, *h_tile_first = nullptr, *d_tile_read = nullptr, *d_tile_first = nullptr;
     uint32_t *h_track_row = nullptr, *d_track_row = nullptr;  // [2][reads_cap]
+    uint32_t* d_site_rows = nullptr;  // [rows_cap] compact row -> dense row
+    float* d_clogit = nullptr;        // [rows_cap][2] logits of the compact rows
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
@@ -472,7 +567,10 @@ int tensor_workspace_alloc(TensorWorkspace& w, uint32_t max_bases, uint32_t max_
         pl += 2 * (size_t)map_channels(i) / 8;
     }
     s->logit_rows_cap = total_rows;
-    for (int c = 0; c < 3; ++c) TCUDA("logit rows", cudaMalloc((void**)&s->d_logit[c], total_rows * 2 * sizeof(float)));
+    if (!compact_mode())
+        for (int c = 0; c < 3; ++c) TCUDA("logit rows", cudaMalloc((void**)&s->d_logit[c], total_rows * 2 * sizeof(float)));
+    TCUDA("site rows", cudaMalloc((void**)&s->d_site_rows, (cap + kTileRows) * sizeof(uint32_t)));
+    TCUDA("site rows", cudaMalloc((void**)&s->d_clogit, (cap + kTileRows) * 2 * sizeof(float)));
     s->tiles_cap = (uint32_t)(total_rows / kTileRows + 1);
     s->reads_cap = max_reads;
     TCUDA("track tables", cudaMallocHost((void**)&s->h_tile_read, (size_t)s->tiles_cap * 4));
@@ -492,6 +590,7 @@ void tensor_workspace_free(TensorWorkspace& w)
     if (!s) return;
     cudaFree(s->d_maps);
     for (float* p : s->d_logit) cudaFree(p);
+    cudaFree(s->d_site_rows); cudaFree(s->d_clogit);
     cudaFreeHost(s->h_tile_read); cudaFreeHost(s->h_tile_first); cudaFree(s->d_tile_read); cudaFree(s->d_tile_first);
     cudaFreeHost(s->h_track_row); cudaFree(s->d_track_row);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -510,6 +609,7 @@ int launch_op(const DevOp& d, const TensorWorkspaceImpl& s, uint32_t n_tiles, fl
         p.seg[i].plane_stride = s.plane_stride;
     }
     p.n_tiles = n_tiles;
+    p.gather_rows = s.d_site_rows;
     if (p.mode == 0) {
         p.out = s.map[d.out_map];
         p.out_plane_stride = s.plane_stride;
@@ -523,6 +623,7 @@ int launch_op(const DevOp& d, const TensorWorkspaceImpl& s, uint32_t n_tiles, fl
 
 struct SubBatch {
     uint32_t gtile0, fwd_tiles, tiles;
+    uint32_t r0, r1;  // reads [r0, r1)
 };
 
 }  // namespace
@@ -554,7 +655,7 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
             ++r1;
         }
         if (rows) {
-            SubBatch sb{gtile, 0, 0};
+            SubBatch sb{gtile, 0, 0, r, r1};
             for (int strand = 0; strand < (want_rev ? 2 : 1); ++strand) {
                 for (uint32_t q = r; q < r1; ++q) {
                     if (!b.h_valid[q]) continue;
@@ -583,6 +684,8 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
     // ---- the plan, sub-batch by sub-batch -------------------------------------------------------------------------------------
     TCUDA("dense plan", cudaEventRecord(s->ev0, stream));
     uint32_t dense_launches = 0;
+    const bool compact = compact_mode();
+    const uint32_t first[4] = {0, b.class_count[0], b.class_count[0] + b.class_count[1], b.class_count[0] + b.class_count[1] + b.class_count[2]};
     for (const SubBatch& sb : subs) {
         track_features_kernel<<<sb.tiles, 128, 0, stream>>>(b.d_bcode, b.d_kinf, b.d_base_off, s->d_tile_read, s->d_tile_first, sb.gtile0,
                                                           s->map[MAP_X], s->map[MAP_X] + s->plane_stride);
@@ -593,19 +696,40 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
             if (!models[c].p) return tfail("model of an enabled context is missing");
             const uint32_t nt = (c == 2) ? sb.tiles : sb.fwd_tiles;
             if (!nt) continue;
-            float* lg = s->d_logit[c] + (size_t)sb.gtile0 * kTileRows * 2;
+            if (!compact) {
+                float* lg = s->d_logit[c] + (size_t)sb.gtile0 * kTileRows * 2;
+                for (const DevOp& d : models[c].p->ops) {
+                    launch_op(d, *s, nt, lg, sm_count, stream);
+                    ++dense_launches;
+                }
+                continue;
+            }
+            // sites of this context inside the sub-batch: class regions are ordered by read, so each is one range
+            const uint32_t* p0 = b.h_read_pref + 4 * (size_t)sb.r0;
+            const uint32_t* p1 = b.h_read_pref + 4 * (size_t)sb.r1;
+            const uint32_t first_a = first[c] + p0[c], n_a = p1[c] - p0[c];
+            const uint32_t first_b = c == 2 ? first[3] + p0[3] : 0u, n_b = c == 2 ? p1[3] - p0[3] : 0u;
+            const uint32_t n = n_a + n_b;
+            if (!n) continue;
+            if (n > s->rows_cap) return tfail("internal: more sites than dense rows in a sub-batch");
+            const uint32_t n_pad = ((n + kTileRows - 1) / kTileRows) * kTileRows;
+            site_rows_kernel<<<(n_pad + 255) / 256, 256, 0, stream>>>(s->d_track_row, s->d_track_row + s->reads_cap, b.d_base_off, b.d_site_read,
+                                                                      b.d_site_pos, first_a, n_a, first_b, n, n_pad, sb.gtile0 * kTileRows,
+                                                                      s->d_site_rows);
             for (const DevOp& d : models[c].p->ops) {
-                launch_op(d, *s, nt, lg, sm_count, stream);
+                launch_op(d, *s, d.compact ? n_pad / kTileRows : nt, s->d_clogit, sm_count, stream);
                 ++dense_launches;
             }
+            site_finish_kernel<<<(n + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const float2*>(s->d_clogit), b.d_site_out, first_a, n_a, first_b, n,
+                                                                    b.d_logits, b.d_ml);
+            *launches += 2;
         }
         TCUDA("dense plan", cudaGetLastError());
     }
     TCUDA("dense plan", cudaEventRecord(s->ev1, stream));
     *launches += dense_launches;
-    // ---- per-site lookup ---------------------------------------------------------------------------------------------------------
-    const uint32_t first[4] = {0, b.class_count[0], b.class_count[0] + b.class_count[1], b.class_count[0] + b.class_count[1] + b.class_count[2]};
-    for (int k = 0; k < 4; ++k) {
+    // ---- per-site lookup (dense-all mode only; compact runs finish per sub-batch) ----------------------------------------------
+    for (int k = 0; k < 4 && !compact; ++k) {
         if (!b.class_count[k]) continue;
         const int c = k < 3 ? k : 2;
         site_lookup_kernel<<<(b.class_count[k] + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const float2*>(s->d_logit[c]), s->d_track_row,
@@ -630,9 +754,10 @@ float tensor_last_dense_ms(TensorWorkspace& w)
 // ---- unit-test hook: one op on caller-provided fp32 maps ------------------------------------------------------------------------
 int tensor_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int cin, int cout, int n_src, const float* const* src, int n_terms,
                           const int32_t* term_src, const int32_t* term_shift, const float* weights, const float* bias, int conv1_taps,
-                          const float* w2, const float* b2, float* out)
+                          const float* w2, const float* b2, const uint32_t* gather_rows, uint32_t gather_mask, float* out)
 {
-    if (rows == 0 || rows % kTileRows || rows_alloc < rows || n_src < 1 || n_src > kMaxSegs || n_terms < 1 || n_terms > kMaxTerms)
+    if (!gather_rows) gather_mask = 0;
+    if (rows == 0 || rows % kTileRows || (!gather_mask && rows_alloc < rows) || n_src < 1 || n_src > kMaxSegs || n_terms < 1 || n_terms > kMaxTerms)
         return tfail("hm_debug_dense_op: bad shape");
     TCUDA("debug op", cudaSetDevice(device));
     if (ensure_kernel_attr()) return -1;
@@ -645,19 +770,27 @@ int tensor_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int ci
         HostTerm t;
         if (term_src[k] < 0 || term_src[k] >= n_src || term_shift[k] < 0) return tfail("hm_debug_dense_op: bad term");
         t.src = term_src[k]; t.shift = term_shift[k];
+        t.gather = ((gather_mask >> k) & 1u) != 0;
         t.w.assign(weights + k * wsz, weights + (k + 1) * wsz);
         h.terms.push_back(std::move(t));
     }
     DevOp d;
     std::vector<uint8_t> blob;
     std::string err;
-    if (!lower_op(h, d, blob, err)) return tfail("hm_debug_dense_op: " + err);
-    for (int i = 0; i < d.p.n_segs; ++i)
-        if ((size_t)rows + d.p.seg[i].row_off + d.p.seg[i].nrows - kTileRows > rows_alloc) return tfail("hm_debug_dense_op: shifts run past rows_alloc");
+    if (!lower_op(h, 0, cout, d, blob, err)) return tfail("hm_debug_dense_op: " + (err == "fit" ? std::string("op does not fit shared memory") : err));
+    h.compact = gather_mask != 0;
+    uint32_t max_g = 0;
+    for (uint32_t r = 0; gather_mask && r < rows; ++r) max_g = std::max(max_g, gather_rows[r]);
+    for (int i = 0; i < d.p.n_segs; ++i) {
+        const size_t last = d.p.seg[i].gather ? (size_t)max_g + d.p.seg[i].row_off + (d.p.gather_taps > 0 ? d.p.gather_taps : 1)
+                                              : (size_t)rows + d.p.seg[i].row_off + d.p.seg[i].nrows - kTileRows;
+        if (last > rows_alloc) return tfail("hm_debug_dense_op: shifts run past rows_alloc");
+    }
     const int groups = cin / 8;
     const unsigned long long ps = (unsigned long long)rows_alloc * 16ull;
     uint8_t *d_blob = nullptr, *d_in = nullptr, *d_out = nullptr;
     float* d_logit = nullptr;
+    uint32_t* d_rows = nullptr;
     const size_t in_bytes = (size_t)n_src * 2 * groups * ps;
     std::vector<uint16_t> img(in_bytes / 2, 0);
     for (int sidx = 0; sidx < n_src; ++sidx)
@@ -684,6 +817,11 @@ int tensor_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int ci
         p.seg[i].src = d_in + (size_t)d.seg_map[i] * 2 * groups * ps;
         p.seg[i].plane_stride = ps;
     }
+    if (gather_mask) {
+        TCUDA("debug op", cudaMalloc((void**)&d_rows, (size_t)rows * 4));
+        TCUDA("debug op", cudaMemcpy(d_rows, gather_rows, (size_t)rows * 4, cudaMemcpyHostToDevice));
+    }
+    p.gather_rows = d_rows;
     p.n_tiles = rows / kTileRows;
     p.out = d_out;
     p.out_plane_stride = ops_;
@@ -705,7 +843,7 @@ int tensor_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int ci
                 out[(size_t)r * cout + c] = hi + lo;
             }
     }
-    cudaFree(d_blob); cudaFree(d_in); cudaFree(d_out); cudaFree(d_logit);
+    cudaFree(d_blob); cudaFree(d_in); cudaFree(d_out); cudaFree(d_logit); cudaFree(d_rows);
     return 0;
 }
 

@@ -34,6 +34,7 @@ struct TensorBatch {
     // host (pinned staging of the slot)
     const uint32_t* h_base_off;
     const uint8_t* h_valid;
+    const uint32_t* h_read_pref;  // [n_reads + 1][4] sites of each class in reads before r (exclusive prefix)
     uint32_t n_reads;
     // class regions of the site list: CpG | CHG | CHH fwd | CHH rev
     uint32_t class_count[4];
@@ -58,6 +59,6 @@ float tensor_last_dense_ms(TensorWorkspace& w);
 // Unit-test hook behind hm_debug_dense_op (include/hm_engine.h).
 int tensor_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int cin, int cout, int n_src, const float* const* src,
                           int n_terms, const int32_t* term_src, const int32_t* term_shift, const float* weights, const float* bias,
-                          int conv1_taps, const float* w2, const float* b2, float* out);
+                          int conv1_taps, const float* w2, const float* b2, const uint32_t* gather_rows, uint32_t gather_mask, float* out);
 
 }  // namespace hm

@@ -35,8 +35,9 @@ constexpr int kDenseThreads = 192;
 struct DenseSeg {
     const uint8_t* src;           // plane 0 (hi, g = 0), row 0 of the input map
     unsigned long long plane_stride;  // bytes between consecutive planes in HBM
-    int32_t row_off;              // rows [tile*128 + row_off, +nrows) are staged
-    uint32_t nrows;               // rows staged per plane (128 + span of the shifts using this segment)
+    int32_t row_off;              // rows [tile*128 + row_off, +nrows) are staged; gather: rows gather_rows[tile*128 + m] + row_off
+    uint32_t nrows;               // rows staged per plane (128 + span of the shifts using this segment; gather: 128)
+    uint32_t gather;              // 1: this segment's rows are picked through DenseOp::gather_rows (16-byte cp.async per row)
     uint32_t groups;              // Cin / 8 of the source map (lo planes start at plane index `groups`)
     uint32_t smem_off;            // byte offset of this segment inside a ring stage
 };
@@ -54,7 +55,10 @@ struct DenseOp {
     int32_t n_stages;        // ring stages per tile (Cin / 16; 1 for the conv1 form)
     int32_t ksteps;          // k16 steps per stage and term (1; conv1 form: ceil(taps / 2))
     uint32_t a_q_off;        // byte advance of the A view per k-step inside a stage (conv1 form: 32)
-    int32_t planes_per_seg;  // planes copied per segment and stage (4 = {hi,lo} x 2 groups; conv1 form: 2)
+    int32_t planes_per_seg;  // planes copied per segment and stage (4 = {hi,lo} x 2 groups; conv1 form: 2;
+                             // gathered conv1 form: 2 * gather_taps, plane p = {hl = p / taps, row + p % taps})
+    int32_t gather_taps;     // > 0: gathered conv1 form
+    const uint32_t* gather_rows;  // [n_tiles * 128] source row of every compact row (gather segments)
     uint32_t stage_bytes;    // bytes of one ring stage
     int32_t ring;            // ring depth
     const uint8_t* w_img;    // packed weights: tiles [stage][kstep][term][hl], each [2][N][8] bf16 (N*32 bytes)
@@ -66,6 +70,8 @@ struct DenseOp {
     int32_t mode;            // 0: ReLU -> hi/lo plane map;  1: ReLU -> fc2 -> logits
     uint8_t* out;            // mode 0: plane 0 row 0 of the output map
     unsigned long long out_plane_stride;
+    uint32_t out_groups;     // mode 0: 8-channel groups of the whole output map (lo planes start there)
+    uint32_t out_g0;         // mode 0: first group this launch writes (an op may be split over output channels)
     const float* w2;         // mode 1: [2][n]
     const float* b2;         // mode 1: [2]
     float* logits;           // mode 1: [rows][2]
@@ -91,10 +97,15 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel(const __gr
     uint64_t* t_empty = t_full + 2;         // [2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(t_empty + 2);
 
+    bool any_gather = false, any_bulk = false;
+    for (int s = 0; s < op.n_segs; ++s) {
+        any_gather |= op.seg[s].gather != 0;
+        any_bulk |= op.seg[s].gather == 0;
+    }
     if (warp == 0) {
         if (lane == 0) {
             for (int i = 0; i < op.ring; ++i) {
-                umma::mbar_init(&full[i], 1);
+                umma::mbar_init(&full[i], (any_bulk ? 1u : 0u) + (any_gather ? 32u : 0u));
                 umma::mbar_init(&empty[i], 1);
             }
             umma::mbar_init(w_full, 1);
@@ -124,27 +135,41 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel(const __gr
         }
         uint32_t slot = 0, phase = 0;
         uint32_t stage_tx = 0;
-        for (int s = 0; s < op.n_segs; ++s) stage_tx += op.seg[s].nrows * 16u * op.planes_per_seg;
+        for (int s = 0; s < op.n_segs; ++s)
+            if (!op.seg[s].gather) stage_tx += op.seg[s].nrows * 16u * op.planes_per_seg;
         for (uint32_t tile = blockIdx.x; tile < op.n_tiles; tile += gridDim.x) {
             const long long row0 = (long long)tile * kTileRows;
+            uint32_t grow[4] = {0, 0, 0, 0};
+            if (any_gather) {
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) grow[j] = __ldg(op.gather_rows + row0 + lane + 32 * j);
+            }
             for (int st = 0; st < op.n_stages; ++st) {
                 umma::mbar_wait(&empty[slot], phase ^ 1u);
                 uint8_t* stage = s_ring + (size_t)slot * op.stage_bytes;
-                if (lane == 0) {
-                    umma::mbar_arrive_expect_tx(&full[slot], stage_tx);
-                    for (int s = 0; s < op.n_segs; ++s) {
+                if (any_bulk && lane == 0) umma::mbar_arrive_expect_tx(&full[slot], stage_tx);
+                for (int s = 0; s < op.n_segs; ++s) {
                     const DenseSeg& sg = op.seg[s];
                     const uint32_t pl_bytes = sg.nrows * 16u;
                     for (int p = 0; p < op.planes_per_seg; ++p) {
-                        // planes of a stage: normal form {hi g0, hi g1, lo g0, lo g1}; conv1 form {hi, lo}
-                        const uint32_t hl = (op.planes_per_seg == 4) ? (uint32_t)(p >> 1) : (uint32_t)p;
-                        const uint32_t g = (op.planes_per_seg == 4) ? (uint32_t)(2 * st + (p & 1)) : 0u;
+                        // planes of a stage: normal form {hi g0, hi g1, lo g0, lo g1}; conv1 form {hi, lo};
+                        // gathered conv1 form {hi tap 0.., lo tap 0..}
+                        uint32_t hl, g, extra = 0;
+                        if (op.gather_taps > 0) { hl = (uint32_t)p / (uint32_t)op.gather_taps; g = 0; extra = (uint32_t)p % (uint32_t)op.gather_taps; }
+                        else if (op.planes_per_seg == 4) { hl = (uint32_t)p >> 1; g = (uint32_t)(2 * st + (p & 1)); }
+                        else { hl = (uint32_t)p; g = 0; }
                         const uint8_t* plane = sg.src + (unsigned long long)(hl * sg.groups + g) * sg.plane_stride;
                         uint8_t* dst = stage + sg.smem_off + p * pl_bytes;
-                        umma::bulk_g2s(dst, plane + (row0 + sg.row_off) * 16ll, pl_bytes, &full[slot]);
-                    }
+                        if (!sg.gather) {
+                            if (lane == 0) umma::bulk_g2s(dst, plane + (row0 + sg.row_off) * 16ll, pl_bytes, &full[slot]);
+                        } else {
+                            #pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                umma::cp_async16(dst + (lane + 32 * j) * 16u, plane + ((long long)grow[j] + sg.row_off + extra) * 16ll);
+                        }
                     }
                 }
+                if (any_gather) umma::cp_async_mbar_arrive_noinc(&full[slot]);
                 __syncwarp();
                 if (++slot == (uint32_t)op.ring) { slot = 0; phase ^= 1u; }
             }
@@ -221,7 +246,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel(const __gr
                         hi[j] = pack_bf16x2(h0, h1);
                         lo[j] = pack_bf16x2(e0, e1);
                     }
-                    const uint32_t groups = (uint32_t)op.n >> 3, g = (uint32_t)c0 >> 3;
+                    const uint32_t groups = op.out_groups, g = op.out_g0 + ((uint32_t)c0 >> 3);
                     uint8_t* p_hi = op.out + (unsigned long long)g * op.out_plane_stride + row * 16ull;
                     uint8_t* p_lo = op.out + (unsigned long long)(groups + g) * op.out_plane_stride + row * 16ull;
                     *reinterpret_cast<uint4*>(p_hi) = make_uint4(hi[0], hi[1], hi[2], hi[3]);

@@ -52,7 +52,7 @@ struct Slot {
     uint32_t* d_totals = nullptr;
     uint32_t *d_site_read = nullptr, *d_site_pos = nullptr, *d_site_out = nullptr;
     // device outputs
-    uint32_t *d_call_off = nullptr, *d_n_fwd = nullptr;
+    uint32_t *d_call_off = nullptr, *d_n_fwd = nullptr, *d_read_pref = nullptr, *h_read_pref = nullptr;
     int32_t* d_qoff = nullptr;
     uint8_t *d_ml = nullptr, *d_call_ctx = nullptr;
     float* d_logits = nullptr;
@@ -185,6 +185,7 @@ void free_slot(Slot& s)
     cudaFreeHost(s.host.base_off); cudaFreeHost(s.host.seq_off); cudaFreeHost(s.host.seq4); cudaFreeHost(s.host.flag);
     cudaFreeHost(s.host.valid); cudaFreeHost(s.host.fi); cudaFreeHost(s.host.fp); cudaFreeHost(s.host.ri); cudaFreeHost(s.host.rp);
     cudaFreeHost(s.h_chunk_read); cudaFreeHost(s.h_chunk_pos); cudaFreeHost(s.h_read_first_chunk);
+    cudaFreeHost(s.h_read_pref); cudaFree(s.d_read_pref);
     cudaFreeHost(s.h_call_off); cudaFreeHost(s.h_n_fwd); cudaFreeHost(s.h_totals); cudaFreeHost(s.h_qoff); cudaFreeHost(s.h_ml);
     void* dev[] = {s.d_seq4, s.d_fi, s.d_fp, s.d_ri, s.d_rp, s.d_valid, s.d_base_off, s.d_seq_off, s.d_flag, s.d_chunk_read,
                    s.d_chunk_pos, s.d_read_first_chunk, s.d_bcode, s.d_kinf, s.d_chunk_cnt, s.d_pref, s.d_totals, s.d_site_read,
@@ -221,6 +222,8 @@ int alloc_slot(hm_engine* e, Slot& s)
     HM_CUDA(e, st, hmalloc(&s.h_call_off, R + 1));
     HM_CUDA(e, st, hmalloc(&s.h_n_fwd, R));
     HM_CUDA(e, st, hmalloc(&s.h_totals, 8));
+    HM_CUDA(e, st, hmalloc(&s.h_read_pref, 4 * (R + 1)));
+    HM_CUDA(e, st, dmalloc(&s.d_read_pref, 4 * (R + 1)));
     HM_CUDA(e, st, hmalloc(&s.h_qoff, B));
     HM_CUDA(e, st, hmalloc(&s.h_ml, B));
     HM_CUDA(e, st, dmalloc(&s.d_seq4, seq_cap));
@@ -333,7 +336,7 @@ int stage_front(hm_engine* e, Slot& s, uint32_t& launches)
         ++launches;
     }
     hm::scan_offsets_kernel<<<1, 1024, 0, s.stream>>>(s.d_chunk_cnt, nc, s.d_pref, s.d_totals);
-    hm::read_offsets_kernel<<<(s.n_reads + 256) / 256, 256, 0, s.stream>>>(s.d_pref, s.d_read_first_chunk, s.n_reads, s.d_call_off, s.d_n_fwd);
+    hm::read_offsets_kernel<<<(s.n_reads + 256) / 256, 256, 0, s.stream>>>(s.d_pref, s.d_read_first_chunk, s.n_reads, s.d_call_off, s.d_n_fwd, s.d_read_pref);
     launches += 2;
     if (nc) {
         hm::scan_write_kernel<<<nc, hm::kChunk, 0, s.stream>>>(s.d_bcode, s.d_base_off, s.d_valid, s.d_chunk_read, s.d_chunk_pos,
@@ -343,6 +346,7 @@ int stage_front(hm_engine* e, Slot& s, uint32_t& launches)
     }
     HM_CUDA(e, "scan", cudaGetLastError());
     HM_CUDA(e, "scan", cudaMemcpyAsync(s.h_totals, s.d_totals, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+    HM_CUDA(e, "scan", cudaMemcpyAsync(s.h_read_pref, s.d_read_pref, 4 * (size_t)(s.n_reads + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
     HM_CUDA(e, "scan", cudaEventRecord(s.ev[3], s.stream));
     return HM_OK;
 }
@@ -357,7 +361,7 @@ int stage_cnn(hm_engine* e, Slot& s, uint32_t& launches)
         hm::TensorBatch tb{};
         tb.d_bcode = s.d_bcode; tb.d_kinf = s.d_kinf; tb.d_base_off = s.d_base_off;
         tb.d_site_read = s.d_site_read; tb.d_site_pos = s.d_site_pos; tb.d_site_out = s.d_site_out;
-        tb.h_base_off = s.host.base_off; tb.h_valid = s.host.valid; tb.n_reads = s.n_reads;
+        tb.h_base_off = s.host.base_off; tb.h_valid = s.host.valid; tb.h_read_pref = s.h_read_pref; tb.n_reads = s.n_reads;
         for (int k = 0; k < 4; ++k) tb.class_count[k] = s.totals[k];
         tb.d_logits = s.d_logits; tb.d_ml = s.d_ml;
         if (hm::tensor_batch_run(e->tensor, e->ctx_mask, s.tws, tb, s.stream, e->sm_count, &launches, &s.timing))
@@ -650,12 +654,12 @@ int hm_debug_dump_logits(hm_engine* e, int slot, float* out)
 
 int hm_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int cin, int cout, int n_src, const float* const* src, int n_terms,
                       const int32_t* term_src, const int32_t* term_shift, const float* weights, const float* bias, int conv1_taps,
-                      const float* w2, const float* b2, float* out)
+                      const float* w2, const float* b2, const uint32_t* gather_rows, uint32_t gather_mask, float* out)
 {
     if (!src || !term_src || !term_shift || !weights || !bias || !out) return fail(nullptr, HM_ERR_ARG, "hm_debug_dense_op: null argument");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(nullptr, HM_ERR_CUDA, "hm_debug_dense_op: no such CUDA device");
-    if (hm::tensor_debug_dense_op(device, rows, rows_alloc, cin, cout, n_src, src, n_terms, term_src, term_shift, weights, bias, conv1_taps, w2, b2, out))
+    if (hm::tensor_debug_dense_op(device, rows, rows_alloc, cin, cout, n_src, src, n_terms, term_src, term_shift, weights, bias, conv1_taps, w2, b2, gather_rows, gather_mask, out))
         return fail(nullptr, HM_ERR_CUDA, "%s", hm::tensor_last_error());
     return HM_OK;
 }
@@ -685,7 +689,7 @@ int hm_microbench(hm_engine* e, int slot, const char* name, uint32_t n_sites, in
             hm_timing keep = s.timing;
             hm::scan_count_kernel<<<std::max(s.n_chunks, 1u), hm::kChunk, 0, st>>>(s.d_bcode, s.d_base_off, s.d_valid, s.d_chunk_read, s.d_chunk_pos, e->ctx_mask, s.d_chunk_cnt);
             hm::scan_offsets_kernel<<<1, 1024, 0, st>>>(s.d_chunk_cnt, s.n_chunks, s.d_pref, s.d_totals);
-            hm::read_offsets_kernel<<<(s.n_reads + 256) / 256, 256, 0, st>>>(s.d_pref, s.d_read_first_chunk, s.n_reads, s.d_call_off, s.d_n_fwd);
+            hm::read_offsets_kernel<<<(s.n_reads + 256) / 256, 256, 0, st>>>(s.d_pref, s.d_read_first_chunk, s.n_reads, s.d_call_off, s.d_n_fwd, s.d_read_pref);
             hm::scan_write_kernel<<<std::max(s.n_chunks, 1u), hm::kChunk, 0, st>>>(s.d_bcode, s.d_base_off, s.d_valid, s.d_chunk_read, s.d_chunk_pos,
                                                                                   s.d_read_first_chunk, s.d_pref, s.n_chunks, e->ctx_mask, s.d_qoff,
                                                                                   s.d_call_ctx, s.d_site_read, s.d_site_pos, s.d_site_out);

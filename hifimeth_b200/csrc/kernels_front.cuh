@@ -196,11 +196,13 @@ scan_offsets_kernel(const ClassCount* __restrict__ chunk_cnt, uint32_t n_chunks,
 }
 
 __global__ void read_offsets_kernel(const ClassCount* __restrict__ pref, const uint32_t* __restrict__ read_first_chunk,
-                                    uint32_t n_reads, uint32_t* __restrict__ call_off, uint32_t* __restrict__ n_fwd)
+                                    uint32_t n_reads, uint32_t* __restrict__ call_off, uint32_t* __restrict__ n_fwd,
+                                    uint32_t* __restrict__ read_pref)
 {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r > n_reads) return;
     ClassCount a = pref[read_first_chunk[r]];  // read_first_chunk[n_reads] = n_chunks
+    reinterpret_cast<ClassCount*>(read_pref)[r] = a;  // per-class sites in reads before r (sub-batching of the CNN stage)
     call_off[r] = a.c[0] + a.c[1] + a.c[2] + a.c[3];
     if (r < n_reads) {
         ClassCount b = pref[read_first_chunk[r + 1]];

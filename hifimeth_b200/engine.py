@@ -94,7 +94,7 @@ def load_library() -> C.CDLL:
     L.hm_debug_dump_features.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, _f32p]
     L.hm_debug_dump_logits.argtypes = [C.c_void_p, C.c_int, _f32p]
     L.hm_debug_dense_op.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(_f32p), C.c_int, _i32p, _i32p,
-                                    _f32p, _f32p, C.c_int, _f32p, _f32p, _f32p]
+                                    _f32p, _f32p, C.c_int, _f32p, _f32p, _u32p, C.c_uint32, _f32p]
     L.hm_microbench.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_uint32, C.c_int, _f32p, C.POINTER(C.c_double),
                                 C.POINTER(C.c_double)]
     _lib = L
@@ -282,11 +282,13 @@ def pack_records_host(bodies, min_read_len: int = 1000, max_bases: int = None):
                      arr["valid"][:n.value], arr["fi"][:nb], arr["fp"][:nb], arr["ri"][:nb], arr["rp"][:nb])
 
 
-def debug_dense_op(srcs, terms, bias, rows: int, conv1_taps: int = 0, w2=None, b2=None, device: int = 0) -> np.ndarray:
+def debug_dense_op(srcs, terms, bias, rows: int, conv1_taps: int = 0, w2=None, b2=None, gather_rows=None, gather_mask: int = 0,
+                   device: int = 0) -> np.ndarray:
     """hm_debug_dense_op: one op of the tensor-core dense plan on caller data (unit test of dense_gemm_kernel).
 
     srcs: list of [rows_alloc, cin] f32 maps; terms: list of (src index, row shift, W) with W [cin, cout]
-    (conv1 form: one term, W [taps, 8, cout]); returns [rows, cout] f32, or [rows, 2] when w2/b2 select the head form."""
+    (conv1 form: one term, W [taps, 8, cout]); returns [rows, cout] f32, or [rows, 2] when w2/b2 select the head form.
+    gather_rows [rows] u32 + gather_mask: terms whose bit is set read row gather_rows[r] + shift (compact ops)."""
     L = load_library()
     srcs = [np.ascontiguousarray(a, np.float32) for a in srcs]
     rows_alloc, cin = srcs[0].shape
@@ -297,6 +299,7 @@ def debug_dense_op(srcs, terms, bias, rows: int, conv1_taps: int = 0, w2=None, b
     tsh = np.array([t[1] for t in terms], np.int32)
     ptrs = (_f32p * len(srcs))(*[a.ctypes.data_as(_f32p) for a in srcs])
     head = w2 is not None
+    gr = np.ascontiguousarray(gather_rows, np.uint32) if gather_rows is not None else None
     out = np.empty((rows, 2 if head else cout), np.float32)
     if head:
         w2 = np.ascontiguousarray(w2, np.float32)
@@ -304,7 +307,7 @@ def debug_dense_op(srcs, terms, bias, rows: int, conv1_taps: int = 0, w2=None, b
     rc = L.hm_debug_dense_op(device, rows, rows_alloc, cin, cout, len(srcs), ptrs, len(terms), tsrc.ctypes.data_as(_i32p),
                              tsh.ctypes.data_as(_i32p), w.ctypes.data_as(_f32p), bias.ctypes.data_as(_f32p), conv1_taps,
                              w2.ctypes.data_as(_f32p) if head else None, b2.ctypes.data_as(_f32p) if head else None,
-                             out.ctypes.data_as(_f32p))
+                             gr.ctypes.data_as(_u32p) if gr is not None else None, gather_mask, out.ctypes.data_as(_f32p))
     if rc != 0:
         raise HmError(f"hm_debug_dense_op failed ({rc}): {L.hm_last_error(None).decode()}")
     return out

@@ -164,10 +164,12 @@ int hm_debug_dump_logits(hm_engine* e, int slot, float* out);
  *   out[r][:] = relu(bias + sum_k src[term_src[k]][r + term_shift[k]][:] . W_k),  r < rows (multiple of 128)
  * src maps are [rows_alloc][cin] f32, W_k = weights + k*cin*cout as [cin][cout].  conv1_taps > 0 selects the conv1 form:
  * cin = 8, one term, weights [taps][8][cout], rows r + shift .. r + shift + taps - 1.  w2 != NULL selects the head
- * form: out = [rows][2] = relu(...) . w2^T + b2 with w2 [2][cout].  Arithmetic: bf16 hi/lo split, fp32 accumulate. */
+ * form: out = [rows][2] = relu(...) . w2^T + b2 with w2 [2][cout].  Bit k of gather_mask makes term k read row
+ * gather_rows[r] + term_shift[k] instead of r + term_shift[k] (the compact ops of the plan; gather_rows [rows]).
+ * Arithmetic: bf16 hi/lo split, fp32 accumulate. */
 int hm_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int cin, int cout, int n_src, const float* const* src,
                       int n_terms, const int32_t* term_src, const int32_t* term_shift, const float* weights, const float* bias,
-                      int conv1_taps, const float* w2, const float* b2, float* out);
+                      int conv1_taps, const float* w2, const float* b2, const uint32_t* gather_rows, uint32_t gather_mask, float* out);
 
 /* ---- kernel microbenchmarks (BASELINE.json config 5) --------------------------------------------------- */
 /* Runs one named kernel family `iters` times on the slot's resident inputs and returns the mean device

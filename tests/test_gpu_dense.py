@@ -86,3 +86,54 @@ def test_dense_op_head_form(lib_built):
     want = h @ w2.astype(np.float64).T + b2
     got = hme.debug_dense_op(srcs, terms, bias, rows, w2=w2, b2=b2)
     assert np.abs(got - want).max() < 2e-4 * np.abs(h).sum(axis=1).max()
+
+
+# ---- compact ops: rows picked through a site-row index (cp.async gather producer) ----------------------------------------
+
+def _gather_ref(srcs, terms, gmask, grows, bias, rows):
+    acc = np.tile(np.asarray(bias, np.float64), (rows, 1))
+    scale = np.zeros((rows, len(bias)))
+    for k, (si, sh, w) in enumerate(terms):
+        a = srcs[si][grows + sh] if (gmask >> k) & 1 else srcs[si][sh:sh + rows]
+        acc += a.astype(np.float64) @ np.asarray(w, np.float64)
+        scale += np.abs(a).astype(np.float64) @ np.abs(w).astype(np.float64)
+    return np.maximum(acc, 0), scale.max(axis=1)
+
+
+@pytest.mark.parametrize("cin,cout,shifts,gmask,n_src", [
+    (96, 64, [2, 66, 130], 0b111, 1),   # T7_1: three gathered views of Y6
+    (128, 128, [0, 2], 0b10, 2),        # F2: compact F1 (direct) + Y1 gathered at +2
+    (128, 96, [370, 378, 0], 0b011, 2),  # G4 (k = 11): two gathered Y3 rows + compact G3
+    (64, 64, [0, 0, 0], 0, 3),          # T8_1: all direct
+])
+def test_compact_op_gather(lib_built, cin, cout, shifts, gmask, n_src):
+    rng = np.random.default_rng(cin * 7 + cout + gmask)
+    rows, rows_alloc = 128 * 9, 6000
+    srcs = [rng.standard_normal((rows_alloc, cin)).astype(np.float32) for _ in range(n_src)]
+    src_of = [0, 0, 1] if (n_src == 2 and len(shifts) == 3) else ([0, 1] if n_src == 2 else ([0, 1, 2] if n_src == 3 else [0, 0, 0]))
+    if n_src == 2 and len(shifts) == 2:
+        src_of = [1, 0]  # direct term reads the compact map (src 1), gathered term the dense map (src 0)
+    terms = [(src_of[k], sh, (rng.standard_normal((cin, cout)) / np.sqrt(cin)).astype(np.float32)) for k, sh in enumerate(shifts)]
+    bias = rng.standard_normal(cout).astype(np.float32)
+    grows = np.sort(rng.integers(0, rows_alloc - 400, size=rows)).astype(np.uint32)
+    want, scale = _gather_ref(srcs, terms, gmask, grows, bias, rows)
+    got = hme.debug_dense_op(srcs, terms, bias, rows, gather_rows=grows, gather_mask=gmask)
+    _check(got, want, scale)
+
+
+@pytest.mark.parametrize("taps,shift", [(11, 0), (11, 392), (13, 390)])
+def test_compact_op_conv1_gather(lib_built, taps, shift):
+    rng = np.random.default_rng(taps * 3 + shift)
+    rows, rows_alloc = 128 * 5, 4000
+    x = rng.random((rows_alloc, 8)).astype(np.float32)
+    w = (rng.standard_normal((taps, 8, 128)) / 9).astype(np.float32)
+    bias = rng.standard_normal(128).astype(np.float32)
+    grows = rng.integers(0, rows_alloc - shift - 16, size=rows).astype(np.uint32)
+    acc = np.tile(bias.astype(np.float64), (rows, 1))
+    scale = np.zeros(rows)
+    for j in range(taps):
+        a = x[grows + shift + j]
+        acc += a.astype(np.float64) @ w[j].astype(np.float64)
+        scale += (np.abs(a).astype(np.float64) @ np.abs(w[j]).astype(np.float64)).max(axis=1)
+    got = hme.debug_dense_op([x], [(0, shift, w)], bias, rows, conv1_taps=taps, gather_rows=grows, gather_mask=1)
+    _check(got, np.maximum(acc, 0), scale)
