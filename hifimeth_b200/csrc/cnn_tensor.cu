@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -43,6 +44,7 @@ constexpr int kHaloL = 208;   // rows before strand position 0 (>= 201, multiple
 constexpr int kHaloR = 200;   // zero-feature rows after the last strand position
 constexpr int kSlackRows = 1024;  // rows past the sub-batch every plane keeps allocated (shifted reads of the last tile)
 constexpr size_t kSmemMax = 232448;
+constexpr size_t kSmemAux = 3456;  // barriers + bias / fc2 staging of dense_gemm_kernel
 
 // Default: dense Y chain + F/G/tail ops evaluated at site rows only ("compact").  HM_DENSE_ALL=1 evaluates every op on
 // every row (the first version of this path; kept for A/B measurements).
@@ -328,8 +330,8 @@ bool lower_op(const HostOp& h, int n0, int n, DevOp& d, std::vector<uint8_t>& bl
             }
     p.w_bytes = (uint32_t)(img.size() * 2);
     const size_t w_al = (p.w_bytes + 127u) & ~127u;
-    if (w_al + 2 * (size_t)p.stage_bytes + 256 > kSmemMax) { err = "fit"; return false; }
-    p.ring = (int)std::min<size_t>(8, (kSmemMax - 256 - w_al) / p.stage_bytes);
+    if (w_al + 2 * (size_t)p.stage_bytes + kSmemAux > kSmemMax) { err = "fit"; return false; }
+    p.ring = (int)std::min<size_t>(kProducerWarps, (kSmemMax - kSmemAux - w_al) / p.stage_bytes);  // producer warp s owns slot s
     d.smem = dense_smem_bytes(p);
     auto append = [&](const void* src, size_t bytes) {
         size_t o = (blob.size() + 255) & ~(size_t)255;
@@ -357,6 +359,7 @@ void bind_blob(DevOp& d, const uint8_t* blob)
 }
 
 bool g_attr_set = false;
+float g_debug_op_ms = 0.f;
 int ensure_kernel_attr()
 {
     if (g_attr_set) return 0;
@@ -751,6 +754,8 @@ float tensor_last_dense_ms(TensorWorkspace& w)
     return ms;
 }
 
+float tensor_debug_last_op_ms() { return g_debug_op_ms; }
+
 // ---- unit-test hook: one op on caller-provided fp32 maps ------------------------------------------------------------------------
 int tensor_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int cin, int cout, int n_src, const float* const* src, int n_terms,
                           const int32_t* term_src, const int32_t* term_shift, const float* weights, const float* bias, int conv1_taps,
@@ -828,9 +833,33 @@ int tensor_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int ci
     p.logits = d_logit;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    dense_gemm_kernel<<<std::min<uint32_t>(p.n_tiles, (uint32_t)sms), kDenseThreads, d.smem>>>(p);
+    if (const char* v = getenv("HM_DENSE_VARIANT")) p.variant = (uint32_t)atoi(v);
+    long long* d_dbg = nullptr;
+    if (p.variant & 32u) { cudaMalloc((void**)&d_dbg, 1024 * 8); cudaMemset(d_dbg, 0, 1024 * 8); p.dbg = d_dbg; }
+    if (const char* v = getenv("HM_DENSE_RING")) p.ring = std::min(p.ring, std::max(2, atoi(v)));
+    const int reps = getenv("HM_DENSE_REPS") ? atoi(getenv("HM_DENSE_REPS")) : 1;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    if (p.variant) cudaFuncSetAttribute(dense_gemm_kernel_dbg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+    for (int i = 0; i < reps; ++i) {
+        if (i == std::max(0, reps - 10)) cudaEventRecord(e0);
+        if (p.variant) dense_gemm_kernel_dbg<<<std::min<uint32_t>(p.n_tiles, (uint32_t)sms), kDenseThreads, d.smem>>>(p);
+        else dense_gemm_kernel<<<std::min<uint32_t>(p.n_tiles, (uint32_t)sms), kDenseThreads, d.smem>>>(p);
+    }
+    cudaEventRecord(e1);
     TCUDA("debug op launch", cudaGetLastError());
     TCUDA("debug op run", cudaDeviceSynchronize());
+    cudaEventElapsedTime(&g_debug_op_ms, e0, e1);
+    g_debug_op_ms /= (float)std::min(reps, 10);
+    if (d_dbg) {
+        std::vector<long long> h(1024);
+        cudaMemcpy(h.data(), d_dbg, 1024 * 8, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "stage: issue  full-seen  stage-done  (cycles from first issue)\n");
+        for (int i = 16; i < 48; ++i) fprintf(stderr, "%3d: %8lld %8lld %8lld  latency %6lld\n", i, h[i] - h[0], h[256 + i] - h[0], h[512 + i] - h[0], h[256 + i] - h[i]);
+        for (int i = 0; i < 8; ++i) fprintf(stderr, "tile %d: t_empty wait %lld -> %lld\n", i, h[768 + 2 * i] - h[0], h[768 + 2 * i + 1] - h[0]);
+        cudaFree(d_dbg);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (h.head) {
         TCUDA("debug op", cudaMemcpy(out, d_logit, (size_t)rows * 2 * sizeof(float), cudaMemcpyDeviceToHost));
     } else {

@@ -61,4 +61,7 @@ int tensor_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int ci
                           int n_terms, const int32_t* term_src, const int32_t* term_shift, const float* weights, const float* bias,
                           int conv1_taps, const float* w2, const float* b2, const uint32_t* gather_rows, uint32_t gather_mask, float* out);
 
+// Device time (ms) of the kernel launched by the last tensor_debug_dense_op.
+float tensor_debug_last_op_ms();
+
 }  // namespace hm

@@ -13,10 +13,12 @@
 // (8 rows x 16 B, SWIZZLE_NONE, K-major), so a convolution tap is a descriptor whose start address is advanced by
 // shift * 16 bytes -- no im2col, no re-load per tap.
 //
-// CTA = 6 warps, persistent over tiles (grid = #SMs):
-//   warp 0    producer: weights once (resident for the whole launch), then the activation ring
-//   warp 1    MMA issuer (one elected lane): 3 tcgen05.mma per term and k-step, commit -> ring slot free
-//   warps 2-5 epilogue: tcgen05.ld the fp32 accumulator (double buffered in TMEM), bias + ReLU, split to hi/lo
+// CTA = 13 warps, persistent over tiles (grid = #SMs):
+//   warps 0-7 producers: weights once (resident for the whole launch), then the activation ring; ring slot s is always
+//             filled by warp s (a warp has one bulk-copy instruction in flight at a time, tools/bulk_copy_probe.cu, so
+//             the number of stages in flight is the number of producer warps)
+//   warp 8    MMA issuer (one elected lane): 3 tcgen05.mma per term and k-step, commit -> ring slot free
+//   warps 9-12 epilogue: tcgen05.ld the fp32 accumulator (double buffered in TMEM), bias + ReLU, split to hi/lo
 //             bf16, coalesced 16-byte stores in plane layout (or the fc2 head -> logits)
 #pragma once
 #include <cstdint>
@@ -30,7 +32,8 @@ namespace hm {
 constexpr int kTileRows = 128;
 constexpr int kMaxTerms = 3;
 constexpr int kMaxSegs = 3;
-constexpr int kDenseThreads = 192;
+constexpr int kProducerWarps = 8;
+constexpr int kDenseThreads = 32 * (kProducerWarps + 1 + 4);
 
 struct DenseSeg {
     const uint8_t* src;           // plane 0 (hi, g = 0), row 0 of the input map
@@ -75,6 +78,8 @@ struct DenseOp {
     const float* w2;         // mode 1: [2][n]
     const float* b2;         // mode 1: [2]
     float* logits;           // mode 1: [rows][2]
+    long long* dbg;          // variant & 32: CTA 0 writes clock64 stamps: [0..255] stage issue, [256..511] stage full seen by the MMA warp
+    uint32_t variant;        // experiments (tools/dense_microbench.py): 1 = hi*hi pass only, 2 = no MMA, 4 = no epilogue stores, 8 = no epilogue work, 16 = plain arrive instead of tcgen05.commit on the ring (only with 2), 64 = producers free-run (no consumer)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b)
@@ -83,8 +88,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
 }
 
 // Shared memory: [weights image][ring stages][barriers]
-__global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel(const __grid_constant__ DenseOp op)
+template <bool kDbg>
+__global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel_t(const __grid_constant__ DenseOp op)
 {
+    const uint32_t variant = kDbg ? op.variant : 0u;  // experiment switches compile away in the product instantiation
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* s_w = smem;
@@ -96,6 +103,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel(const __gr
     uint64_t* t_full = w_full + 1;          // [2]
     uint64_t* t_empty = t_full + 2;         // [2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(t_empty + 2);
+    float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(t_empty + 3) + 15) & ~(uintptr_t)15);  // [768]: bias | fc2 row 0 | fc2 row 1
 
     bool any_gather = false, any_bulk = false;
     for (int s = 0; s < op.n_segs; ++s) {
@@ -124,19 +132,31 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel(const __gr
     const uint32_t tmem_base = *s_tmem;
     const uint32_t acc_stride = op.tmem_cols >> 1;
 
-    if (warp == 0) {
-        // ===================================== producer =====================================================
-        if (lane == 0) {
-            umma::mbar_arrive_expect_tx(w_full, op.w_bytes);
-            for (uint32_t off = 0; off < op.w_bytes; off += 32768u) {
-                uint32_t n = min(32768u, op.w_bytes - off);
-                umma::bulk_g2s(s_w + off, op.w_img + off, n, w_full);
-            }
+    if (warp < (uint32_t)kProducerWarps) {
+        // ===================================== producers ====================================================
+        if (warp == 0) {
+            if (lane == 0) umma::mbar_arrive_expect_tx(w_full, op.w_bytes);
+            __syncwarp();
+            const uint32_t per = (((op.w_bytes + 31u) / 32u) + 15u) & ~15u;  // one copy per lane, one instruction
+            const uint32_t off = lane * per;
+            if (off < op.w_bytes) umma::bulk_g2s(s_w + off, op.w_img + off, min(per, op.w_bytes - off), w_full);
         }
-        uint32_t slot = 0, phase = 0;
-        uint32_t stage_tx = 0;
+        // Bulk copies issued by one warp execute one INSTRUCTION at a time (about one memory latency each, however many
+        // lanes take part): 1 lane x 2 KB per instruction = 0.75 TB/s chip-wide, 32 lanes = 6.7 TB/s, 8 warps x 1 lane =
+        // 6.2 TB/s (tools/bulk_copy_probe.cu).  So all copies of a stage leave in one instruction (lane c issues copy c)
+        // and consecutive stages are filled by different warps.
+        // A ring slot must always be filled by the same warp (parity waits are only valid one phase ahead): warp s owns
+        // slot s, ring <= kProducerWarps.
+        const uint32_t n_prod = (uint32_t)op.ring;
+        uint32_t stage_no = 0;
+        uint32_t stage_tx = 0, ncopies = 0;
+        int bulk_seg[kMaxSegs] = {0, 0, 0};
         for (int s = 0; s < op.n_segs; ++s)
-            if (!op.seg[s].gather) stage_tx += op.seg[s].nrows * 16u * op.planes_per_seg;
+            if (!op.seg[s].gather) {
+                stage_tx += op.seg[s].nrows * 16u * op.planes_per_seg;
+                bulk_seg[ncopies / (uint32_t)op.planes_per_seg] = s;
+                ncopies += (uint32_t)op.planes_per_seg;
+            }
         for (uint32_t tile = blockIdx.x; tile < op.n_tiles; tile += gridDim.x) {
             const long long row0 = (long long)tile * kTileRows;
             uint32_t grow[4] = {0, 0, 0, 0};
@@ -144,83 +164,124 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel(const __gr
                 #pragma unroll
                 for (int j = 0; j < 4; ++j) grow[j] = __ldg(op.gather_rows + row0 + lane + 32 * j);
             }
-            for (int st = 0; st < op.n_stages; ++st) {
-                umma::mbar_wait(&empty[slot], phase ^ 1u);
+            for (int st = 0; st < op.n_stages; ++st, ++stage_no) {
+                if (stage_no % n_prod != warp) continue;
+                const uint32_t slot = stage_no % (uint32_t)op.ring, phase = (stage_no / (uint32_t)op.ring) & 1u;
+                if (variant & 64u) { if (stage_no >= n_prod) umma::mbar_wait(&full[slot], phase ^ 1u); }
+                else umma::mbar_wait(&empty[slot], phase ^ 1u);
                 uint8_t* stage = s_ring + (size_t)slot * op.stage_bytes;
-                if (any_bulk && lane == 0) umma::mbar_arrive_expect_tx(&full[slot], stage_tx);
-                for (int s = 0; s < op.n_segs; ++s) {
-                    const DenseSeg& sg = op.seg[s];
-                    const uint32_t pl_bytes = sg.nrows * 16u;
-                    for (int p = 0; p < op.planes_per_seg; ++p) {
-                        // planes of a stage: normal form {hi g0, hi g1, lo g0, lo g1}; conv1 form {hi, lo};
-                        // gathered conv1 form {hi tap 0.., lo tap 0..}
-                        uint32_t hl, g, extra = 0;
-                        if (op.gather_taps > 0) { hl = (uint32_t)p / (uint32_t)op.gather_taps; g = 0; extra = (uint32_t)p % (uint32_t)op.gather_taps; }
-                        else if (op.planes_per_seg == 4) { hl = (uint32_t)p >> 1; g = (uint32_t)(2 * st + (p & 1)); }
-                        else { hl = (uint32_t)p; g = 0; }
+                if (any_bulk) {
+                    if (lane == 0) umma::mbar_arrive_expect_tx(&full[slot], stage_tx);
+                    if ((variant & 32u) && blockIdx.x == 0 && lane == 0 && stage_no < 256) op.dbg[stage_no] = clock64();
+                    __syncwarp();
+                    const uint32_t c = lane;  // this lane's copy of the stage, if < ncopies
+                    if (c < ncopies) {
+                        const uint32_t p = c % (uint32_t)op.planes_per_seg;
+                        const DenseSeg& sg = op.seg[bulk_seg[c / (uint32_t)op.planes_per_seg]];
+                        // planes of a stage: normal form {hi g0, hi g1, lo g0, lo g1}; conv1 form {hi, lo}
+                        const uint32_t hl = (op.planes_per_seg == 4) ? (p >> 1) : p;
+                        const uint32_t g = (op.planes_per_seg == 4) ? (uint32_t)(2 * st) + (p & 1u) : 0u;
+                        const uint32_t pl_bytes = sg.nrows * 16u;
                         const uint8_t* plane = sg.src + (unsigned long long)(hl * sg.groups + g) * sg.plane_stride;
-                        uint8_t* dst = stage + sg.smem_off + p * pl_bytes;
-                        if (!sg.gather) {
-                            if (lane == 0) umma::bulk_g2s(dst, plane + (row0 + sg.row_off) * 16ll, pl_bytes, &full[slot]);
-                        } else {
+                        umma::bulk_g2s(stage + sg.smem_off + p * pl_bytes, plane + (row0 + sg.row_off) * 16ll, pl_bytes, &full[slot]);
+                    }
+                }
+                if (any_gather) {
+                    for (int s = 0; s < op.n_segs; ++s) {
+                        const DenseSeg& sg = op.seg[s];
+                        if (!sg.gather) continue;
+                        const uint32_t pl_bytes = sg.nrows * 16u;
+                        for (int p = 0; p < op.planes_per_seg; ++p) {
+                            // normal form {hi g0, hi g1, lo g0, lo g1}; gathered conv1 form {hi tap 0.., lo tap 0..}
+                            uint32_t hl, g, extra = 0;
+                            if (op.gather_taps > 0) { hl = (uint32_t)p / (uint32_t)op.gather_taps; g = 0; extra = (uint32_t)p % (uint32_t)op.gather_taps; }
+                            else { hl = (uint32_t)p >> 1; g = (uint32_t)(2 * st + (p & 1)); }
+                            const uint8_t* plane = sg.src + (unsigned long long)(hl * sg.groups + g) * sg.plane_stride;
+                            uint8_t* dst = stage + sg.smem_off + p * pl_bytes;
                             #pragma unroll
                             for (int j = 0; j < 4; ++j)
                                 umma::cp_async16(dst + (lane + 32 * j) * 16u, plane + ((long long)grow[j] + sg.row_off + extra) * 16ll);
                         }
                     }
+                    umma::cp_async_mbar_arrive_noinc(&full[slot]);
                 }
-                if (any_gather) umma::cp_async_mbar_arrive_noinc(&full[slot]);
                 __syncwarp();
-                if (++slot == (uint32_t)op.ring) { slot = 0; phase ^= 1u; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == (uint32_t)kProducerWarps) {
         // ===================================== MMA issuer ===================================================
+        // One lane issues every tcgen05.mma of the CTA, so the per-MMA instruction count matters: all descriptors are
+        // built once and advanced by adding 16-byte units to their address field (bits [0,14), never carries out).
         const uint32_t idesc = umma::make_idesc_bf16_m128((uint32_t)op.n);
-        const uint32_t w_tile = (uint32_t)op.n * 32u;
-        const uint32_t b_lbo = (uint32_t)op.n * 16u;
-        const uint32_t s_w_addr = umma::smem_u32(s_w);
+        // Only the low word of a descriptor changes (address bits [0,14), LBO bits [16,30)); the high word (SBO, version)
+        // is the same for every operand, so descriptor arithmetic is 32-bit adds on the low word.
+        const uint32_t desc_hi = (uint32_t)(umma::make_desc(0, 0, 128) >> 32);
+        const uint32_t b_step = ((uint32_t)op.n * 32u) >> 4;                 // one weight tile, in descriptor units
+        const uint32_t b_base = (uint32_t)umma::make_desc(umma::smem_u32(s_w), (uint32_t)op.n * 16u, 128);
+        const uint32_t ring16 = umma::smem_u32(s_ring) >> 4, stage16 = op.stage_bytes >> 4, aq16 = op.a_q_off >> 4;
+        uint32_t a_hi[kMaxTerms], a_lo[kMaxTerms];
+        #pragma unroll
+        for (int k = 0; k < kMaxTerms; ++k) {
+            a_hi[k] = (uint32_t)umma::make_desc(op.term[k].a_off, op.term[k].a_lbo, 128);
+            a_lo[k] = (uint32_t)umma::make_desc(op.term[k].a_off + op.term[k].a_hl_off, op.term[k].a_lbo, 128);
+        }
+        const int n_terms = op.n_terms, ksteps = op.ksteps, n_stages = op.n_stages, ring = op.ring;
         umma::mbar_wait(w_full, 0);
         uint32_t slot = 0, phase = 0, it = 0;
         for (uint32_t tile = blockIdx.x; tile < op.n_tiles; tile += gridDim.x, ++it) {
             const uint32_t buf = it & 1u, use = it >> 1;
+            if ((variant & 32u) && blockIdx.x == 0 && lane == 0 && it < 32) op.dbg[768 + 2 * it] = clock64();
             umma::mbar_wait(&t_empty[buf], (use & 1u) ^ 1u);
             umma::tc_fence_after();
+            if ((variant & 32u) && blockIdx.x == 0 && lane == 0 && it < 32) op.dbg[768 + 2 * it + 1] = clock64();
             const uint32_t d_addr = tmem_base + buf * acc_stride;
-            uint32_t first = 1;
-            for (int st = 0; st < op.n_stages; ++st) {
+            uint32_t acc = 0;
+            uint32_t b_cur = b_base;
+            for (int st = 0; st < n_stages; ++st) {
+                if (variant & 64u) continue;
                 umma::mbar_wait(&full[slot], phase);
                 umma::tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t stage_addr = umma::smem_u32(s_ring + (size_t)slot * op.stage_bytes);
-                    for (int q = 0; q < op.ksteps; ++q) {
-                        for (int k = 0; k < op.n_terms; ++k) {
-                            const DenseTerm& tm = op.term[k];
-                            const uint32_t a_hi = stage_addr + tm.a_off + q * op.a_q_off;
-                            const uint32_t a_lo = a_hi + tm.a_hl_off;
-                            const uint32_t wt = s_w_addr + (uint32_t)(((st * op.ksteps + q) * op.n_terms + k) * 2) * w_tile;
-                            const uint64_t da_hi = umma::make_desc(a_hi, tm.a_lbo, 128);
-                            const uint64_t da_lo = umma::make_desc(a_lo, tm.a_lbo, 128);
-                            const uint64_t db_hi = umma::make_desc(wt, b_lbo, 128);
-                            const uint64_t db_lo = umma::make_desc(wt + w_tile, b_lbo, 128);
-                            umma::mma_bf16(d_addr, da_hi, db_hi, idesc, first ^ 1u);
-                            first = 0;
-                            umma::mma_bf16(d_addr, da_lo, db_hi, idesc, 1);
-                            umma::mma_bf16(d_addr, da_hi, db_lo, idesc, 1);
+                if ((variant & 32u) && blockIdx.x == 0 && lane == 0 && it * n_stages + st < 256) op.dbg[256 + it * n_stages + st] = clock64();
+                if (umma::elect_one()) {
+                    uint32_t sa = ring16 + slot * stage16, bq = b_cur;
+                    uint32_t a0 = acc;
+                    for (int q = 0; q < ksteps; ++q, sa += aq16) {
+                        #pragma unroll
+                        for (int k = 0; k < kMaxTerms; ++k) {
+                            if (k < n_terms) {
+                                if (!(variant & 2u)) umma::mma_bf16_w(d_addr, a_hi[k] + sa, bq, desc_hi, idesc, a0);
+                                a0 = 1;
+                                if (!(variant & 3u)) {
+                                    umma::mma_bf16_w(d_addr, a_lo[k] + sa, bq, desc_hi, idesc, 1);
+                                    umma::mma_bf16_w(d_addr, a_hi[k] + sa, bq + b_step, desc_hi, idesc, 1);
+                                }
+                                bq += 2 * b_step;
+                            }
                         }
                     }
-                    umma::mma_commit(&empty[slot]);
+                    if (variant & 16u) umma::mbar_arrive(&empty[slot]);
+                    else umma::mma_commit(&empty[slot]);
                 }
+                acc = 1;
+                b_cur += 2 * b_step * (uint32_t)(ksteps * n_terms);
                 __syncwarp();
-                if (++slot == (uint32_t)op.ring) { slot = 0; phase ^= 1u; }
+                if ((variant & 32u) && blockIdx.x == 0 && lane == 0 && it * n_stages + st < 256) op.dbg[512 + it * n_stages + st] = clock64();
+                if (++slot == (uint32_t)ring) { slot = 0; phase ^= 1u; }
             }
-            if (lane == 0) umma::mma_commit(&t_full[buf]);
+            if (umma::elect_one()) umma::mma_commit(&t_full[buf]);
             __syncwarp();
         }
     } else {
         // ===================================== epilogue ======================================================
         const uint32_t lane_grp = (warp & 3u) * 32u;  // TMEM lanes this warp may touch
         const uint32_t m = lane_grp + lane;            // row of the tile
+        const int n = op.n;
+        // bias (and the fc2 weights of the head form) live in shared memory for the whole launch
+        for (int i = (int)threadIdx.x - 32 * (kProducerWarps + 1); i < n; i += 128) {
+            s_bias[i] = __ldg(op.bias + i);
+            if (op.mode == 1) { s_bias[256 + i] = __ldg(op.w2 + i); s_bias[512 + i] = __ldg(op.w2 + n + i); }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         uint32_t it = 0;
         for (uint32_t tile = blockIdx.x; tile < op.n_tiles; tile += gridDim.x, ++it) {
             const uint32_t buf = it & 1u, use = it >> 1;
@@ -229,35 +290,42 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel(const __gr
             const uint32_t t_addr = tmem_base + (lane_grp << 16) + buf * acc_stride;
             const unsigned long long row = (unsigned long long)tile * kTileRows + m;
             float l0 = 0.f, l1 = 0.f;
-            for (int c0 = 0; c0 < op.n; c0 += 16) {
-                uint32_t v[16];
-                umma::tmem_ld16(t_addr + (uint32_t)c0, v);
+            for (int c0 = 0; c0 < n && !(variant & 8u); c0 += 32) {
+                uint32_t v[32];
+                umma::tmem_ld32(t_addr + (uint32_t)c0, v);
                 umma::tmem_ld_wait();
-                float f[16];
+                float f[32];
                 #pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = fmaxf(__uint_as_float(v[j]) + __ldg(op.bias + c0 + j), 0.f);
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 bv = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+                    f[j] = fmaxf(__uint_as_float(v[j]) + bv.x, 0.f);
+                    f[j + 1] = fmaxf(__uint_as_float(v[j + 1]) + bv.y, 0.f);
+                    f[j + 2] = fmaxf(__uint_as_float(v[j + 2]) + bv.z, 0.f);
+                    f[j + 3] = fmaxf(__uint_as_float(v[j + 3]) + bv.w, 0.f);
+                }
                 if (op.mode == 0) {
-                    uint32_t hi[8], lo[8];
+                    const uint32_t g0 = op.out_g0 + ((uint32_t)c0 >> 3);
+                    uint8_t* p_hi = op.out + (unsigned long long)g0 * op.out_plane_stride + row * 16ull;
+                    uint8_t* p_lo = p_hi + (unsigned long long)op.out_groups * op.out_plane_stride;
                     #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * j]), h1 = __float2bfloat16_rn(f[2 * j + 1]);
-                        __nv_bfloat16 e0 = __float2bfloat16_rn(f[2 * j] - __bfloat162float(h0));
-                        __nv_bfloat16 e1 = __float2bfloat16_rn(f[2 * j + 1] - __bfloat162float(h1));
-                        hi[j] = pack_bf16x2(h0, h1);
-                        lo[j] = pack_bf16x2(e0, e1);
+                    for (int g = 0; g < 4; ++g) {
+                        uint32_t hi[4], lo[4];
+                        #pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float x0 = f[8 * g + 2 * j], x1 = f[8 * g + 2 * j + 1];
+                            const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                            hi[j] = pack_bf16x2(h0, h1);
+                            lo[j] = pack_bf16x2(__float2bfloat16_rn(x0 - __bfloat162float(h0)), __float2bfloat16_rn(x1 - __bfloat162float(h1)));
+                        }
+                        if (variant & 4u) continue;
+                        *reinterpret_cast<uint4*>(p_hi + g * op.out_plane_stride) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(p_lo + g * op.out_plane_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
-                    const uint32_t groups = op.out_groups, g = op.out_g0 + ((uint32_t)c0 >> 3);
-                    uint8_t* p_hi = op.out + (unsigned long long)g * op.out_plane_stride + row * 16ull;
-                    uint8_t* p_lo = op.out + (unsigned long long)(groups + g) * op.out_plane_stride + row * 16ull;
-                    *reinterpret_cast<uint4*>(p_hi) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4*>(p_hi + op.out_plane_stride) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                    *reinterpret_cast<uint4*>(p_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    *reinterpret_cast<uint4*>(p_lo + op.out_plane_stride) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                 } else {
                     #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        l0 = fmaf(f[j], __ldg(op.w2 + c0 + j), l0);
-                        l1 = fmaf(f[j], __ldg(op.w2 + op.n + c0 + j), l1);
+                    for (int j = 0; j < 32; ++j) {
+                        l0 = fmaf(f[j], s_bias[256 + c0 + j], l0);
+                        l1 = fmaf(f[j], s_bias[512 + c0 + j], l1);
                     }
                 }
             }
@@ -275,9 +343,13 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel(const __gr
     if (warp == 0) umma::tmem_dealloc(tmem_base, op.tmem_cols);
 }
 
+// Product instantiation (no experiment switches) and the one tools/dense_microbench.py drives.
+#define dense_gemm_kernel dense_gemm_kernel_t<false>
+#define dense_gemm_kernel_dbg dense_gemm_kernel_t<true>
+
 inline size_t dense_smem_bytes(const DenseOp& op)
 {
-    return ((op.w_bytes + 127u) & ~127u) + (size_t)op.ring * op.stage_bytes + (2 * op.ring + 5) * sizeof(uint64_t) + 16;
+    return ((op.w_bytes + 127u) & ~127u) + (size_t)op.ring * op.stage_bytes + (2 * op.ring + 5 + 1) * sizeof(uint64_t) + 16 + 768 * sizeof(float);
 }
 
 }  // namespace hm

@@ -664,6 +664,8 @@ int hm_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int cin, i
     return HM_OK;
 }
 
+float hm_debug_last_op_ms(void) { return hm::tensor_debug_last_op_ms(); }
+
 int hm_microbench(hm_engine* e, int slot, const char* name, uint32_t n_sites, int iters, float* ms_per_launch, double* algo_bytes, double* algo_flops)
 {
     if (!e || !name || !ms_per_launch || slot < 0 || slot >= e->n_slots || iters < 1) return fail(e, HM_ERR_ARG, "hm_microbench: bad argument");

@@ -57,7 +57,7 @@ class hm_timing(C.Structure):
 ABI_SYMBOLS = ["hm_engine_create", "hm_engine_destroy", "hm_last_error", "hm_version", "hm_batch_acquire", "hm_batch_submit",
                "hm_batch_collect", "hm_batch_timing", "hm_codev1_encode", "hm_codev1_decode", "hm_pack_record",
                "hm_mod_record_bound", "hm_build_mod_record", "hm_debug_dump_decode", "hm_debug_dump_ctx",
-               "hm_debug_dump_features", "hm_debug_dump_logits", "hm_debug_dense_op", "hm_microbench"]
+               "hm_debug_dump_features", "hm_debug_dump_logits", "hm_debug_dense_op", "hm_debug_last_op_ms", "hm_microbench"]
 
 _lib = None
 
@@ -95,6 +95,7 @@ def load_library() -> C.CDLL:
     L.hm_debug_dump_logits.argtypes = [C.c_void_p, C.c_int, _f32p]
     L.hm_debug_dense_op.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(_f32p), C.c_int, _i32p, _i32p,
                                     _f32p, _f32p, C.c_int, _f32p, _f32p, _u32p, C.c_uint32, _f32p]
+    L.hm_debug_last_op_ms.restype = C.c_float
     L.hm_microbench.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_uint32, C.c_int, _f32p, C.POINTER(C.c_double),
                                 C.POINTER(C.c_double)]
     _lib = L

@@ -171,6 +171,9 @@ int hm_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int cin, i
                       int n_terms, const int32_t* term_src, const int32_t* term_shift, const float* weights, const float* bias,
                       int conv1_taps, const float* w2, const float* b2, const uint32_t* gather_rows, uint32_t gather_mask, float* out);
 
+/* Device time (ms, CUDA events) of the kernel launched by the last hm_debug_dense_op (tools/dense_microbench.py). */
+float hm_debug_last_op_ms(void);
+
 /* ---- kernel microbenchmarks (BASELINE.json config 5) --------------------------------------------------- */
 /* Runs one named kernel family `iters` times on the slot's resident inputs and returns the mean device
  * time per launch (CUDA events) and the algorithmic bytes / flops one launch processes.
