@@ -553,7 +553,7 @@ int tensor_workspace_alloc(TensorWorkspace& w, uint32_t max_bases, uint32_t max_
     size_t cap = max_rows;
     if (!cap) {
         const char* env = getenv("HM_DENSE_ROWS");
-        cap = env ? (size_t)atoll(env) : ((size_t)1 << 19);
+        cap = env ? (size_t)atoll(env) : ((size_t)1 << 21);  // 2 Mi rows: ~20 GB of maps; fewer, larger launches
     }
     cap = std::min(cap, total_rows);
     cap = ((cap + kTileRows - 1) / kTileRows) * kTileRows;
