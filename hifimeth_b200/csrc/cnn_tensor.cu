@@ -358,6 +358,12 @@ void bind_blob(DevOp& d, const uint8_t* blob)
     }
 }
 
+bool pdl_enabled()
+{
+    static const bool v = getenv("HM_NO_PDL") == nullptr;
+    return v;
+}
+
 bool g_attr_set = false;
 float g_debug_op_ms = 0.f;
 int ensure_kernel_attr()
@@ -620,8 +626,17 @@ int launch_op(const DevOp& d, const TensorWorkspaceImpl& s, uint32_t n_tiles, fl
         p.logits = logit_out;
     }
     const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)sm_count);
-    dense_gemm_kernel<<<grid, kDenseThreads, d.smem, stream>>>(p);
-    return 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kDenseThreads);
+    cfg.dynamicSmemBytes = d.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, dense_gemm_kernel, p) == cudaSuccess ? 0 : -1;
 }
 
 struct SubBatch {

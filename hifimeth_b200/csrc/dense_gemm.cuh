@@ -18,7 +18,7 @@
 //             filled by warp s (a warp has one bulk-copy instruction in flight at a time, tools/bulk_copy_probe.cu, so
 //             the number of stages in flight is the number of producer warps)
 //   warp 8    MMA issuer (one elected lane): 3 tcgen05.mma per term and k-step, commit -> ring slot free
-//   warps 9-12 epilogue: tcgen05.ld the fp32 accumulator (double buffered in TMEM), bias + ReLU, split to hi/lo
+//   warps 9-16 epilogue: tcgen05.ld the fp32 accumulator (double buffered in TMEM), bias + ReLU, split to hi/lo
 //             bf16, coalesced 16-byte stores in plane layout (or the fc2 head -> logits)
 #pragma once
 #include <cstdint>
@@ -33,7 +33,8 @@ constexpr int kTileRows = 128;
 constexpr int kMaxTerms = 3;
 constexpr int kMaxSegs = 3;
 constexpr int kProducerWarps = 8;
-constexpr int kDenseThreads = 32 * (kProducerWarps + 1 + 4);
+constexpr int kEpilogueWarps = 8;  // two per TMEM lane group; 32-column chunks alternate between the two
+constexpr int kDenseThreads = 32 * (kProducerWarps + 1 + kEpilogueWarps);
 
 struct DenseSeg {
     const uint8_t* src;           // plane 0 (hi, g = 0), row 0 of the input map
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel_t(const __
             umma::mbar_init(w_full, 1);
             for (int i = 0; i < 2; ++i) {
                 umma::mbar_init(&t_full[i], 1);
-                umma::mbar_init(&t_empty[i], 128);
+                umma::mbar_init(&t_empty[i], 32 * kEpilogueWarps);
             }
             umma::fence_barrier_init();
         }
@@ -132,6 +133,9 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel_t(const __
     const uint32_t tmem_base = *s_tmem;
     const uint32_t acc_stride = op.tmem_cols >> 1;
 
+    // Programmatic dependent launch: the next launch of the stream may start its prologue (barrier init, TMEM allocation,
+    // weight load) on SMs this grid has left; everything that reads or overwrites activations waits for the previous grid.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (warp < (uint32_t)kProducerWarps) {
         // ===================================== producers ====================================================
         if (warp == 0) {
@@ -148,6 +152,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel_t(const __
         // A ring slot must always be filled by the same warp (parity waits are only valid one phase ahead): warp s owns
         // slot s, ring <= kProducerWarps.
         const uint32_t n_prod = (uint32_t)op.ring;
+        asm volatile("griddepcontrol.wait;" ::: "memory");  // activations (and the site-row index) come from earlier launches
         uint32_t stage_no = 0;
         uint32_t stage_tx = 0, ncopies = 0;
         int bulk_seg[kMaxSegs] = {0, 0, 0};
@@ -274,14 +279,15 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel_t(const __
     } else {
         // ===================================== epilogue ======================================================
         const uint32_t lane_grp = (warp & 3u) * 32u;  // TMEM lanes this warp may touch
+        const uint32_t half = (warp - (uint32_t)(kProducerWarps + 1)) >> 2;  // which 32-column chunks this warp takes
         const uint32_t m = lane_grp + lane;            // row of the tile
         const int n = op.n;
         // bias (and the fc2 weights of the head form) live in shared memory for the whole launch
-        for (int i = (int)threadIdx.x - 32 * (kProducerWarps + 1); i < n; i += 128) {
+        for (int i = (int)threadIdx.x - 32 * (kProducerWarps + 1); i < n; i += 32 * kEpilogueWarps) {
             s_bias[i] = __ldg(op.bias + i);
             if (op.mode == 1) { s_bias[256 + i] = __ldg(op.w2 + i); s_bias[512 + i] = __ldg(op.w2 + n + i); }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpilogueWarps) : "memory");
         uint32_t it = 0;
         for (uint32_t tile = blockIdx.x; tile < op.n_tiles; tile += gridDim.x, ++it) {
             const uint32_t buf = it & 1u, use = it >> 1;
@@ -290,7 +296,10 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel_t(const __
             const uint32_t t_addr = tmem_base + (lane_grp << 16) + buf * acc_stride;
             const unsigned long long row = (unsigned long long)tile * kTileRows + m;
             float l0 = 0.f, l1 = 0.f;
-            for (int c0 = 0; c0 < n && !(variant & 8u); c0 += 32) {
+            // map form: chunks alternate between the two warps of a lane group; head form: the first warp does all
+            const int c_first = op.mode == 0 ? (int)half * 32 : 0, c_step = op.mode == 0 ? 64 : 32;
+            const int c_end = (op.mode == 0 || half == 0) && !(variant & 8u) ? n : 0;
+            for (int c0 = c_first; c0 < c_end; c0 += c_step) {
                 uint32_t v[32];
                 umma::tmem_ld32(t_addr + (uint32_t)c0, v);
                 umma::tmem_ld_wait();
@@ -312,10 +321,13 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel_t(const __
                         uint32_t hi[4], lo[4];
                         #pragma unroll
                         for (int j = 0; j < 4; ++j) {
+                            // hi = bf16(x) for two values in one cvt; lo = bf16(x - hi), hi widened back with integer ops
                             const float x0 = f[8 * g + 2 * j], x1 = f[8 * g + 2 * j + 1];
-                            const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-                            hi[j] = pack_bf16x2(h0, h1);
-                            lo[j] = pack_bf16x2(__float2bfloat16_rn(x0 - __bfloat162float(h0)), __float2bfloat16_rn(x1 - __bfloat162float(h1)));
+                            const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+                            const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+                            const __nv_bfloat162 e = __floats2bfloat162_rn(x0 - __uint_as_float(hb << 16), x1 - __uint_as_float(hb & 0xffff0000u));
+                            hi[j] = hb;
+                            lo[j] = *reinterpret_cast<const uint32_t*>(&e);
                         }
                         if (variant & 4u) continue;
                         *reinterpret_cast<uint4*>(p_hi + g * op.out_plane_stride) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -331,7 +343,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel_t(const __
             }
             umma::tc_fence_before();
             umma::mbar_arrive(&t_empty[buf]);
-            if (op.mode == 1) {
+            if (op.mode == 1 && half == 0) {
                 float2 o = make_float2(l0 + __ldg(op.b2), l1 + __ldg(op.b2 + 1));
                 *reinterpret_cast<float2*>(op.logits + row * 2ull) = o;
             }
