@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "dense_gemm.cuh"
+#include "dense_gemm2.cuh"
 #include "postprocess.cuh"
 
 namespace hm {
@@ -224,6 +225,7 @@ struct DevOp {
     int seg_map[kMaxSegs] = {0, 0, 0};
     int out_map = -1;
     bool compact = false;
+    bool two_cta = false;  // launched as dense_gemm2_kernel (CTA pairs, each holding half of every weight tile)
     size_t smem = 0;
     size_t w_off = 0, bias_off = 0, w2_off = 0, b2_off = 0;  // offsets into the model blob
     double macs_per_row = 0;  // executed MACs per output row, one precision pass
@@ -231,7 +233,7 @@ struct DevOp {
 
 // Lowers output channels [n0, n0 + n) of a plan op to kernel parameters + packed weights.  Returns false with
 // err = "fit" when the slice's resident weights leave no room for a 2-deep ring (the caller then splits it).
-bool lower_op(const HostOp& h, int n0, int n, DevOp& d, std::vector<uint8_t>& blob, std::string& err)
+bool lower_op(const HostOp& h, int n0, int n, DevOp& d, std::vector<uint8_t>& blob, std::string& err, bool two_cta = false)
 {
     DenseOp& p = d.p;
     p = DenseOp{};
@@ -247,6 +249,8 @@ bool lower_op(const HostOp& h, int n0, int n, DevOp& d, std::vector<uint8_t>& bl
     d.out_map = h.out;
     uint32_t stage = 0;
     d.compact = h.compact;
+    d.two_cta = two_cta;
+    if (two_cta && (h.compact || h.head || h.conv1_taps > 0 || n0 != 0 || n != h.cout || n % 32)) { err = "op not eligible for the CTA-pair form"; return false; }
     p.gather_taps = 0;
     p.gather_rows = nullptr;
     if (h.conv1_taps > 0) {
@@ -304,31 +308,35 @@ bool lower_op(const HostOp& h, int n0, int n, DevOp& d, std::vector<uint8_t>& bl
         d.macs_per_row = (double)h.cin * n * h.terms.size();
     }
     p.stage_bytes = (stage + 127u) & ~127u;
-    // ---- weight image: tiles [stage][kstep][term][hl], each [2][n][8] bf16 ------------------------------------------
-    const uint32_t tile_elems = 2u * n * 8u;
+    // ---- weight image: tiles [stage][kstep][term][hl], each [2][nw][8] bf16; the CTA-pair form stores one image per rank
+    // holding that rank's nw = n / 2 output channels ------------------------------------------------------------------
+    const int n_img = two_cta ? 2 : 1, nw = n / n_img;
+    const uint32_t tile_elems = 2u * nw * 8u;
     const size_t n_tiles = (size_t)p.n_stages * p.ksteps * p.n_terms * 2;
-    std::vector<uint16_t> img(n_tiles * tile_elems, 0);
+    std::vector<uint16_t> img(n_img * n_tiles * tile_elems, 0);
+    for (int r = 0; r < n_img; ++r)
     for (int st = 0; st < p.n_stages; ++st)
         for (int q = 0; q < p.ksteps; ++q)
             for (int k = 0; k < p.n_terms; ++k) {
-                uint16_t* hi = &img[(((size_t)(st * p.ksteps + q) * p.n_terms + k) * 2) * tile_elems];
+                uint16_t* hi = &img[(r * n_tiles + ((size_t)(st * p.ksteps + q) * p.n_terms + k) * 2) * tile_elems];
                 uint16_t* lo = hi + tile_elems;
                 for (int c = 0; c < 2; ++c)
-                    for (int o = 0; o < n; ++o)
+                    for (int o = 0; o < nw; ++o)
                         for (int e = 0; e < 8; ++e) {
                             float w = 0.f;
+                            const int col = n0 + r * nw + o;
                             if (h.conv1_taps > 0) {
                                 int tap = 2 * q + c;
-                                if (tap < h.conv1_taps) w = h.terms[0].w[((size_t)tap * 8 + e) * nfull + n0 + o];
+                                if (tap < h.conv1_taps) w = h.terms[0].w[((size_t)tap * 8 + e) * nfull + col];
                             } else {
-                                w = h.terms[k].w[(size_t)(16 * st + 8 * c + e) * nfull + n0 + o];
+                                w = h.terms[k].w[(size_t)(16 * st + 8 * c + e) * nfull + col];
                             }
                             uint16_t wh = f2bf(w);
-                            hi[((size_t)c * n + o) * 8 + e] = wh;
-                            lo[((size_t)c * n + o) * 8 + e] = f2bf(w - bf2f(wh));
+                            hi[((size_t)c * nw + o) * 8 + e] = wh;
+                            lo[((size_t)c * nw + o) * 8 + e] = f2bf(w - bf2f(wh));
                         }
             }
-    p.w_bytes = (uint32_t)(img.size() * 2);
+    p.w_bytes = (uint32_t)(img.size() * 2 / n_img);  // per CTA
     const size_t w_al = (p.w_bytes + 127u) & ~127u;
     if (w_al + 2 * (size_t)p.stage_bytes + kSmemAux > kSmemMax) { err = "fit"; return false; }
     p.ring = (int)std::min<size_t>(kProducerWarps, (kSmemMax - kSmemAux - w_al) / p.stage_bytes);  // producer warp s owns slot s
@@ -364,12 +372,19 @@ bool pdl_enabled()
     return v;
 }
 
+bool two_cta_enabled()
+{
+    static const bool v = getenv("HM_NO_2CTA") == nullptr;
+    return v;
+}
+
 bool g_attr_set = false;
 float g_debug_op_ms = 0.f;
 int ensure_kernel_attr()
 {
     if (g_attr_set) return 0;
     TCUDA("dense kernel attribute", cudaFuncSetAttribute(dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    TCUDA("dense kernel attribute", cudaFuncSetAttribute(dense_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     g_attr_set = true;
     return 0;
 }
@@ -503,6 +518,17 @@ int tensor_model_build(TensorModelHandle& m, const CnnModel& host)
     std::vector<uint8_t> blob;
     for (const HostOp& h : plan) {
         // an op whose resident weights leave no room for the activation ring is split over output channels
+        // dense layers with > 128 KiB of weights (conv2, conv3, conv4) run as CTA pairs: half the weights per SM, deep ring
+        if (two_cta_enabled() && !h.compact && !h.head && h.conv1_taps == 0 && (size_t)h.cin * h.cout * h.terms.size() * 4 > (128u << 10)) {
+            DevOp d;
+            std::vector<uint8_t> trial = blob;
+            if (lower_op(h, 0, h.cout, d, trial, err, true)) {
+                blob.swap(trial);
+                t->macs_per_row += d.macs_per_row;
+                t->ops.push_back(d);
+                continue;
+            }
+        }
         int parts = 1;
         for (; parts <= 4; parts *= 2) {
             if (h.cout % (16 * parts) || (h.head && parts > 1)) { parts = 8; break; }
@@ -625,7 +651,8 @@ int launch_op(const DevOp& d, const TensorWorkspaceImpl& s, uint32_t n_tiles, fl
     } else {
         p.logits = logit_out;
     }
-    const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)sm_count);
+    uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)sm_count);
+    if (d.two_cta) grid = std::min<uint32_t>(((n_tiles + 1) / 2) * 2, (uint32_t)sm_count & ~1u);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kDenseThreads);
@@ -636,6 +663,7 @@ int launch_op(const DevOp& d, const TensorWorkspaceImpl& s, uint32_t n_tiles, fl
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    if (d.two_cta) return cudaLaunchKernelEx(&cfg, dense_gemm2_kernel, p) == cudaSuccess ? 0 : -1;
     return cudaLaunchKernelEx(&cfg, dense_gemm_kernel, p) == cudaSuccess ? 0 : -1;
 }
 
@@ -702,6 +730,12 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
     // ---- the plan, sub-batch by sub-batch -------------------------------------------------------------------------------------
     TCUDA("dense plan", cudaEventRecord(s->ev0, stream));
     uint32_t dense_launches = 0;
+    // HM_OP_TIMES=1: per-op device time (events between launches; serialises nothing, but PDL overlap is attributed to the
+    // earlier op), summed over the sub-batches of this batch and printed to stderr.  Analysis aid, off by default.
+    static const bool prof = getenv("HM_OP_TIMES") != nullptr;
+    static std::vector<cudaEvent_t> pe(1 << 16);
+    static std::vector<int> pk(1 << 16);
+    size_t np = 0;
     const bool compact = compact_mode();
     const uint32_t first[4] = {0, b.class_count[0], b.class_count[0] + b.class_count[1], b.class_count[0] + b.class_count[1] + b.class_count[2]};
     for (const SubBatch& sb : subs) {
@@ -734,10 +768,14 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
             site_rows_kernel<<<(n_pad + 255) / 256, 256, 0, stream>>>(s->d_track_row, s->d_track_row + s->reads_cap, b.d_base_off, b.d_site_read,
                                                                       b.d_site_pos, first_a, n_a, first_b, n, n_pad, sb.gtile0 * kTileRows,
                                                                       s->d_site_rows);
+            int op_i = 0;
             for (const DevOp& d : models[c].p->ops) {
+                if (prof) { cudaEventCreate(&pe[np]); cudaEventRecord(pe[np], stream); pk[np++] = c * 64 + op_i; }
                 launch_op(d, *s, d.compact ? n_pad / kTileRows : nt, s->d_clogit, sm_count, stream);
                 ++dense_launches;
+                ++op_i;
             }
+            if (prof) { cudaEventCreate(&pe[np]); cudaEventRecord(pe[np], stream); pk[np++] = -1; }
             site_finish_kernel<<<(n + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const float2*>(s->d_clogit), b.d_site_out, first_a, n_a, first_b, n,
                                                                     b.d_logits, b.d_ml);
             *launches += 2;
@@ -746,6 +784,27 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
     }
     TCUDA("dense plan", cudaEventRecord(s->ev1, stream));
     *launches += dense_launches;
+    if (prof && np) {
+        cudaStreamSynchronize(stream);
+        double acc[3][64] = {};
+        for (size_t i = 0; i + 1 < np; ++i) {
+            if (pk[i] < 0) continue;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, pe[i], pe[i + 1]);
+            acc[pk[i] / 64][pk[i] % 64] += ms;
+        }
+        for (size_t i = 0; i < np; ++i) cudaEventDestroy(pe[i]);
+        for (int c = 0; c < 3; ++c) {
+            if (!models[c].p) continue;
+            double tot = 0;
+            fprintf(stderr, "ctx %d op ms:", c);
+            for (size_t k = 0; k < models[c].p->ops.size(); ++k) {
+                fprintf(stderr, " %s%.2f", models[c].p->ops[k].compact ? "c" : "D", acc[c][k]);
+                tot += acc[c][k];
+            }
+            fprintf(stderr, "  | total %.2f\n", tot);
+        }
+    }
     // ---- per-site lookup (dense-all mode only; compact runs finish per sub-batch) ----------------------------------------------
     for (int k = 0; k < 4 && !compact; ++k) {
         if (!b.class_count[k]) continue;
@@ -797,7 +856,9 @@ int tensor_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int ci
     DevOp d;
     std::vector<uint8_t> blob;
     std::string err;
-    if (!lower_op(h, 0, cout, d, blob, err)) return tfail("hm_debug_dense_op: " + (err == "fit" ? std::string("op does not fit shared memory") : err));
+    const bool two = getenv("HM_DENSE_2CTA") != nullptr && !gather_mask && !h.head && conv1_taps == 0;
+    if (!lower_op(h, 0, cout, d, blob, err, two)) return tfail("hm_debug_dense_op: " + (err == "fit" ? std::string("op does not fit shared memory") : err));
+    if (two && rows_alloc < rows + kTileRows + 512) return tfail("hm_debug_dense_op: the CTA-pair form needs one spare tile of rows");
     h.compact = gather_mask != 0;
     uint32_t max_g = 0;
     for (uint32_t r = 0; gather_mask && r < rows; ++r) max_g = std::max(max_g, gather_rows[r]);
@@ -823,11 +884,13 @@ int tensor_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int ci
                 img[base + ((size_t)(groups + c / 8) * rows_alloc + r) * 8 + c % 8] = f2bf(v - bf2f(hi));
             }
     const int ogroups = cout / 8;
-    const unsigned long long ops_ = (unsigned long long)rows * 16ull;
+    const size_t orows = (size_t)rows + kTileRows;  // the CTA-pair form may write one tile past `rows`
+    const unsigned long long ops_ = (unsigned long long)orows * 16ull;
     const size_t out_bytes = h.head ? 0 : (size_t)2 * ogroups * ops_;
+    const size_t out_alloc = out_bytes + 4096;
     TCUDA("debug op", cudaMalloc((void**)&d_blob, blob.size()));
     TCUDA("debug op", cudaMalloc((void**)&d_in, in_bytes));
-    TCUDA("debug op", cudaMalloc((void**)&d_out, std::max<size_t>(out_bytes, 16)));
+    TCUDA("debug op", cudaMalloc((void**)&d_out, out_alloc));
     TCUDA("debug op", cudaMalloc((void**)&d_logit, (size_t)rows * 2 * sizeof(float)));
     TCUDA("debug op", cudaMemcpy(d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     TCUDA("debug op", cudaMemcpy(d_in, img.data(), in_bytes, cudaMemcpyHostToDevice));
@@ -858,7 +921,8 @@ int tensor_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int ci
     if (p.variant) cudaFuncSetAttribute(dense_gemm_kernel_dbg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
     for (int i = 0; i < reps; ++i) {
         if (i == std::max(0, reps - 10)) cudaEventRecord(e0);
-        if (p.variant) dense_gemm_kernel_dbg<<<std::min<uint32_t>(p.n_tiles, (uint32_t)sms), kDenseThreads, d.smem>>>(p);
+        if (d.two_cta) dense_gemm2_kernel<<<std::min<uint32_t>(((p.n_tiles + 1) / 2) * 2, (uint32_t)sms & ~1u), kDenseThreads, d.smem>>>(p);
+        else if (p.variant) dense_gemm_kernel_dbg<<<std::min<uint32_t>(p.n_tiles, (uint32_t)sms), kDenseThreads, d.smem>>>(p);
         else dense_gemm_kernel<<<std::min<uint32_t>(p.n_tiles, (uint32_t)sms), kDenseThreads, d.smem>>>(p);
     }
     cudaEventRecord(e1);
@@ -882,8 +946,8 @@ int tensor_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int ci
         TCUDA("debug op", cudaMemcpy(o.data(), d_out, out_bytes, cudaMemcpyDeviceToHost));
         for (uint32_t r = 0; r < rows; ++r)
             for (int c = 0; c < cout; ++c) {
-                const float hi = bf2f(o[((size_t)(c / 8) * rows + r) * 8 + c % 8]);
-                const float lo = bf2f(o[((size_t)(ogroups + c / 8) * rows + r) * 8 + c % 8]);
+                const float hi = bf2f(o[((size_t)(c / 8) * orows + r) * 8 + c % 8]);
+                const float lo = bf2f(o[((size_t)(ogroups + c / 8) * orows + r) * 8 + c % 8]);
                 out[(size_t)r * cout + c] = hi + lo;
             }
     }

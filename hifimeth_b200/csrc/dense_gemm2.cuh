@@ -1,0 +1,214 @@
+// dense_gemm2.cuh -- the CTA-pair (cta_group::2) form of dense_gemm_kernel for the layers whose weights are too large
+// to leave room for a deep activation ring in one SM (conv2, conv3: 3 x 128 x 128 x {hi,lo} = 192 KiB).
+//
+// A cluster of two CTAs computes 256 rows per tcgen05.mma: each CTA stages its own 128 rows of A and HALF of every weight
+// tile (its N/2 output channels), so resident weights drop to 96 KiB per SM and the ring deepens from 3 to 8 stages.
+//   * rank 0 (leader): warp 8 issues every MMA (M = 256) and commits with a multicast arrive to BOTH CTAs' barriers
+//   * rank 1 (peer):   every producer warp relays its own ring slot's `full` barrier to the leader once its copies have
+//                      landed (cluster-scope arrive); warp 8 relays the weight barrier
+//   * producers and epilogue warps work on their own CTA's tile exactly as in the single-CTA kernel
+// Dense (bulk-copy), normal-form, map-output ops only; same DenseOp parameters, w_img = [rank 0 half][rank 1 half],
+// w_bytes = bytes of ONE half.
+#pragma once
+#include "dense_gemm.cuh"
+
+namespace hm {
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) dense_gemm2_kernel(const __grid_constant__ DenseOp op)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = umma::cluster_ctarank();
+    const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    uint8_t* s_w = smem;
+    uint8_t* s_ring = smem + ((op.w_bytes + 127u) & ~127u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + (size_t)op.ring * op.stage_bytes);
+    uint64_t* full = bars;                  // [ring]  leader: own expect_tx arrive + the peer's relay; peer: own arrive
+    uint64_t* empty = bars + op.ring;       // [ring]  multicast commit from the leader
+    uint64_t* w_full = bars + 2 * op.ring;  // [1]
+    uint64_t* t_full = w_full + 1;          // [2]     multicast commit from the leader
+    uint64_t* t_empty = t_full + 2;         // [2]     leader only: one arrive per epilogue warp of both CTAs
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(t_empty + 2);
+    float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(t_empty + 3) + 15) & ~(uintptr_t)15);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < op.ring; ++i) {
+                umma::mbar_init(&full[i], rank == 0 ? 2u : 1u);
+                umma::mbar_init(&empty[i], 1);
+            }
+            umma::mbar_init(w_full, rank == 0 ? 2u : 1u);
+            for (int i = 0; i < 2; ++i) {
+                umma::mbar_init(&t_full[i], 1);
+                umma::mbar_init(&t_empty[i], 2 * kEpilogueWarps);
+            }
+            umma::fence_barrier_init();
+        }
+        __syncwarp();
+        umma::tmem_alloc2(s_tmem, op.tmem_cols);
+    }
+    umma::tc_fence_before();
+    umma::cluster_sync();  // both CTAs' barriers exist before anyone arrives remotely
+    umma::tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    const uint32_t acc_stride = op.tmem_cols >> 1;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    if (warp < (uint32_t)kProducerWarps) {
+        // ===================================== producers (own CTA's rows, own half of the weights) ==================
+        if (warp == 0) {
+            if (lane == 0) umma::mbar_arrive_expect_tx(w_full, op.w_bytes);
+            __syncwarp();
+            const uint32_t per = (((op.w_bytes + 31u) / 32u) + 15u) & ~15u;
+            const uint32_t off = lane * per;
+            if (off < op.w_bytes) umma::bulk_g2s(s_w + off, op.w_img + (size_t)rank * op.w_bytes + off, min(per, op.w_bytes - off), w_full);
+        }
+        const uint32_t n_prod = (uint32_t)op.ring;
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        uint32_t stage_no = 0, stage_tx = 0, ncopies = 0;
+        for (int s = 0; s < op.n_segs; ++s) {
+            stage_tx += op.seg[s].nrows * 16u * 4u;
+            ncopies += 4u;
+        }
+        for (uint32_t t2 = pair; 2 * t2 < op.n_tiles; t2 += n_pairs) {
+            const long long row0 = (long long)(2 * t2 + rank) * kTileRows;  // odd n_tiles: the peer's last tile lies in the slack rows
+            for (int st = 0; st < op.n_stages; ++st, ++stage_no) {
+                if (stage_no % n_prod != warp) continue;
+                const uint32_t slot = stage_no % (uint32_t)op.ring, phase = (stage_no / (uint32_t)op.ring) & 1u;
+                umma::mbar_wait(&empty[slot], phase ^ 1u);
+                uint8_t* stage = s_ring + (size_t)slot * op.stage_bytes;
+                if (lane == 0) umma::mbar_arrive_expect_tx(&full[slot], stage_tx);
+                __syncwarp();
+                if (lane < ncopies) {
+                    const uint32_t p = lane & 3u;
+                    const DenseSeg& sg = op.seg[lane >> 2];
+                    const uint32_t pl_bytes = sg.nrows * 16u;
+                    const uint8_t* plane = sg.src + (unsigned long long)((p >> 1) * sg.groups + (uint32_t)(2 * st) + (p & 1u)) * sg.plane_stride;
+                    umma::bulk_g2s(stage + sg.smem_off + p * pl_bytes, plane + (row0 + sg.row_off) * 16ll, pl_bytes, &full[slot]);
+                }
+                __syncwarp();
+                if (rank != 0) {
+                    // the peer tells the leader when its half of the stage has landed (one relay per slot owner, in parallel)
+                    umma::mbar_wait(&full[slot], phase);
+                    if (lane == 0) umma::mbar_arrive_cluster(umma::mapa(umma::smem_u32(&full[slot]), 0));
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == (uint32_t)kProducerWarps) {
+        const int n_terms = op.n_terms, n_stages = op.n_stages, ring = op.ring;
+        if (rank == 0) {
+            // ===================================== MMA issuer (leader) ============================================
+            const uint32_t idesc = umma::make_idesc_bf16_m256((uint32_t)op.n);
+            const uint32_t desc_hi = (uint32_t)(umma::make_desc(0, 0, 128) >> 32);
+            const uint32_t nh = (uint32_t)op.n >> 1;                       // B rows held by each CTA
+            const uint32_t b_step = (nh * 32u) >> 4;
+            const uint32_t b_base = (uint32_t)umma::make_desc(umma::smem_u32(s_w), nh * 16u, 128);
+            const uint32_t ring16 = umma::smem_u32(s_ring) >> 4, stage16 = op.stage_bytes >> 4;
+            uint32_t a_hi[kMaxTerms], a_lo[kMaxTerms];
+            #pragma unroll
+            for (int k = 0; k < kMaxTerms; ++k) {
+                a_hi[k] = (uint32_t)umma::make_desc(op.term[k].a_off, op.term[k].a_lbo, 128);
+                a_lo[k] = (uint32_t)umma::make_desc(op.term[k].a_off + op.term[k].a_hl_off, op.term[k].a_lbo, 128);
+            }
+            umma::mbar_wait(w_full, 0);  // both halves of the weights have landed (own copy + the peer's relay)
+            uint32_t slot = 0, phase = 0, it = 0;
+            for (uint32_t t2 = pair; 2 * t2 < op.n_tiles; t2 += n_pairs, ++it) {
+                const uint32_t buf = it & 1u, use = it >> 1;
+                umma::mbar_wait(&t_empty[buf], (use & 1u) ^ 1u);
+                umma::tc_fence_after();
+                const uint32_t d_addr = tmem_base + buf * acc_stride;
+                uint32_t acc = 0, b_cur = b_base;
+                for (int st = 0; st < n_stages; ++st) {
+                    umma::mbar_wait(&full[slot], phase);
+                    umma::tc_fence_after();
+                    if (umma::elect_one()) {
+                        const uint32_t sa = ring16 + slot * stage16;
+                        uint32_t bq = b_cur, a0 = acc;
+                        #pragma unroll
+                        for (int k = 0; k < kMaxTerms; ++k) {
+                            if (k < n_terms) {
+                                umma::mma2_bf16_w(d_addr, a_hi[k] + sa, bq, desc_hi, idesc, a0);
+                                a0 = 1;
+                                umma::mma2_bf16_w(d_addr, a_lo[k] + sa, bq, desc_hi, idesc, 1);
+                                umma::mma2_bf16_w(d_addr, a_hi[k] + sa, bq + b_step, desc_hi, idesc, 1);
+                                bq += 2 * b_step;
+                            }
+                        }
+                        umma::mma2_commit_mc(&empty[slot]);
+                    }
+                    acc = 1;
+                    b_cur += 2 * b_step * (uint32_t)n_terms;
+                    __syncwarp();
+                    if (++slot == (uint32_t)ring) { slot = 0; phase ^= 1u; }
+                }
+                if (umma::elect_one()) umma::mma2_commit_mc(&t_full[buf]);
+                __syncwarp();
+            }
+        } else {
+            // ===================================== peer: only the weights need relaying here ==========================
+            umma::mbar_wait(w_full, 0);
+            if (lane == 0) umma::mbar_arrive_cluster(umma::mapa(umma::smem_u32(w_full), 0));
+        }
+    } else {
+        // ===================================== epilogue (own CTA's 128 rows) ==========================================
+        const uint32_t lane_grp = (warp & 3u) * 32u;
+        const uint32_t half = (warp - (uint32_t)(kProducerWarps + 1)) >> 2;
+        const uint32_t m = lane_grp + lane;
+        const int n = op.n;
+        for (int i = (int)threadIdx.x - 32 * (kProducerWarps + 1); i < n; i += 32 * kEpilogueWarps) s_bias[i] = __ldg(op.bias + i);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpilogueWarps) : "memory");
+        uint32_t it = 0;
+        for (uint32_t t2 = pair; 2 * t2 < op.n_tiles; t2 += n_pairs, ++it) {
+            const uint32_t buf = it & 1u, use = it >> 1;
+            umma::mbar_wait(&t_full[buf], use & 1u);
+            umma::tc_fence_after();
+            const uint32_t t_addr = tmem_base + (lane_grp << 16) + buf * acc_stride;
+            const unsigned long long row = (unsigned long long)(2 * t2 + rank) * kTileRows + m;
+            for (int c0 = (int)half * 32; c0 < n; c0 += 64) {
+                uint32_t v[32];
+                umma::tmem_ld32(t_addr + (uint32_t)c0, v);
+                umma::tmem_ld_wait();
+                float f[32];
+                #pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 bv = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+                    f[j] = fmaxf(__uint_as_float(v[j]) + bv.x, 0.f);
+                    f[j + 1] = fmaxf(__uint_as_float(v[j + 1]) + bv.y, 0.f);
+                    f[j + 2] = fmaxf(__uint_as_float(v[j + 2]) + bv.z, 0.f);
+                    f[j + 3] = fmaxf(__uint_as_float(v[j + 3]) + bv.w, 0.f);
+                }
+                const uint32_t g0 = op.out_g0 + ((uint32_t)c0 >> 3);
+                uint8_t* p_hi = op.out + (unsigned long long)g0 * op.out_plane_stride + row * 16ull;
+                uint8_t* p_lo = p_hi + (unsigned long long)op.out_groups * op.out_plane_stride;
+                #pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t hi[4], lo[4];
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float x0 = f[8 * g + 2 * j], x1 = f[8 * g + 2 * j + 1];
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+                        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+                        const __nv_bfloat162 e = __floats2bfloat162_rn(x0 - __uint_as_float(hb << 16), x1 - __uint_as_float(hb & 0xffff0000u));
+                        hi[j] = hb;
+                        lo[j] = *reinterpret_cast<const uint32_t*>(&e);
+                    }
+                    *reinterpret_cast<uint4*>(p_hi + g * op.out_plane_stride) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(p_lo + g * op.out_plane_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+            umma::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (rank == 0) umma::mbar_arrive(&t_empty[buf]);
+                else umma::mbar_arrive_cluster(umma::mapa(umma::smem_u32(&t_empty[buf]), 0));
+            }
+        }
+    }
+    umma::tc_fence_before();
+    umma::cluster_sync();  // the peer's shared memory and TMEM stay alive until the leader's last MMA and arrive are done
+    umma::tc_fence_after();
+    if (warp == 0) umma::tmem_dealloc2(tmem_base, op.tmem_cols);
+}
+
+}  // namespace hm

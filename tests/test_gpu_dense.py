@@ -137,3 +137,24 @@ def test_compact_op_conv1_gather(lib_built, taps, shift):
         scale += (np.abs(a).astype(np.float64) @ np.abs(w[j]).astype(np.float64)).max(axis=1)
     got = hme.debug_dense_op([x], [(0, shift, w)], bias, rows, conv1_taps=taps, gather_rows=grows, gather_mask=1)
     _check(got, np.maximum(acc, 0), scale)
+
+
+# ---- CTA-pair (cta_group::2) form: M = 256 per MMA, half of every weight tile per CTA --------------------------------------
+
+@pytest.mark.parametrize("rows,cin,cout,shifts", [
+    (256, 128, 128, [0]),
+    (128 * 3, 128, 128, [0, 2, 4]),     # odd tile count: the peer's last tile lies in the slack rows
+    (128 * 8, 128, 96, [0, 8, 16]),
+    (128 * 600, 128, 128, [0, 4, 8]),   # several tile pairs per cluster: ring phases, TMEM double buffering, relay
+])
+def test_dense_op_cta_pair(lib_built, rows, cin, cout, shifts, monkeypatch):
+    monkeypatch.setenv("HM_DENSE_2CTA", "1")
+    rng = np.random.default_rng(rows + cout)
+    rows_alloc = rows + max(shifts) + 128 + 512
+    srcs = [rng.standard_normal((rows_alloc, cin)).astype(np.float32)]
+    terms = [(0, sh, (rng.standard_normal((cin, cout)) / np.sqrt(cin)).astype(np.float32)) for sh in shifts]
+    bias = rng.standard_normal(cout).astype(np.float32)
+    want = _ref(srcs, terms, bias, rows)
+    scale = sum(np.abs(srcs[0][sh:sh + rows]).astype(np.float64) @ np.abs(w).astype(np.float64) for _, sh, w in terms).max(axis=1)
+    got = hme.debug_dense_op(srcs, terms, bias, rows)
+    _check(got, want, scale)

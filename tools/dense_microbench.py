@@ -17,7 +17,7 @@ def run(cin, cout, shifts, variant=0, head=False, conv1=0):
     os.environ["HM_DENSE_VARIANT"] = str(variant)
     os.environ["HM_DENSE_REPS"] = os.environ.get("HM_DENSE_REPS", "400")  # long enough for clocks to ramp; last 10 timed
     rng = np.random.default_rng(0)
-    rows_alloc = ROWS + max(shifts) + 32
+    rows_alloc = ROWS + max(shifts) + 32 + 640
     x = rng.standard_normal((rows_alloc, cin)).astype(np.float32)
     if conv1:
         terms = [(0, shifts[0], (rng.standard_normal((conv1, 8, cout)) / 9).astype(np.float32))]
@@ -59,6 +59,15 @@ if __name__ == "__main__":
             run(96, 96, [0, 16, 32], v)
         for v in (0, 8, 10):
             run(64, 64, [0, 0], v)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "pair":
+        for two in (0, 1):
+            if two:
+                os.environ["HM_DENSE_2CTA"] = "1"
+            print("CTA pair" if two else "single CTA")
+            run(128, 128, [0, 2, 4], 0)
+            run(128, 128, [0], 0)
+            run(128, 96, [0, 8, 16], 0)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "big":
         for v in (0, 8, 10):
