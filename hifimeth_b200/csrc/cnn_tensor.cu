@@ -518,8 +518,8 @@ int tensor_model_build(TensorModelHandle& m, const CnnModel& host)
     std::vector<uint8_t> blob;
     for (const HostOp& h : plan) {
         // an op whose resident weights leave no room for the activation ring is split over output channels
-        // dense layers with > 128 KiB of weights (conv2, conv3, conv4) run as CTA pairs: half the weights per SM, deep ring
-        if (two_cta_enabled() && !h.compact && !h.head && h.conv1_taps == 0 && (size_t)h.cin * h.cout * h.terms.size() * 4 > (128u << 10)) {
+        // dense layers with > 64 KiB of weights (conv2 .. conv6) run as CTA pairs: half the weights per SM, deep ring
+        if (two_cta_enabled() && !h.compact && !h.head && h.conv1_taps == 0 && (size_t)h.cin * h.cout * h.terms.size() * 4 > (64u << 10)) {
             DevOp d;
             std::vector<uint8_t> trial = blob;
             if (lower_op(h, 0, h.cout, d, trial, err, true)) {
