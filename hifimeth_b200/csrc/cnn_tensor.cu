@@ -55,7 +55,10 @@ bool compact_mode()
     return v;
 }
 
-enum MapId { MAP_X = 0, MAP_Y = 1, MAP_F = 7, MAP_G = 13, MAP_T7 = 19, MAP_T8 = 23, N_MAPS = 25 };
+// X and Y1..Y6 are dense (one row per strand position of the sub-batch); F, G, T7, T8 and the scatter buffers S hold one row
+// per site of the running context (compact), except under HM_DENSE_ALL where F/G/T are dense too.
+constexpr int kMaxScatterMaps = 20;
+enum MapId { MAP_X = 0, MAP_Y = 1, MAP_F = 7, MAP_G = 13, MAP_T7 = 19, MAP_T8 = 23, MAP_S = 25, N_MAPS = 25 + kMaxScatterMaps };
 const int kLayerCout[6] = {128, 128, 128, 96, 96, 96};
 
 int map_channels(int id)
@@ -64,6 +67,7 @@ int map_channels(int id)
     if (id < MAP_F) return kLayerCout[id - MAP_Y];
     if (id < MAP_G) return kLayerCout[id - MAP_F];
     if (id < MAP_T7) return kLayerCout[id - MAP_G];
+    if (id >= MAP_S) return 128;  // scatter buffers are sized for the widest map
     return 64;
 }
 
@@ -81,6 +85,7 @@ struct HostOp {
     int conv1_taps = 0;  // > 0: conv1 form (one term, weights [taps][8][cout], rows shift .. shift + taps - 1)
     bool head = false;
     bool compact = false;  // evaluated at site rows only (one output row per site of the run)
+    std::vector<std::pair<int, int>> scatter;  // dense op: (row shift, compact buffer) copies its epilogue also writes
     std::vector<float> w2, b2;
 };
 
@@ -152,6 +157,20 @@ bool build_plan(const CnnModel& m, bool compact, std::vector<HostOp>& ops, std::
     conv1_op(MAP_F + 0, 0, 0);
     conv1_op(MAP_G + 0, 2 * (lens[1] - 1), k1 - 1);
 
+    // A compact op that reads dense map `mp` at (site row + sh) gets that operand from a compact scatter buffer which the
+    // producing dense op fills from its epilogue.
+    int n_scatter_maps = 0;
+    auto scatter_buffer = [&](int mp, int sh) {
+        for (HostOp& pr : ops) {
+            if (pr.out != mp || pr.compact) continue;
+            for (auto& sc : pr.scatter)
+                if (sc.first == sh) return sc.second;
+            if ((int)pr.scatter.size() == kMaxScatter || n_scatter_maps == kMaxScatterMaps) return -1;
+            pr.scatter.push_back({sh, MAP_S + n_scatter_maps});
+            return MAP_S + n_scatter_maps++;
+        }
+        return -1;
+    };
     auto off = [](int l) { return -((1 << l) - 2); };
     // site-level element q of layer l's output -> (map, shift) relative to row s; false = zero pad
     auto src = [&](int l, int q, int& map, int& sh) {
@@ -198,7 +217,11 @@ bool build_plan(const CnnModel& m, bool compact, std::vector<HostOp>& ops, std::
                 if (!src(l - 1, 2 * ov.second - 1 + j, mp, sh)) continue;
                 if (sh < 0) { err = "negative shift in plan"; return false; }
                 HostTerm t; t.src = mp; t.shift = sh; t.w = tap(j);
-                t.gather = compact && mp >= MAP_Y && mp < MAP_F;  // dense Y maps are read through the site-row index
+                if (compact && mp >= MAP_Y && mp < MAP_F) {  // a dense Y map read at site rows: through a scatter buffer
+                    t.src = scatter_buffer(mp, sh);
+                    t.shift = 0;
+                    if (t.src < 0) { err = "too many scatter buffers in plan"; return false; }
+                }
                 op.terms.push_back(std::move(t));
             }
             ops.push_back(std::move(op));
@@ -225,6 +248,7 @@ struct DevOp {
     int seg_map[kMaxSegs] = {0, 0, 0};
     int out_map = -1;
     bool compact = false;
+    int sc_map[kMaxScatter] = {0, 0, 0, 0, 0};
     bool two_cta = false;  // launched as dense_gemm2_kernel (CTA pairs, each holding half of every weight tile)
     size_t smem = 0;
     size_t w_off = 0, bias_off = 0, w2_off = 0, b2_off = 0;  // offsets into the model blob
@@ -250,6 +274,9 @@ bool lower_op(const HostOp& h, int n0, int n, DevOp& d, std::vector<uint8_t>& bl
     uint32_t stage = 0;
     d.compact = h.compact;
     d.two_cta = two_cta;
+    p.n_scatter = (int)h.scatter.size();
+    for (int k = 0; k < p.n_scatter; ++k) { p.sc_shift[k] = h.scatter[k].first; d.sc_map[k] = h.scatter[k].second; }
+    if (p.n_scatter && (n0 != 0 || n != h.cout)) { err = "a scattering op cannot be split over output channels"; return false; }
     if (two_cta && (h.compact || h.head || h.conv1_taps > 0 || n0 != 0 || n != h.cout || n % 32)) { err = "op not eligible for the CTA-pair form"; return false; }
     p.gather_taps = 0;
     p.gather_rows = nullptr;
@@ -465,7 +492,7 @@ __global__ void __launch_bounds__(256)
 site_rows_kernel(const uint32_t* __restrict__ track_row_fwd, const uint32_t* __restrict__ track_row_rev,
                  const uint32_t* __restrict__ base_off, const uint32_t* __restrict__ site_read, const uint32_t* __restrict__ site_pos,
                  uint32_t first_a, uint32_t n_a, uint32_t first_b, uint32_t n, uint32_t n_pad, uint32_t row_base,
-                 uint32_t* __restrict__ rows)
+                 uint32_t* __restrict__ rows, int32_t* __restrict__ site_of_row)
 {
     const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= n_pad) return;
@@ -479,6 +506,7 @@ site_rows_kernel(const uint32_t* __restrict__ track_row_fwd, const uint32_t* __r
         const int L = (int)(base_off[r + 1] - base_off[r]);
         const int o = rev ? L - 1 - p : p;
         row = (rev ? track_row_rev[r] : track_row_fwd[r]) - row_base + (uint32_t)(kHaloL + o - 201);
+        site_of_row[row] = (int32_t)m;  // inverse map for the dense layers' scatter (cleared to -1 before this launch)
     }
     rows[m] = row;
 }
@@ -564,7 +592,9 @@ void tensor_model_free(TensorModelHandle& m)
 // ---- workspace ---------------------------------------------------------------------------------------------------------------
 struct TensorWorkspaceImpl {
     uint32_t rows_cap = 0;            // dense rows of one sub-batch
-    unsigned long long plane_stride = 0;
+    uint32_t compact_cap = 0;         // sites of one context in one sub-batch
+    unsigned long long plane_stride = 0, cplane_stride = 0;  // dense maps / compact maps
+    int32_t* d_site_of_row = nullptr; // [rows_cap + slack] compact row of the site whose s-row this is, or -1
     uint8_t* d_maps = nullptr;
     uint8_t* map[N_MAPS] = {};
     size_t logit_rows_cap = 0;
@@ -590,17 +620,24 @@ int tensor_workspace_alloc(TensorWorkspace& w, uint32_t max_bases, uint32_t max_
     cap = std::min(cap, total_rows);
     cap = ((cap + kTileRows - 1) / kTileRows) * kTileRows;
     s->rows_cap = (uint32_t)cap;
+    s->compact_cap = compact_mode() ? (uint32_t)(((cap / 2 + kTileRows - 1) / kTileRows) * kTileRows) : (uint32_t)cap;
     s->plane_stride = (unsigned long long)(cap + kSlackRows) * 16ull;
-    size_t planes = 0;
-    for (int i = 0; i < N_MAPS; ++i) planes += 2 * (size_t)map_channels(i) / 8;
-    const size_t bytes = planes * s->plane_stride;
+    s->cplane_stride = (unsigned long long)(s->compact_cap + kSlackRows) * 16ull;
+    auto is_dense_map = [](int i) { return i < MAP_F || !compact_mode(); };
+    size_t bytes = 0;
+    for (int i = 0; i < N_MAPS; ++i) {
+        if (i >= MAP_S && !compact_mode()) continue;
+        bytes += 2 * (size_t)map_channels(i) / 8 * (is_dense_map(i) ? s->plane_stride : s->cplane_stride);
+    }
     TCUDA("activation workspace", cudaMalloc((void**)&s->d_maps, bytes));
     TCUDA("activation workspace", cudaMemset(s->d_maps, 0, bytes));
-    size_t pl = 0;
+    size_t at = 0;
     for (int i = 0; i < N_MAPS; ++i) {
-        s->map[i] = s->d_maps + pl * s->plane_stride;
-        pl += 2 * (size_t)map_channels(i) / 8;
+        if (i >= MAP_S && !compact_mode()) continue;
+        s->map[i] = s->d_maps + at;
+        at += 2 * (size_t)map_channels(i) / 8 * (is_dense_map(i) ? s->plane_stride : s->cplane_stride);
     }
+    TCUDA("site rows", cudaMalloc((void**)&s->d_site_of_row, (cap + kSlackRows) * sizeof(int32_t)));
     s->logit_rows_cap = total_rows;
     if (!compact_mode())
         for (int c = 0; c < 3; ++c) TCUDA("logit rows", cudaMalloc((void**)&s->d_logit[c], total_rows * 2 * sizeof(float)));
@@ -625,7 +662,7 @@ void tensor_workspace_free(TensorWorkspace& w)
     if (!s) return;
     cudaFree(s->d_maps);
     for (float* p : s->d_logit) cudaFree(p);
-    cudaFree(s->d_site_rows); cudaFree(s->d_clogit);
+    cudaFree(s->d_site_rows); cudaFree(s->d_clogit); cudaFree(s->d_site_of_row);
     cudaFreeHost(s->h_tile_read); cudaFreeHost(s->h_tile_first); cudaFree(s->d_tile_read); cudaFree(s->d_tile_first);
     cudaFreeHost(s->h_track_row); cudaFree(s->d_track_row);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -639,18 +676,22 @@ namespace {
 int launch_op(const DevOp& d, const TensorWorkspaceImpl& s, uint32_t n_tiles, float* logit_out, int sm_count, cudaStream_t stream)
 {
     DenseOp p = d.p;
+    auto stride_of = [&](int map) { return (map < MAP_F || !compact_mode()) ? s.plane_stride : s.cplane_stride; };
     for (int i = 0; i < p.n_segs; ++i) {
         p.seg[i].src = s.map[d.seg_map[i]];
-        p.seg[i].plane_stride = s.plane_stride;
+        p.seg[i].plane_stride = stride_of(d.seg_map[i]);
     }
     p.n_tiles = n_tiles;
     p.gather_rows = s.d_site_rows;
     if (p.mode == 0) {
         p.out = s.map[d.out_map];
-        p.out_plane_stride = s.plane_stride;
+        p.out_plane_stride = stride_of(d.out_map);
     } else {
         p.logits = logit_out;
     }
+    for (int k = 0; k < p.n_scatter; ++k) p.sc_out[k] = s.map[d.sc_map[k]];
+    p.sc_plane_stride = s.cplane_stride;
+    p.site_of_row = s.d_site_of_row;
     uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)sm_count);
     if (d.two_cta) grid = std::min<uint32_t>(((n_tiles + 1) / 2) * 2, (uint32_t)sm_count & ~1u);
     cudaLaunchConfig_t cfg{};
@@ -696,6 +737,13 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
                 const uint32_t need = tr * (want_rev ? 2u : 1u);
                 if (need > s->rows_cap) return tfail("a read is longer than the dense workspace (raise HM_DENSE_ROWS)");
                 if (rows + need > s->rows_cap) break;
+                if (compact_mode() && b.h_read_pref && r1 > r) {
+                    // compact buffers hold one row per site of a context: keep every context's sites within compact_cap
+                    const uint32_t* p0 = b.h_read_pref + 4 * (size_t)r;
+                    const uint32_t* p1 = b.h_read_pref + 4 * (size_t)(r1 + 1);
+                    const uint32_t worst = std::max(std::max(p1[0] - p0[0], p1[1] - p0[1]), (p1[2] - p0[2]) + (p1[3] - p0[3]));
+                    if (worst > s->compact_cap) break;
+                }
                 rows += need;
             }
             ++r1;
@@ -763,11 +811,12 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
             const uint32_t first_b = c == 2 ? first[3] + p0[3] : 0u, n_b = c == 2 ? p1[3] - p0[3] : 0u;
             const uint32_t n = n_a + n_b;
             if (!n) continue;
-            if (n > s->rows_cap) return tfail("internal: more sites than dense rows in a sub-batch");
+            if (n > s->compact_cap) return tfail("internal: more sites than compact rows in a sub-batch");
+            TCUDA("site rows", cudaMemsetAsync(s->d_site_of_row, 0xff, ((size_t)nt * kTileRows + kSlackRows) * sizeof(int32_t), stream));
             const uint32_t n_pad = ((n + kTileRows - 1) / kTileRows) * kTileRows;
             site_rows_kernel<<<(n_pad + 255) / 256, 256, 0, stream>>>(s->d_track_row, s->d_track_row + s->reads_cap, b.d_base_off, b.d_site_read,
                                                                       b.d_site_pos, first_a, n_a, first_b, n, n_pad, sb.gtile0 * kTileRows,
-                                                                      s->d_site_rows);
+                                                                      s->d_site_rows, s->d_site_of_row);
             int op_i = 0;
             for (const DevOp& d : models[c].p->ops) {
                 if (prof) { cudaEventCreate(&pe[np]); cudaEventRecord(pe[np], stream); pk[np++] = c * 64 + op_i; }

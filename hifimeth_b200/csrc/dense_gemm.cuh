@@ -32,6 +32,7 @@ namespace hm {
 constexpr int kTileRows = 128;
 constexpr int kMaxTerms = 3;
 constexpr int kMaxSegs = 3;
+constexpr int kMaxScatter = 5;
 constexpr int kProducerWarps = 8;
 constexpr int kEpilogueWarps = 8;  // two per TMEM lane group; 32-column chunks alternate between the two
 constexpr int kDenseThreads = 32 * (kProducerWarps + 1 + kEpilogueWarps);
@@ -79,6 +80,14 @@ struct DenseOp {
     const float* w2;         // mode 1: [2][n]
     const float* b2;         // mode 1: [2]
     float* logits;           // mode 1: [rows][2]
+    // Scatter (dense ops whose output is later read at site rows): besides its own map the epilogue copies row r into
+    // compact row site_of_row[r - sc_shift[k]] of compact buffer k, so that the compact ops read gathered operands with
+    // full-line bulk copies (a 16-byte gather costs a 128-byte DRAM fetch: 8x read amplification, profiles/).
+    int32_t n_scatter;
+    int32_t sc_shift[kMaxScatter];
+    uint8_t* sc_out[kMaxScatter];     // plane 0 (hi, g = 0) of compact buffer k (same channel count as the output map)
+    unsigned long long sc_plane_stride;
+    const int32_t* site_of_row;       // [rows] compact row of the site whose s-row this is, or -1
     long long* dbg;          // variant & 32: CTA 0 writes clock64 stamps: [0..255] stage issue, [256..511] stage full seen by the MMA warp
     uint32_t variant;        // experiments (tools/dense_microbench.py): 1 = hi*hi pass only, 2 = no MMA, 4 = no epilogue stores, 8 = no epilogue work, 16 = plain arrive instead of tcgen05.commit on the ring (only with 2), 64 = producers free-run (no consumer)
 };
@@ -86,6 +95,51 @@ struct DenseOp {
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b)
 {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// Epilogue of one 32-column chunk of one row: ReLU'd values -> hi/lo bf16 -> the op's own map (plane layout) and the
+// compact scatter copies.  msc[k] = compact row for scatter k, or -1.
+__device__ __forceinline__ void epilogue_store_chunk(const DenseOp& op, unsigned long long row, int c0, const float (&f)[32],
+                                                     const int (&msc)[kMaxScatter], bool skip_store)
+{
+    const uint32_t g0 = op.out_g0 + ((uint32_t)c0 >> 3);
+    uint8_t* p_hi = op.out + (unsigned long long)g0 * op.out_plane_stride + row * 16ull;
+    uint8_t* p_lo = p_hi + (unsigned long long)op.out_groups * op.out_plane_stride;
+    #pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint32_t hi[4], lo[4];
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            // hi = bf16(x) for two values in one cvt; lo = bf16(x - hi), hi widened back with integer ops
+            const float x0 = f[8 * g + 2 * j], x1 = f[8 * g + 2 * j + 1];
+            const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+            const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+            const __nv_bfloat162 e = __floats2bfloat162_rn(x0 - __uint_as_float(hb << 16), x1 - __uint_as_float(hb & 0xffff0000u));
+            hi[j] = hb;
+            lo[j] = *reinterpret_cast<const uint32_t*>(&e);
+        }
+        if (skip_store) continue;
+        const uint4 vh = make_uint4(hi[0], hi[1], hi[2], hi[3]), vl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(p_hi + g * op.out_plane_stride) = vh;
+        *reinterpret_cast<uint4*>(p_lo + g * op.out_plane_stride) = vl;
+        #pragma unroll
+        for (int k = 0; k < kMaxScatter; ++k) {
+            if (k < op.n_scatter && msc[k] >= 0) {
+                uint8_t* q = op.sc_out[k] + (unsigned long long)(g0 + g) * op.sc_plane_stride + (unsigned long long)msc[k] * 16ull;
+                *reinterpret_cast<uint4*>(q) = vh;
+                *reinterpret_cast<uint4*>(q + (unsigned long long)op.out_groups * op.sc_plane_stride) = vl;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void scatter_rows(const DenseOp& op, unsigned long long row, int (&msc)[kMaxScatter])
+{
+    #pragma unroll
+    for (int k = 0; k < kMaxScatter; ++k) {
+        msc[k] = -1;
+        if (k < op.n_scatter && row >= (unsigned long long)op.sc_shift[k]) msc[k] = __ldg(op.site_of_row + (row - (unsigned long long)op.sc_shift[k]));
+    }
 }
 
 // Shared memory: [weights image][ring stages][barriers]
@@ -296,6 +350,8 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel_t(const __
             const uint32_t t_addr = tmem_base + (lane_grp << 16) + buf * acc_stride;
             const unsigned long long row = (unsigned long long)tile * kTileRows + m;
             float l0 = 0.f, l1 = 0.f;
+            int msc[kMaxScatter];
+            scatter_rows(op, row, msc);
             // map form: chunks alternate between the two warps of a lane group; head form: the first warp does all
             const int c_first = op.mode == 0 ? (int)half * 32 : 0, c_step = op.mode == 0 ? 64 : 32;
             const int c_end = (op.mode == 0 || half == 0) && !(variant & 8u) ? n : 0;
@@ -313,26 +369,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel_t(const __
                     f[j + 3] = fmaxf(__uint_as_float(v[j + 3]) + bv.w, 0.f);
                 }
                 if (op.mode == 0) {
-                    const uint32_t g0 = op.out_g0 + ((uint32_t)c0 >> 3);
-                    uint8_t* p_hi = op.out + (unsigned long long)g0 * op.out_plane_stride + row * 16ull;
-                    uint8_t* p_lo = p_hi + (unsigned long long)op.out_groups * op.out_plane_stride;
-                    #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        uint32_t hi[4], lo[4];
-                        #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            // hi = bf16(x) for two values in one cvt; lo = bf16(x - hi), hi widened back with integer ops
-                            const float x0 = f[8 * g + 2 * j], x1 = f[8 * g + 2 * j + 1];
-                            const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-                            const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
-                            const __nv_bfloat162 e = __floats2bfloat162_rn(x0 - __uint_as_float(hb << 16), x1 - __uint_as_float(hb & 0xffff0000u));
-                            hi[j] = hb;
-                            lo[j] = *reinterpret_cast<const uint32_t*>(&e);
-                        }
-                        if (variant & 4u) continue;
-                        *reinterpret_cast<uint4*>(p_hi + g * op.out_plane_stride) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<uint4*>(p_lo + g * op.out_plane_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    }
+                    epilogue_store_chunk(op, row, c0, f, msc, (variant & 4u) != 0);
                 } else {
                     #pragma unroll
                     for (int j = 0; j < 32; ++j) {

@@ -165,6 +165,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) de
             umma::tc_fence_after();
             const uint32_t t_addr = tmem_base + (lane_grp << 16) + buf * acc_stride;
             const unsigned long long row = (unsigned long long)(2 * t2 + rank) * kTileRows + m;
+            int msc[kMaxScatter];
+            scatter_rows(op, row, msc);
             for (int c0 = (int)half * 32; c0 < n; c0 += 64) {
                 uint32_t v[32];
                 umma::tmem_ld32(t_addr + (uint32_t)c0, v);
@@ -178,24 +180,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) de
                     f[j + 2] = fmaxf(__uint_as_float(v[j + 2]) + bv.z, 0.f);
                     f[j + 3] = fmaxf(__uint_as_float(v[j + 3]) + bv.w, 0.f);
                 }
-                const uint32_t g0 = op.out_g0 + ((uint32_t)c0 >> 3);
-                uint8_t* p_hi = op.out + (unsigned long long)g0 * op.out_plane_stride + row * 16ull;
-                uint8_t* p_lo = p_hi + (unsigned long long)op.out_groups * op.out_plane_stride;
-                #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint32_t hi[4], lo[4];
-                    #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float x0 = f[8 * g + 2 * j], x1 = f[8 * g + 2 * j + 1];
-                        const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-                        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
-                        const __nv_bfloat162 e = __floats2bfloat162_rn(x0 - __uint_as_float(hb << 16), x1 - __uint_as_float(hb & 0xffff0000u));
-                        hi[j] = hb;
-                        lo[j] = *reinterpret_cast<const uint32_t*>(&e);
-                    }
-                    *reinterpret_cast<uint4*>(p_hi + g * op.out_plane_stride) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4*>(p_lo + g * op.out_plane_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                }
+                epilogue_store_chunk(op, row, c0, f, msc, false);
             }
             umma::tc_fence_before();
             __syncwarp();
