@@ -277,7 +277,8 @@ bool lower_op(const HostOp& h, int n0, int n, DevOp& d, std::vector<uint8_t>& bl
     p.n_scatter = (int)h.scatter.size();
     for (int k = 0; k < p.n_scatter; ++k) { p.sc_shift[k] = h.scatter[k].first; d.sc_map[k] = h.scatter[k].second; }
     if (p.n_scatter && (n0 != 0 || n != h.cout)) { err = "a scattering op cannot be split over output channels"; return false; }
-    if (two_cta && (h.compact || h.head || h.conv1_taps > 0 || n0 != 0 || n != h.cout || n % 32)) { err = "op not eligible for the CTA-pair form"; return false; }
+    for (const HostTerm& t : h.terms) if (two_cta && t.gather) { err = "op not eligible for the CTA-pair form"; return false; }
+    if (two_cta && (h.head || h.conv1_taps > 0 || n0 != 0 || n != h.cout || n % 32)) { err = "op not eligible for the CTA-pair form"; return false; }
     p.gather_taps = 0;
     p.gather_rows = nullptr;
     if (h.conv1_taps > 0) {
@@ -396,6 +397,12 @@ void bind_blob(DevOp& d, const uint8_t* blob)
 bool pdl_enabled()
 {
     static const bool v = getenv("HM_NO_PDL") == nullptr;
+    return v;
+}
+
+bool pair_compact()
+{
+    static const bool v = getenv("HM_NO_PAIR_COMPACT") == nullptr;
     return v;
 }
 
@@ -547,7 +554,8 @@ int tensor_model_build(TensorModelHandle& m, const CnnModel& host)
     for (const HostOp& h : plan) {
         // an op whose resident weights leave no room for the activation ring is split over output channels
         // dense layers with > 64 KiB of weights (conv2 .. conv6) run as CTA pairs: half the weights per SM, deep ring
-        if (two_cta_enabled() && !h.compact && !h.head && h.conv1_taps == 0 && (size_t)h.cin * h.cout * h.terms.size() * 4 > (64u << 10)) {
+        if (two_cta_enabled() && (!h.compact || pair_compact()) && !h.head && h.conv1_taps == 0 && h.cout % 32 == 0 &&
+            (size_t)h.cin * h.cout * h.terms.size() * 4 > ((h.compact ? 32u : 64u) << 10)) {
             DevOp d;
             std::vector<uint8_t> trial = blob;
             if (lower_op(h, 0, h.cout, d, trial, err, true)) {

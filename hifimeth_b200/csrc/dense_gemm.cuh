@@ -102,9 +102,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
 __device__ __forceinline__ void epilogue_store_chunk(const DenseOp& op, unsigned long long row, int c0, const float (&f)[32],
                                                      const int (&msc)[kMaxScatter], bool skip_store)
 {
-    const uint32_t g0 = op.out_g0 + ((uint32_t)c0 >> 3);
-    uint8_t* p_hi = op.out + (unsigned long long)g0 * op.out_plane_stride + row * 16ull;
-    uint8_t* p_lo = p_hi + (unsigned long long)op.out_groups * op.out_plane_stride;
+    uint4 vh[4], vl[4];
     #pragma unroll
     for (int g = 0; g < 4; ++g) {
         uint32_t hi[4], lo[4];
@@ -118,16 +116,30 @@ __device__ __forceinline__ void epilogue_store_chunk(const DenseOp& op, unsigned
             hi[j] = hb;
             lo[j] = *reinterpret_cast<const uint32_t*>(&e);
         }
-        if (skip_store) continue;
-        const uint4 vh = make_uint4(hi[0], hi[1], hi[2], hi[3]), vl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        *reinterpret_cast<uint4*>(p_hi + g * op.out_plane_stride) = vh;
-        *reinterpret_cast<uint4*>(p_lo + g * op.out_plane_stride) = vl;
+        vh[g] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        vl[g] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    if (skip_store) return;
+    const uint32_t g0 = op.out_g0 + ((uint32_t)c0 >> 3);
+    {
+        uint8_t* p_hi = op.out + (unsigned long long)g0 * op.out_plane_stride + row * 16ull;
+        uint8_t* p_lo = p_hi + (unsigned long long)op.out_groups * op.out_plane_stride;
         #pragma unroll
-        for (int k = 0; k < kMaxScatter; ++k) {
-            if (k < op.n_scatter && msc[k] >= 0) {
-                uint8_t* q = op.sc_out[k] + (unsigned long long)(g0 + g) * op.sc_plane_stride + (unsigned long long)msc[k] * 16ull;
-                *reinterpret_cast<uint4*>(q) = vh;
-                *reinterpret_cast<uint4*>(q + (unsigned long long)op.out_groups * op.sc_plane_stride) = vl;
+        for (int g = 0; g < 4; ++g) {
+            *reinterpret_cast<uint4*>(p_hi + g * op.out_plane_stride) = vh[g];
+            *reinterpret_cast<uint4*>(p_lo + g * op.out_plane_stride) = vl[g];
+        }
+    }
+    // compact copies: msc[k] = -1 for rows that feed no site (and for k >= n_scatter)
+    #pragma unroll
+    for (int k = 0; k < kMaxScatter; ++k) {
+        if (msc[k] >= 0) {
+            uint8_t* q_hi = op.sc_out[k] + (unsigned long long)g0 * op.sc_plane_stride + (unsigned long long)msc[k] * 16ull;
+            uint8_t* q_lo = q_hi + (unsigned long long)op.out_groups * op.sc_plane_stride;
+            #pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                *reinterpret_cast<uint4*>(q_hi + g * op.sc_plane_stride) = vh[g];
+                *reinterpret_cast<uint4*>(q_lo + g * op.sc_plane_stride) = vl[g];
             }
         }
     }
