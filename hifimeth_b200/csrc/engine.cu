@@ -16,6 +16,7 @@
 #include "cnn_tensor.cuh"
 #include "kernels_cnn_fp32.cuh"
 #include "kernels_front.cuh"
+#include "kernels_mm.cuh"
 #include "onnx_weights.h"
 
 namespace {
@@ -60,6 +61,13 @@ struct Slot {
     uint32_t *h_call_off = nullptr, *h_n_fwd = nullptr, *h_totals = nullptr;
     int32_t* h_qoff = nullptr;
     uint8_t* h_ml = nullptr;
+    // MM skip-count text (row N1; HM_SUBMIT_MM_TEXT)
+    uint32_t *d_mm_delta = nullptr, *d_mm_bsum = nullptr, *d_mm_boff = nullptr, *d_mm_toff = nullptr, *d_mm_off = nullptr, *d_mm_fwd_len = nullptr;
+    uint8_t* d_mm_text = nullptr;
+    uint32_t *h_mm_off = nullptr, *h_mm_fwd_len = nullptr, *h_mm_total = nullptr;
+    uint8_t* h_mm_text = nullptr;
+    size_t mm_text_cap = 0;
+    bool mm_valid = false;
     // fp32 CNN workspace (site chunk)
     float* d_feat = nullptr;
     float* d_act[8] = {};
@@ -186,6 +194,8 @@ void free_slot(Slot& s)
     cudaFreeHost(s.host.valid); cudaFreeHost(s.host.fi); cudaFreeHost(s.host.fp); cudaFreeHost(s.host.ri); cudaFreeHost(s.host.rp);
     cudaFreeHost(s.h_chunk_read); cudaFreeHost(s.h_chunk_pos); cudaFreeHost(s.h_read_first_chunk);
     cudaFreeHost(s.h_read_pref); cudaFree(s.d_read_pref);
+    cudaFree(s.d_mm_delta); cudaFree(s.d_mm_bsum); cudaFree(s.d_mm_boff); cudaFree(s.d_mm_toff); cudaFree(s.d_mm_off); cudaFree(s.d_mm_fwd_len);
+    cudaFree(s.d_mm_text); cudaFreeHost(s.h_mm_off); cudaFreeHost(s.h_mm_fwd_len); cudaFreeHost(s.h_mm_total); cudaFreeHost(s.h_mm_text);
     cudaFreeHost(s.h_call_off); cudaFreeHost(s.h_n_fwd); cudaFreeHost(s.h_totals); cudaFreeHost(s.h_qoff); cudaFreeHost(s.h_ml);
     void* dev[] = {s.d_seq4, s.d_fi, s.d_fp, s.d_ri, s.d_rp, s.d_valid, s.d_base_off, s.d_seq_off, s.d_flag, s.d_chunk_read,
                    s.d_chunk_pos, s.d_read_first_chunk, s.d_bcode, s.d_kinf, s.d_chunk_cnt, s.d_pref, s.d_totals, s.d_site_read,
@@ -252,6 +262,18 @@ int alloc_slot(hm_engine* e, Slot& s)
     HM_CUDA(e, st, dmalloc(&s.d_ml, B));
     HM_CUDA(e, st, dmalloc(&s.d_call_ctx, B));
     HM_CUDA(e, st, dmalloc(&s.d_logits, 2 * B));
+    s.mm_text_cap = 3 * B + 64;  // ",0" is 2 bytes per call; a skip count of d digits needs d skipped bases
+    HM_CUDA(e, st, dmalloc(&s.d_mm_delta, B));
+    HM_CUDA(e, st, dmalloc(&s.d_mm_bsum, B / hm::kMmBlock + 2));
+    HM_CUDA(e, st, dmalloc(&s.d_mm_boff, B / hm::kMmBlock + 2));
+    HM_CUDA(e, st, dmalloc(&s.d_mm_toff, B + 1));
+    HM_CUDA(e, st, dmalloc(&s.d_mm_off, R + 1));
+    HM_CUDA(e, st, dmalloc(&s.d_mm_fwd_len, R));
+    HM_CUDA(e, st, dmalloc(&s.d_mm_text, s.mm_text_cap));
+    HM_CUDA(e, st, hmalloc(&s.h_mm_off, R + 1));
+    HM_CUDA(e, st, hmalloc(&s.h_mm_fwd_len, R));
+    HM_CUDA(e, st, hmalloc(&s.h_mm_total, 1));
+    HM_CUDA(e, st, hmalloc(&s.h_mm_text, s.mm_text_cap));
     if (e->cfg.cnn_mode == HM_CNN_FP32_SIMT) {
         const size_t S = e->site_chunk;
         HM_CUDA(e, st, dmalloc(&s.d_feat, S * HM_KMER * HM_FEATURES_PER_BASE));
@@ -516,6 +538,27 @@ int hm_batch_submit(hm_engine* e, int slot, uint32_t n_reads, uint32_t flags)
     memcpy(s.totals, s.h_totals, sizeof(s.totals));
     s.n_calls = s.totals[4];
     if (s.n_calls > e->cfg.max_bases) return fail(e, HM_ERR_STATE, "internal: %u calls exceed capacity", s.n_calls);
+    const bool want_mm = (flags & HM_SUBMIT_MM_TEXT) != 0;
+    s.mm_valid = false;
+    if (want_mm) {
+        // row N1: MM skip counts + their decimal text from the resident forward-strand codes (independent of the CNN)
+        *s.h_mm_total = 0;
+        if (s.n_calls) {
+            const uint32_t nb = (s.n_calls + hm::kMmBlock - 1) / hm::kMmBlock;
+            hm::mm_delta_kernel<<<nb, hm::kMmBlock, 0, st>>>(s.d_bcode, s.d_base_off, s.d_call_off, s.d_n_fwd, s.d_qoff, s.n_reads, s.n_calls,
+                                                            s.d_mm_delta, s.d_mm_bsum);
+            hm::mm_scan_blocks_kernel<<<1, 1024, 0, st>>>(s.d_mm_bsum, nb, s.d_mm_boff);
+            hm::mm_write_kernel<<<nb, hm::kMmBlock, 0, st>>>(s.d_mm_delta, s.d_mm_boff, s.n_calls, (uint32_t)s.mm_text_cap, s.d_mm_toff, s.d_mm_text);
+            hm::mm_read_offsets_kernel<<<(s.n_reads + 256) / 256, 256, 0, st>>>(s.d_mm_toff, s.d_call_off, s.d_n_fwd, s.n_reads, s.d_mm_off, s.d_mm_fwd_len);
+            launches += 4;
+            HM_CUDA(e, "MM text", cudaGetLastError());
+            HM_CUDA(e, "MM text", cudaMemcpyAsync(s.h_mm_total, s.d_mm_toff + s.n_calls, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        } else {
+            HM_CUDA(e, "MM text", cudaMemsetAsync(s.d_mm_off, 0, (s.n_reads + 1) * sizeof(uint32_t), st));
+            HM_CUDA(e, "MM text", cudaMemsetAsync(s.d_mm_fwd_len, 0, std::max<size_t>(s.n_reads, 1) * sizeof(uint32_t), st));
+        }
+        HM_CUDA(e, "MM text", cudaEventRecord(s.ev[6], st));
+    }
     if ((rc = stage_cnn(e, s, launches))) return rc;
     HM_CUDA(e, "CNN", cudaEventRecord(s.ev[4], st));
     if (!(flags & HM_SUBMIT_SKIP_D2H)) {
@@ -526,6 +569,14 @@ int hm_batch_submit(hm_engine* e, int slot, uint32_t n_reads, uint32_t flags)
         HM_CUDA(e, stg, cp(s.h_n_fwd, s.d_n_fwd, s.n_reads * sizeof(uint32_t)));
         HM_CUDA(e, stg, cp(s.h_qoff, s.d_qoff, (size_t)s.n_calls * sizeof(int32_t)));
         HM_CUDA(e, stg, cp(s.h_ml, s.d_ml, s.n_calls));
+        if (want_mm) {
+            HM_CUDA(e, stg, cudaEventSynchronize(s.ev[6]));  // total text bytes; those kernels ran ahead of the CNN
+            if (*s.h_mm_total > s.mm_text_cap) return fail(e, HM_ERR_STATE, "MM text of %u bytes exceeds the staging capacity", *s.h_mm_total);
+            HM_CUDA(e, stg, cp(s.h_mm_text, s.d_mm_text, *s.h_mm_total));
+            HM_CUDA(e, stg, cp(s.h_mm_off, s.d_mm_off, (s.n_reads + 1) * sizeof(uint32_t)));
+            HM_CUDA(e, stg, cp(s.h_mm_fwd_len, s.d_mm_fwd_len, s.n_reads * sizeof(uint32_t)));
+            s.mm_valid = true;
+        }
         s.timing.d2h_bytes = bytes + 5 * sizeof(uint32_t);
     }
     HM_CUDA(e, "submit", cudaEventRecord(s.ev[5], st));
@@ -560,6 +611,9 @@ int hm_batch_collect(hm_engine* e, int slot, hm_call_batch* out)
     out->n_sites[0] = s.totals[0];
     out->n_sites[1] = s.totals[1];
     out->n_sites[2] = (uint64_t)s.totals[2] + s.totals[3];
+    out->mm_text = s.mm_valid ? s.h_mm_text : nullptr;
+    out->mm_off = s.mm_valid ? s.h_mm_off : nullptr;
+    out->mm_fwd_len = s.mm_valid ? s.h_mm_fwd_len : nullptr;
     s.collected = true;
     return HM_OK;
 }

@@ -167,23 +167,17 @@ int hm_pack_record(hm_read_batch* b, uint32_t* n_reads, const uint8_t* body, siz
     return HM_OK;
 }
 
-size_t hm_mod_record_bound(size_t len, uint32_t n_calls) { return len + 64 + 12 * (size_t)n_calls; }
-
-int hm_build_mod_record(const uint8_t* body, size_t len, int keep_kinetics, const int32_t* fwd_qoff,
-                        const uint8_t* fwd_ml, uint32_t n_fwd, const int32_t* rev_qoff, const uint8_t* rev_ml,
-                        uint32_t n_rev, uint8_t* out, size_t* out_len)
+// Copies the record up to the aux block and filters the tags the way s_remove_skipped_tags + bam_aux_update_int do
+// (src/corelib/build_mod_bam.cpp:87-109,178-247): drops fi/ri/fp/rp (unless -k), the first ML and MM; an existing integer MN is
+// rewritten in place when there are calls.  Returns the output length so far.
+static size_t strip_tags(const uint8_t* body, size_t len, const RecLayout& r, int keep_kinetics, bool have_calls, uint8_t* out,
+                         bool& mn_written)
 {
-    RecLayout r;
-    if (!body || !out || !out_len || !layout_of(body, len, r)) return HM_ERR_FORMAT;
-    const bool have_calls = (n_fwd + n_rev) > 0;
     memcpy(out, body, r.aux_off);
     size_t o = r.aux_off;
-
-    // One filtering pass == the reference's delete-by-name sequence: first fi/ri/fp/rp (unless -k),
-    // then the first ML and the first MM; an existing integer MN is rewritten in place.
     bool dropped[6] = {false, false, false, false, false, false};
     static const char names[6][2] = {{'f', 'i'}, {'r', 'i'}, {'f', 'p'}, {'r', 'p'}, {'M', 'L'}, {'M', 'M'}};
-    bool mn_written = false;
+    mn_written = false;
     size_t p = r.aux_off;
     AuxField f;
     while (p < len) {
@@ -210,6 +204,20 @@ int hm_build_mod_record(const uint8_t* body, size_t len, int keep_kinetics, cons
         }
         p = f.end_off;
     }
+    return o;
+}
+
+size_t hm_mod_record_bound(size_t len, uint32_t n_calls) { return len + 64 + 12 * (size_t)n_calls; }
+
+int hm_build_mod_record(const uint8_t* body, size_t len, int keep_kinetics, const int32_t* fwd_qoff,
+                        const uint8_t* fwd_ml, uint32_t n_fwd, const int32_t* rev_qoff, const uint8_t* rev_ml,
+                        uint32_t n_rev, uint8_t* out, size_t* out_len)
+{
+    RecLayout r;
+    if (!body || !out || !out_len || !layout_of(body, len, r)) return HM_ERR_FORMAT;
+    const bool have_calls = (n_fwd + n_rev) > 0;
+    bool mn_written = false;
+    size_t o = strip_tags(body, len, r, keep_kinetics, have_calls, out, mn_written);
     if (!have_calls) { *out_len = o; return HM_OK; }
 
     // forward-strand base at original-read offset k: get_bam_fwd_strand_base (bam_info.cpp:224-232)
@@ -249,6 +257,37 @@ int hm_build_mod_record(const uint8_t* body, size_t len, int keep_kinetics, cons
     o += n_fwd;
     if (n_rev) memcpy(out + o, rev_ml, n_rev);
     o += n_rev;
+    if (!mn_written) o += put_mn(out + o, r.l_seq);
+    *out_len = o;
+    return HM_OK;
+}
+
+int hm_build_mod_record_mm(const uint8_t* body, size_t len, int keep_kinetics, const uint8_t* mm_fwd, uint32_t mm_fwd_len,
+                           const uint8_t* mm_rev, uint32_t mm_rev_len, const uint8_t* ml, uint32_t n_fwd, uint32_t n_rev, uint8_t* out,
+                           size_t* out_len)
+{
+    RecLayout r;
+    if (!body || !out || !out_len || !layout_of(body, len, r)) return HM_ERR_FORMAT;
+    const bool have_calls = (n_fwd + n_rev) > 0;
+    if (have_calls && (!ml || (n_fwd && !mm_fwd) || (n_rev && !mm_rev))) return HM_ERR_ARG;
+    bool mn_written = false;
+    size_t o = strip_tags(body, len, r, keep_kinetics, have_calls, out, mn_written);
+    if (!have_calls) { *out_len = o; return HM_OK; }
+    out[o++] = 'M'; out[o++] = 'M'; out[o++] = 'Z';
+    out[o++] = 'C'; out[o++] = '+'; out[o++] = 'm';
+    if (mm_fwd_len) memcpy(out + o, mm_fwd, mm_fwd_len);
+    o += mm_fwd_len;
+    out[o++] = ';';
+    out[o++] = 'G'; out[o++] = '-'; out[o++] = 'm';
+    if (mm_rev_len) memcpy(out + o, mm_rev, mm_rev_len);
+    o += mm_rev_len;
+    out[o++] = ';';
+    out[o++] = 0;
+    out[o++] = 'M'; out[o++] = 'L'; out[o++] = 'B'; out[o++] = 'C';
+    const uint32_t cnt = n_fwd + n_rev;
+    memcpy(out + o, &cnt, 4); o += 4;
+    memcpy(out + o, ml, cnt);
+    o += cnt;
     if (!mn_written) o += put_mn(out + o, r.l_seq);
     *out_len = o;
     return HM_OK;

@@ -19,7 +19,7 @@ DEFAULT_MODEL_DIR = PKG.parent / "models"
 
 HM_CTX_CPG, HM_CTX_CHG, HM_CTX_CHH = 1, 2, 4
 HM_CNN_TENSOR, HM_CNN_FP32_SIMT = 0, 1
-HM_SUBMIT_SKIP_H2D, HM_SUBMIT_SKIP_D2H = 1, 2
+HM_SUBMIT_SKIP_H2D, HM_SUBMIT_SKIP_D2H, HM_SUBMIT_MM_TEXT = 1, 2, 4
 
 _u8p = C.POINTER(C.c_uint8)
 _u16p = C.POINTER(C.c_uint16)
@@ -45,7 +45,7 @@ class hm_read_batch(C.Structure):
 
 class hm_call_batch(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_calls", C.c_uint32), ("call_off", _u32p), ("n_fwd", _u32p), ("qoff", _i32p),
-                ("ml", _u8p), ("n_sites", C.c_uint64 * 3)]
+                ("ml", _u8p), ("n_sites", C.c_uint64 * 3), ("mm_text", _u8p), ("mm_off", _u32p), ("mm_fwd_len", _u32p)]
 
 
 class hm_timing(C.Structure):
@@ -56,7 +56,7 @@ class hm_timing(C.Structure):
 
 ABI_SYMBOLS = ["hm_engine_create", "hm_engine_destroy", "hm_last_error", "hm_version", "hm_batch_acquire", "hm_batch_submit",
                "hm_batch_collect", "hm_batch_timing", "hm_codev1_encode", "hm_codev1_decode", "hm_pack_record",
-               "hm_mod_record_bound", "hm_build_mod_record", "hm_debug_dump_decode", "hm_debug_dump_ctx",
+               "hm_mod_record_bound", "hm_build_mod_record", "hm_build_mod_record_mm", "hm_debug_dump_decode", "hm_debug_dump_ctx",
                "hm_debug_dump_features", "hm_debug_dump_logits", "hm_debug_dense_op", "hm_debug_last_op_ms", "hm_microbench"]
 
 _lib = None
@@ -89,6 +89,8 @@ def load_library() -> C.CDLL:
     L.hm_mod_record_bound.restype = C.c_size_t
     L.hm_build_mod_record.argtypes = [_u8p, C.c_size_t, C.c_int, _i32p, _u8p, C.c_uint32, _i32p, _u8p, C.c_uint32, _u8p,
                                       C.POINTER(C.c_size_t)]
+    L.hm_build_mod_record_mm.argtypes = [_u8p, C.c_size_t, C.c_int, _u8p, C.c_uint32, _u8p, C.c_uint32, _u8p, C.c_uint32, C.c_uint32, _u8p,
+                                         C.POINTER(C.c_size_t)]
     L.hm_debug_dump_decode.argtypes = [C.c_void_p, C.c_int, _u16p, _u16p, _u16p, _u16p, _u8p, _u8p]
     L.hm_debug_dump_ctx.argtypes = [C.c_void_p, C.c_int, _u8p]
     L.hm_debug_dump_features.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, _f32p]
@@ -117,6 +119,14 @@ class CallBatch:
     qoff: np.ndarray
     ml: np.ndarray
     n_sites: tuple
+    mm_text: np.ndarray = None     # HM_SUBMIT_MM_TEXT: device-built MM skip-count text
+    mm_off: np.ndarray = None
+    mm_fwd_len: np.ndarray = None
+
+    def read_mm(self, r: int):
+        """(fwd text, rev text) of read r: the ",d,d,..." runs that follow "C+m" and "G-m" in its MM tag."""
+        a, b, nf = int(self.mm_off[r]), int(self.mm_off[r + 1]), int(self.mm_fwd_len[r])
+        return self.mm_text[a:a + nf], self.mm_text[a + nf:b]
 
     def read_calls(self, r: int):
         """(fwd_qoff, fwd_ml, rev_qoff, rev_ml) of read r: the argument lists of build_one_mod_bam."""
@@ -194,18 +204,23 @@ class Engine:
         c = hm_call_batch()
         self._check(self.lib.hm_batch_collect(self.h, slot, C.byref(c)), "hm_batch_collect")
         f = (lambda a: a.copy()) if copy else (lambda a: a)
-        return CallBatch(c.n_reads, c.n_calls, f(_view(c.call_off, c.n_reads + 1, np.uint32)), f(_view(c.n_fwd, c.n_reads, np.uint32)),
-                         f(_view(c.qoff, c.n_calls, np.int32)), f(_view(c.ml, c.n_calls, np.uint8)), tuple(int(x) for x in c.n_sites))
+        out = CallBatch(c.n_reads, c.n_calls, f(_view(c.call_off, c.n_reads + 1, np.uint32)), f(_view(c.n_fwd, c.n_reads, np.uint32)),
+                        f(_view(c.qoff, c.n_calls, np.int32)), f(_view(c.ml, c.n_calls, np.uint8)), tuple(int(x) for x in c.n_sites))
+        if c.mm_off:
+            out.mm_off = f(_view(c.mm_off, c.n_reads + 1, np.uint32))
+            out.mm_fwd_len = f(_view(c.mm_fwd_len, c.n_reads, np.uint32))
+            out.mm_text = f(_view(c.mm_text, int(out.mm_off[-1]), np.uint8))
+        return out
 
     def timing(self, slot: int) -> hm_timing:
         t = hm_timing()
         self._check(self.lib.hm_batch_timing(self.h, slot, C.byref(t)), "hm_batch_timing")
         return t
 
-    def call(self, batch, slot: int = 0) -> CallBatch:
+    def call(self, batch, slot: int = 0, flags: int = 0) -> CallBatch:
         """Public one-shot API: host batch in, host calls out (H2D + kernels + D2H)."""
         n = self.stage(slot, batch)
-        self.submit(slot, n)
+        self.submit(slot, n, flags)
         return self.collect(slot)
 
     # -- validation hooks ---------------------------------------------------------------------------------------
@@ -312,3 +327,18 @@ def debug_dense_op(srcs, terms, bias, rows: int, conv1_taps: int = 0, w2=None, b
     if rc != 0:
         raise HmError(f"hm_debug_dense_op failed ({rc}): {L.hm_last_error(None).decode()}")
     return out
+
+
+def build_mod_record_mm(body: bytes, keep_kinetics: bool, mm_fwd, mm_rev, ml, n_fwd: int, n_rev: int) -> bytes:
+    """hm_build_mod_record_mm: the record from device-built MM text (no per-base loop on the host)."""
+    L = load_library()
+    src = np.frombuffer(body, np.uint8)
+    as_u8 = lambda a: np.frombuffer(a, np.uint8) if isinstance(a, (bytes, bytearray)) else np.ascontiguousarray(a, np.uint8)
+    f, r, m = as_u8(mm_fwd), as_u8(mm_rev), as_u8(ml)
+    out = np.empty(len(body) + 64 + len(f) + len(r) + len(m), np.uint8)
+    n = C.c_size_t()
+    rc = L.hm_build_mod_record_mm(src.ctypes.data_as(_u8p), len(body), int(keep_kinetics), f.ctypes.data_as(_u8p), len(f), r.ctypes.data_as(_u8p),
+                                  len(r), m.ctypes.data_as(_u8p), n_fwd, n_rev, out.ctypes.data_as(_u8p), C.byref(n))
+    if rc != 0:
+        raise HmError(f"hm_build_mod_record_mm failed ({rc})")
+    return out[:n.value].tobytes()

@@ -98,6 +98,12 @@ typedef struct hm_call_batch {
     const int32_t* qoff;      /* [n_calls] */
     const uint8_t* ml;        /* [n_calls] scaled_prob = min(255,(int)(255*p1)) (mod_batch.cpp:46-64) */
     uint64_t n_sites[3];      /* CpG, CHG, CHH samples in this batch (mod_main.cpp:364-407 statistics) */
+    /* HM_SUBMIT_MM_TEXT only (else NULL): the skip counts of the MM tag as decimal text, built on the device
+     * (build_one_mod_bam, src/corelib/build_mod_bam.cpp:134-168).  Read r owns mm_text[mm_off[r] .. mm_off[r+1]): first
+     * mm_fwd_len[r] bytes ",d,d,..." for its forward-strand calls, then the same for its reverse-strand calls. */
+    const uint8_t* mm_text;
+    const uint32_t* mm_off;     /* [n_reads+1] */
+    const uint32_t* mm_fwd_len; /* [n_reads] */
 } hm_call_batch;
 
 /* Device-side timing of the last submit of a slot (CUDA events on the slot's stream). */
@@ -111,6 +117,7 @@ typedef struct hm_timing {
 
 #define HM_SUBMIT_SKIP_H2D 1u   /* inputs of this slot are already resident in HBM (re-run) */
 #define HM_SUBMIT_SKIP_D2H 2u   /* leave results on the device (kernel-only timing) */
+#define HM_SUBMIT_MM_TEXT 4u    /* also build the MM skip-count text on the device (hm_call_batch.mm_*) */
 
 typedef struct hm_engine hm_engine;
 
@@ -144,6 +151,13 @@ size_t hm_mod_record_bound(size_t len, uint32_t n_calls);
 int hm_build_mod_record(const uint8_t* body, size_t len, int keep_kinetics, const int32_t* fwd_qoff,
                         const uint8_t* fwd_ml, uint32_t n_fwd, const int32_t* rev_qoff, const uint8_t* rev_ml,
                         uint32_t n_rev, uint8_t* out, size_t* out_len);
+
+/* The same record, with the MM skip-count text taken from hm_call_batch (HM_SUBMIT_MM_TEXT) instead of being recounted
+ * from the sequence: mm_fwd / mm_rev are the ",d,d,..." runs of the read's forward / reverse calls, ml holds the n_fwd
+ * forward bytes followed by the n_rev reverse bytes. */
+int hm_build_mod_record_mm(const uint8_t* body, size_t len, int keep_kinetics, const uint8_t* mm_fwd, uint32_t mm_fwd_len,
+                           const uint8_t* mm_rev, uint32_t mm_rev_len, const uint8_t* ml, uint32_t n_fwd, uint32_t n_rev,
+                           uint8_t* out, size_t* out_len);
 
 /* ---- validation hooks (parity tests; need cfg.keep_debug = 1, call after hm_batch_collect) ------------ */
 

@@ -111,3 +111,29 @@ def test_build_mod_record_rejects_bad_calls(lib_built, golden):
     with pytest.raises(hme.HmError):
         not_c = int(np.nonzero(golden["fwd0"] != 1)[0][0])  # a call on a base that is not C (build_mod_bam.cpp:139-140)
         hme.build_mod_record(body, False, [not_c], [1], [], [])
+
+
+def test_build_mod_record_from_mm_text_vs_golden(lib_built, golden):
+    """hm_build_mod_record_mm (row N1's host half) against the records the REFERENCE's build_mod_bam.cpp produced: the MM text
+    is cut out of the reference record itself, so only the assembly (tag stripping, MM/ML/MN layout) is under test here."""
+    n = 0
+    for i in range(int(golden["n_reads"])):
+        body = golden[f"body{i}"].tobytes()
+        if not golden[f"ok{i}"]:
+            assert hme.build_mod_record_mm(body, False, b"", b"", b"", 0, 0) == golden[f"mod{i}"].tobytes()
+            continue
+        fq, rq, fml, rml = (golden[f"{k}{i}"] for k in ("fq", "rq", "fml", "rml"))
+        want = golden[f"mod{i}"].tobytes()
+        if len(fq) + len(rq) == 0:
+            assert hme.build_mod_record_mm(body, False, b"", b"", b"", 0, 0) == want
+            continue
+        mm = want[want.index(b"MMZC+m") + 3:]
+        mm = mm[:mm.index(b"\0")]
+        fwd_part, rev_part, tail = mm.split(b";")
+        assert fwd_part.startswith(b"C+m") and rev_part.startswith(b"G-m") and tail == b""
+        ml = np.concatenate([fml, rml]).astype(np.uint8)
+        for keep, key in ((False, "mod"), (True, "modkeep")):
+            got = hme.build_mod_record_mm(body, keep, np.frombuffer(fwd_part[3:], np.uint8), np.frombuffer(rev_part[3:], np.uint8), ml, len(fq), len(rq))
+            assert got == golden[f"{key}{i}"].tobytes(), (i, keep)
+        n += 1
+    assert n >= 4

@@ -200,3 +200,42 @@ def test_microbench_kernels_run(eng):
     for name in ("decode", "scan", "gather", "cnn"):
         ms, by, fl = eng.microbench(0, name, 0, 2)
         assert ms > 0 and (by > 0 or fl > 0)
+
+
+def test_mm_text_built_on_device(eng, models):
+    """Row N1: the MM skip-count text comes from the device; records assembled from it equal the oracle's build_one_mod_bam
+    restatement byte for byte (which test_oracle.py pins to the reference's own compiled build_mod_bam.cpp)."""
+    reads = golden_reads()
+    bodies = golden_bodies(reads)
+    batch = hme.pack_records_host(bodies, min_read_len=1000)
+    got = eng.call(batch, slot=0, flags=hme.HM_SUBMIT_MM_TEXT)
+    assert got.mm_off is not None and int(got.mm_off[0]) == 0
+    O = hmoracle.oracle()
+    n_with = 0
+    for r, body in enumerate(bodies):
+        fq, fml, rq, rml = got.read_calls(r)
+        mm_f, mm_r = got.read_mm(r)
+        a, b = int(got.call_off[r]), int(got.call_off[r + 1])
+        rec = hme.build_mod_record_mm(body, False, mm_f, mm_r, got.ml[a:b], len(fq), len(rq))
+        assert rec == O.build_mod_record(body, False, fq, fml, rq, rml), r
+        assert rec == hme.build_mod_record(body, False, fq, fml, rq, rml), r
+        n_with += len(fq) + len(rq) > 0
+    assert n_with >= 4
+    # a context subset skips C's and G's between calls: counts above 9 exercise multi-digit text
+    e2 = hme.Engine(ctx_mask=1, max_reads=16, max_bases=1 << 18, keep_debug=True)
+    try:
+        b2, rd = synth.make_reads(3, (1500, 2500), seed=91, flag_rev_every=2)
+        g2 = e2.call(b2, flags=hme.HM_SUBMIT_MM_TEXT)
+        for r, rr in enumerate(rd):
+            body = synth.record_body(rr)
+            fq, fml, rq, rml = g2.read_calls(r)
+            mm_f, mm_r = g2.read_mm(r)
+            a, b = int(g2.call_off[r]), int(g2.call_off[r + 1])
+            assert hme.build_mod_record_mm(body, True, mm_f, mm_r, g2.ml[a:b], len(fq), len(rq)) == O.build_mod_record(body, True, fq, fml, rq, rml)
+        assert any(bytes(g2.read_mm(r)[0]).count(b",1") for r in range(3))
+    finally:
+        e2.close()
+    # no calls at all: empty text
+    short, _ = synth.make_reads(2, 400, seed=3)
+    g3 = eng.call(short, slot=1, flags=hme.HM_SUBMIT_MM_TEXT)
+    assert g3.n_calls == 0 and int(g3.mm_off[-1]) == 0
