@@ -754,6 +754,17 @@ int hm_microbench(hm_engine* e, int slot, const char* name, uint32_t n_sites, in
         } else if (k == "gather") {
             if (ns) hm::gather_features_kernel<<<ns, 128, 0, st>>>(s.d_bcode, s.d_kinf, s.d_base_off, s.d_site_read, s.d_site_pos, 0, ns, d_tmp);
             bytes = 12832.0 * ns;
+        } else if (k == "mm") {
+            if (s.n_calls) {
+                const uint32_t nb = (s.n_calls + hm::kMmBlock - 1) / hm::kMmBlock;
+                hm::mm_delta_kernel<<<nb, hm::kMmBlock, 0, st>>>(s.d_bcode, s.d_base_off, s.d_call_off, s.d_n_fwd, s.d_qoff, s.n_reads, s.n_calls,
+                                                                s.d_mm_delta, s.d_mm_bsum);
+                hm::mm_scan_blocks_kernel<<<1, 1024, 0, st>>>(s.d_mm_bsum, nb, s.d_mm_boff);
+                hm::mm_write_kernel<<<nb, hm::kMmBlock, 0, st>>>(s.d_mm_delta, s.d_mm_boff, s.n_calls, (uint32_t)s.mm_text_cap, s.d_mm_toff, s.d_mm_text);
+                hm::mm_read_offsets_kernel<<<(s.n_reads + 256) / 256, 256, 0, st>>>(s.d_mm_toff, s.d_call_off, s.d_n_fwd, s.n_reads, s.d_mm_off, s.d_mm_fwd_len);
+            }
+            // forward-strand codes read once (1 B/base), qoff in (4 B/call), delta out + in (8), text offset (4), ~2.3 B of text
+            bytes = 1.0 * s.n_bases + 18.3 * s.n_calls;
         } else if (k == "cnn") {
             hm_timing keep = s.timing;
             int rc = stage_cnn(e, s, launches);

@@ -191,7 +191,7 @@ float hm_debug_last_op_ms(void);
 /* ---- kernel microbenchmarks (BASELINE.json config 5) --------------------------------------------------- */
 /* Runs one named kernel family `iters` times on the slot's resident inputs and returns the mean device
  * time per launch (CUDA events) and the algorithmic bytes / flops one launch processes.
- * name: "decode", "scan", "gather", "cnn". */
+ * name: "decode", "scan", "gather", "cnn", "mm" (row N1: MM skip counts + text). */
 int hm_microbench(hm_engine* e, int slot, const char* name, uint32_t n_sites, int iters, float* ms_per_launch,
                   double* algo_bytes, double* algo_flops);
 

@@ -197,7 +197,7 @@ def test_mod_records_round_trip(eng, models):
 def test_microbench_kernels_run(eng):
     batch, _ = synth.make_reads(4, 2000, seed=41)
     eng.call(batch, slot=0)
-    for name in ("decode", "scan", "gather", "cnn"):
+    for name in ("decode", "scan", "gather", "cnn", "mm"):
         ms, by, fl = eng.microbench(0, name, 0, 2)
         assert ms > 0 and (by > 0 or fl > 0)
 
