@@ -236,11 +236,12 @@ int alloc_slot(hm_engine* e, Slot& s)
     HM_CUDA(e, st, dmalloc(&s.d_read_pref, 4 * (R + 1)));
     HM_CUDA(e, st, hmalloc(&s.h_qoff, B));
     HM_CUDA(e, st, hmalloc(&s.h_ml, B));
-    HM_CUDA(e, st, dmalloc(&s.d_seq4, seq_cap));
-    HM_CUDA(e, st, dmalloc(&s.d_fi, B));
-    HM_CUDA(e, st, dmalloc(&s.d_fp, B));
-    HM_CUDA(e, st, dmalloc(&s.d_ri, B));
-    HM_CUDA(e, st, dmalloc(&s.d_rp, B));
+    // decode_kernel stages with 16-byte loads that may over-read by < 16 bytes: 64 bytes of slack on every input array
+    HM_CUDA(e, st, dmalloc(&s.d_seq4, seq_cap + 64));
+    HM_CUDA(e, st, dmalloc(&s.d_fi, B + 64));
+    HM_CUDA(e, st, dmalloc(&s.d_fp, B + 64));
+    HM_CUDA(e, st, dmalloc(&s.d_ri, B + 64));
+    HM_CUDA(e, st, dmalloc(&s.d_rp, B + 64));
     HM_CUDA(e, st, dmalloc(&s.d_valid, R));
     HM_CUDA(e, st, dmalloc(&s.d_base_off, R + 1));
     HM_CUDA(e, st, dmalloc(&s.d_seq_off, R + 1));
@@ -347,21 +348,21 @@ int stage_front(hm_engine* e, Slot& s, uint32_t& launches)
 {
     const uint32_t nc = s.n_chunks;
     if (nc) {
-        hm::decode_kernel<<<nc, 256, 0, s.stream>>>(s.d_seq4, s.d_fi, s.d_fp, s.d_ri, s.d_rp, s.d_base_off, s.d_seq_off, s.d_flag,
+        hm::decode_kernel<<<nc, hm::kFrontThreads, 0, s.stream>>>(s.d_seq4, s.d_fi, s.d_fp, s.d_ri, s.d_rp, s.d_base_off, s.d_seq_off, s.d_flag,
                                                      s.d_chunk_read, s.d_chunk_pos, s.d_bcode, s.d_kinf);
         ++launches;
     }
     HM_CUDA(e, "decode", cudaGetLastError());
     HM_CUDA(e, "decode", cudaEventRecord(s.ev[2], s.stream));
     if (nc) {
-        hm::scan_count_kernel<<<nc, hm::kChunk, 0, s.stream>>>(s.d_bcode, s.d_base_off, s.d_valid, s.d_chunk_read, s.d_chunk_pos, e->ctx_mask, s.d_chunk_cnt);
+        hm::scan_count_kernel<<<nc, hm::kFrontThreads, 0, s.stream>>>(s.d_bcode, s.d_base_off, s.d_valid, s.d_chunk_read, s.d_chunk_pos, e->ctx_mask, s.d_chunk_cnt);
         ++launches;
     }
     hm::scan_offsets_kernel<<<1, 1024, 0, s.stream>>>(s.d_chunk_cnt, nc, s.d_pref, s.d_totals);
     hm::read_offsets_kernel<<<(s.n_reads + 256) / 256, 256, 0, s.stream>>>(s.d_pref, s.d_read_first_chunk, s.n_reads, s.d_call_off, s.d_n_fwd, s.d_read_pref);
     launches += 2;
     if (nc) {
-        hm::scan_write_kernel<<<nc, hm::kChunk, 0, s.stream>>>(s.d_bcode, s.d_base_off, s.d_valid, s.d_chunk_read, s.d_chunk_pos,
+        hm::scan_write_kernel<<<nc, hm::kFrontThreads, 0, s.stream>>>(s.d_bcode, s.d_base_off, s.d_valid, s.d_chunk_read, s.d_chunk_pos,
                                                                s.d_read_first_chunk, s.d_pref, nc, e->ctx_mask, s.d_qoff, s.d_call_ctx,
                                                                s.d_site_read, s.d_site_pos, s.d_site_out);
         ++launches;
@@ -738,15 +739,15 @@ int hm_microbench(hm_engine* e, int slot, const char* name, uint32_t n_sites, in
         if (it == 0) HM_CUDA(e, "microbench", cudaEventRecord(a, st));
         if (k == "decode") {
             if (s.n_chunks)
-                hm::decode_kernel<<<s.n_chunks, 256, 0, st>>>(s.d_seq4, s.d_fi, s.d_fp, s.d_ri, s.d_rp, s.d_base_off, s.d_seq_off, s.d_flag,
+                hm::decode_kernel<<<s.n_chunks, hm::kFrontThreads, 0, st>>>(s.d_seq4, s.d_fi, s.d_fp, s.d_ri, s.d_rp, s.d_base_off, s.d_seq_off, s.d_flag,
                                                               s.d_chunk_read, s.d_chunk_pos, s.d_bcode, s.d_kinf);
             bytes = 12.0 * s.n_bases;  // 4 code planes in, 4 x u16 frames out
         } else if (k == "scan") {
             hm_timing keep = s.timing;
-            hm::scan_count_kernel<<<std::max(s.n_chunks, 1u), hm::kChunk, 0, st>>>(s.d_bcode, s.d_base_off, s.d_valid, s.d_chunk_read, s.d_chunk_pos, e->ctx_mask, s.d_chunk_cnt);
+            hm::scan_count_kernel<<<std::max(s.n_chunks, 1u), hm::kFrontThreads, 0, st>>>(s.d_bcode, s.d_base_off, s.d_valid, s.d_chunk_read, s.d_chunk_pos, e->ctx_mask, s.d_chunk_cnt);
             hm::scan_offsets_kernel<<<1, 1024, 0, st>>>(s.d_chunk_cnt, s.n_chunks, s.d_pref, s.d_totals);
             hm::read_offsets_kernel<<<(s.n_reads + 256) / 256, 256, 0, st>>>(s.d_pref, s.d_read_first_chunk, s.n_reads, s.d_call_off, s.d_n_fwd, s.d_read_pref);
-            hm::scan_write_kernel<<<std::max(s.n_chunks, 1u), hm::kChunk, 0, st>>>(s.d_bcode, s.d_base_off, s.d_valid, s.d_chunk_read, s.d_chunk_pos,
+            hm::scan_write_kernel<<<std::max(s.n_chunks, 1u), hm::kFrontThreads, 0, st>>>(s.d_bcode, s.d_base_off, s.d_valid, s.d_chunk_read, s.d_chunk_pos,
                                                                                   s.d_read_first_chunk, s.d_pref, s.n_chunks, e->ctx_mask, s.d_qoff,
                                                                                   s.d_call_ctx, s.d_site_read, s.d_site_pos, s.d_site_out);
             s.timing = keep;

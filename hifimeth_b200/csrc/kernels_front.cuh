@@ -13,7 +13,8 @@
 
 namespace hm {
 
-constexpr int kChunk = 1024;          // positions per scan chunk; a chunk never straddles two reads
+constexpr int kChunk = 4096;          // positions per chunk (one block); a chunk never straddles two reads
+constexpr int kFrontThreads = 256;    // 16 positions per thread
 constexpr int kKmer = 401;
 constexpr int kHalf = 200;
 constexpr int kFpb = 8;
@@ -36,37 +37,63 @@ __device__ __forceinline__ uint32_t nib_to_code(uint32_t nib)
     return nib == 1 ? 0u : nib == 2 ? 1u : nib == 4 ? 2u : nib == 8 ? 3u : kCodeN;
 }
 
-// One block per chunk (kChunk forward positions of one read), 256 threads x 4 positions.
+// Copies n bytes starting at src (any alignment) into dst + (src & 15) with 16-byte global loads; returns the pointer to the
+// first copied byte in dst.  May read up to 15 bytes before src and after src + n (inside the same allocation: every input
+// array is allocated with 64 bytes of slack and starts 256-byte aligned).
+__device__ __forceinline__ const uint8_t* stage_bytes(uint8_t* dst, const uint8_t* src, uint32_t n)
+{
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+    const uint4* s4 = reinterpret_cast<const uint4*>(src - mis);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    const uint32_t nv = (mis + n + 15u) >> 4;
+    for (uint32_t i = threadIdx.x; i < nv; i += blockDim.x) d4[i] = __ldg(s4 + i);
+    return dst + mis;
+}
+
+// One block per chunk (kChunk forward positions of one read), 256 threads.  Inputs are staged in shared memory with
+// 16-byte loads (the four kinetics planes are byte arrays at arbitrary alignment, two of them read backwards); outputs are
+// written position-major so that a warp's stores are contiguous (8 B x 32 for kinf).
 // bcode[B+p]  = forward-strand code at forward position p (flag 0x10: reverse complement of the stored SEQ)
 // kinf[B+p]   = frames {fi[p], fp[p], ri[L-1-p], rp[L-1-p]}: the four kinetics of forward position p's base
 //               pair, so that a window is one contiguous run in either strand direction.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kFrontThreads)
 decode_kernel(const uint8_t* __restrict__ seq4, const uint8_t* __restrict__ fi, const uint8_t* __restrict__ fp,
               const uint8_t* __restrict__ ri, const uint8_t* __restrict__ rp, const uint32_t* __restrict__ base_off,
               const uint32_t* __restrict__ seq_off, const uint16_t* __restrict__ flag,
               const uint32_t* __restrict__ chunk_read, const uint32_t* __restrict__ chunk_pos,
               uint8_t* __restrict__ bcode, ushort4* __restrict__ kinf)
 {
+    __shared__ __align__(16) uint8_t s_buf[4][kChunk + 32];
+    __shared__ __align__(16) uint8_t s_seq[kChunk / 2 + 48];
     const uint32_t r = chunk_read[blockIdx.x];
     const uint32_t p0 = chunk_pos[blockIdx.x];
     const uint32_t B = base_off[r];
     const uint32_t L = base_off[r + 1] - B;
     const uint32_t S = seq_off[r];
     const bool rev = (flag[r] & 16) != 0;
-    #pragma unroll
-    for (int it = 0; it < kChunk / 256; ++it) {
-        uint32_t p = p0 + it * 256 + threadIdx.x;
-        if (p >= L) break;
-        uint32_t q = rev ? L - 1 - p : p;  // index into the stored SEQ
-        uint32_t nib = (seq4[S + (q >> 1)] >> ((~q & 1u) << 2)) & 0xfu;
+    const uint32_t n = min((uint32_t)kChunk, L - p0);
+    // forward planes: positions [p0, p0+n); reverse planes: indices L-1-p, i.e. [L-p0-n, L-p0)
+    const uint32_t r0 = L - p0 - n;
+    const uint8_t* s_fi = stage_bytes(s_buf[0], fi + B + p0, n);
+    const uint8_t* s_fp = stage_bytes(s_buf[1], fp + B + p0, n);
+    const uint8_t* s_ri = stage_bytes(s_buf[2], ri + B + r0, n);
+    const uint8_t* s_rp = stage_bytes(s_buf[3], rp + B + r0, n);
+    // stored-SEQ indices q: p (forward) or L-1-p (flag 0x10) -> nibble range [q0, q0+n)
+    const uint32_t q0 = rev ? r0 : p0;
+    const uint8_t* s_sq = stage_bytes(s_seq, seq4 + S + (q0 >> 1), ((q0 + n + 1) >> 1) - (q0 >> 1));
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += kFrontThreads) {
+        const uint32_t p = p0 + i;
+        const uint32_t q = rev ? L - 1 - p : p;  // index into the stored SEQ
+        const uint32_t nib = (s_sq[(q >> 1) - (q0 >> 1)] >> ((~q & 1u) << 2)) & 0xfu;
         uint32_t code = nib_to_code(nib);
         if (rev && code < 4) code = 3u - code;
         bcode[B + p] = (uint8_t)code;
         ushort4 k;
-        k.x = (unsigned short)codev1_frames(fi[B + p]);
-        k.y = (unsigned short)codev1_frames(fp[B + p]);
-        k.z = (unsigned short)codev1_frames(ri[B + L - 1 - p]);
-        k.w = (unsigned short)codev1_frames(rp[B + L - 1 - p]);
+        k.x = (unsigned short)codev1_frames(s_fi[i]);
+        k.y = (unsigned short)codev1_frames(s_fp[i]);
+        k.z = (unsigned short)codev1_frames(s_ri[n - 1 - i]);
+        k.w = (unsigned short)codev1_frames(s_rp[n - 1 - i]);
         kinf[B + p] = k;
     }
 }
@@ -98,50 +125,92 @@ decode_unpack_kernel(const uint8_t* __restrict__ bcode, const ushort4* __restric
     }
 }
 
-// Site class at forward position p of a read with codes c[0..L): 0..3, or -1 for none.
-// CpG: C,G.  CHG: C,[ACT],G.  CHH fwd: C,[ACT],[ACT].  CHH rev: [AGT],[AGT],G -> the G.
-// (eval_kmer_features.cpp:67-126; the three sets are disjoint.)
-__device__ __forceinline__ int site_class(const uint8_t* __restrict__ c, uint32_t p, uint32_t L, uint32_t ctx_mask)
+// Shared staging of one chunk's forward-strand codes with a 2-position halo on both sides (0xff outside the read), so that
+// every thread classifies 16 consecutive positions from registers.  s_code[2 + i] = code at chunk position i.
+__device__ __forceinline__ void stage_codes(uint8_t (&s_code)[kChunk + 48], const uint8_t* __restrict__ codes, uint32_t p0, uint32_t n,
+                                            uint32_t L)
 {
-    uint32_t b = c[p];
+    // positions [p0 - 2, p0 + n + 2) clipped to the read; shared index 2 + (p - p0)
+    for (uint32_t i = threadIdx.x; i < n + 4; i += blockDim.x) {
+        const int p = (int)p0 - 2 + (int)i;
+        s_code[i] = (p >= 0 && p < (int)L) ? codes[p] : (uint8_t)0xff;
+    }
+}
+
+// Site class from a thread-local window: w[2 + j] is the code at the thread's position j, w[0..1] / w[18..19] the halo.
+// CpG: C,G.  CHG: C,[ACT],G.  CHH fwd: C,[ACT],[ACT].  CHH rev: [AGT],[AGT],G -> the G.  0xff (outside the read) and 4 (N) are
+// "no base" (eval_kmer_features.cpp:67-126; the three sets are disjoint).
+__device__ __forceinline__ int class_at(const uint8_t* w, int j, uint32_t ctx_mask)
+{
+    const uint32_t b = w[2 + j];
     if (b == 1u) {
-        if (p + 1 >= L) return -1;
-        uint32_t n1 = c[p + 1];
+        const uint32_t n1 = w[3 + j];
         if (n1 == 2u) return (ctx_mask & 1u) ? 0 : -1;
-        if (n1 > 3u || p + 2 >= L) return -1;
-        uint32_t n2 = c[p + 2];
+        if (n1 > 3u) return -1;
+        const uint32_t n2 = w[4 + j];
         if (n2 == 2u) return (ctx_mask & 2u) ? 1 : -1;
         if (n2 > 3u) return -1;
         return (ctx_mask & 4u) ? 2 : -1;
     }
-    if (b == 2u) {
-        if (p < 2 || !(ctx_mask & 4u)) return -1;
-        uint32_t m1 = c[p - 1], m2 = c[p - 2];
+    if (b == 2u && (ctx_mask & 4u)) {
+        const uint32_t m1 = w[1 + j], m2 = w[j];
         if (m1 > 3u || m2 > 3u || m1 == 1u || m2 == 1u) return -1;
         return 3;
     }
     return -1;
 }
 
-// Pass 1: per-chunk class counts.  One block (kChunk threads) per chunk.
-__global__ void __launch_bounds__(kChunk)
+constexpr int kPosPerThread = kChunk / kFrontThreads;  // 16
+
+// Loads the thread's 16 positions + halo from the staged chunk into w[20] and returns the packed classes:
+// 4 bits per position (0..3, 0xf = none), position j in bits [4j, 4j+4).
+__device__ __forceinline__ uint64_t thread_classes(const uint8_t (&s_code)[kChunk + 48], uint32_t n, uint32_t ctx_mask, bool valid)
+{
+    uint64_t packed = ~0ull;
+    const uint32_t t0 = threadIdx.x * kPosPerThread;
+    if (!valid || t0 >= n) return packed;
+    uint8_t w[kPosPerThread + 4];
+    #pragma unroll
+    for (int i = 0; i < kPosPerThread + 4; ++i) w[i] = s_code[t0 + i];
+    #pragma unroll
+    for (int j = 0; j < kPosPerThread; ++j) {
+        if (t0 + j >= n) break;
+        const int c = class_at(w, j, ctx_mask);
+        if (c >= 0) packed = (packed & ~(0xfull << (4 * j))) | ((uint64_t)c << (4 * j));
+    }
+    return packed;
+}
+
+// Pass 1: per-chunk class counts.  One block (256 threads x 16 positions) per chunk.
+__global__ void __launch_bounds__(kFrontThreads)
 scan_count_kernel(const uint8_t* __restrict__ bcode, const uint32_t* __restrict__ base_off,
                   const uint8_t* __restrict__ valid, const uint32_t* __restrict__ chunk_read,
                   const uint32_t* __restrict__ chunk_pos, uint32_t ctx_mask, ClassCount* __restrict__ chunk_cnt)
 {
+    __shared__ __align__(16) uint8_t s_code[kChunk + 48];
     __shared__ uint32_t s_cnt[4];
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
     const uint32_t r = chunk_read[blockIdx.x];
     const uint32_t B = base_off[r];
     const uint32_t L = base_off[r + 1] - B;
-    const uint32_t p = chunk_pos[blockIdx.x] + threadIdx.x;
-    int cls = -1;
-    if (valid[r] && p < L) cls = site_class(bcode + B, p, L, ctx_mask);
+    const uint32_t p0 = chunk_pos[blockIdx.x];
+    const uint32_t n = min((uint32_t)kChunk, L - p0);
+    stage_codes(s_code, bcode + B, p0, n, L);
+    __syncthreads();
+    const uint64_t cls = thread_classes(s_code, n, ctx_mask, valid[r] != 0);
+    uint32_t c[4] = {0, 0, 0, 0};
+    #pragma unroll
+    for (int j = 0; j < kPosPerThread; ++j) {
+        const uint32_t v = (uint32_t)(cls >> (4 * j)) & 0xfu;
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) c[k] += (v == (uint32_t)k);
+    }
     #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        uint32_t m = __ballot_sync(0xffffffffu, cls == k);
-        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_cnt[k], __popc(m));
+        uint32_t v = c[k];
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt[k], v);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -213,7 +282,7 @@ __global__ void read_offsets_kernel(const ClassCount* __restrict__ pref, const u
 // Pass 3: write.  Output order per read: forward-strand calls (classes 0,1,2) ascending, then reverse
 // (class 3) ascending -- the order the worker thread hands to build_one_mod_bam (mod_main.cpp:217-251).
 // Per-class work lists (site_read / site_pos / site_out) are laid out class after class.
-__global__ void __launch_bounds__(kChunk)
+__global__ void __launch_bounds__(kFrontThreads)
 scan_write_kernel(const uint8_t* __restrict__ bcode, const uint32_t* __restrict__ base_off,
                   const uint8_t* __restrict__ valid, const uint32_t* __restrict__ chunk_read,
                   const uint32_t* __restrict__ chunk_pos, const uint32_t* __restrict__ read_first_chunk,
@@ -221,63 +290,71 @@ scan_write_kernel(const uint8_t* __restrict__ bcode, const uint32_t* __restrict_
                   int32_t* __restrict__ qoff, uint8_t* __restrict__ call_ctx, uint32_t* __restrict__ site_read,
                   uint32_t* __restrict__ site_pos, uint32_t* __restrict__ site_out)
 {
-    __shared__ uint32_t s_warp[32][4];
+    __shared__ __align__(16) uint8_t s_code[kChunk + 48];
+    __shared__ uint32_t s_warp[kFrontThreads / 32][4];
     const uint32_t r = chunk_read[blockIdx.x];
     const uint32_t B = base_off[r];
     const uint32_t L = base_off[r + 1] - B;
-    const uint32_t p = chunk_pos[blockIdx.x] + threadIdx.x;
-    int cls = -1;
-    if (valid[r] && p < L) cls = site_class(bcode + B, p, L, ctx_mask);
+    const uint32_t p0 = chunk_pos[blockIdx.x];
+    const uint32_t n = min((uint32_t)kChunk, L - p0);
+    stage_codes(s_code, bcode + B, p0, n, L);
+    __syncthreads();
+    const uint64_t cls = thread_classes(s_code, n, ctx_mask, valid[r] != 0);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t rank_in_warp[4];
+    // exclusive rank of this thread's first site of each class inside the chunk: thread counts -> warp scan -> block scan
+    uint32_t rk[4];
     #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        uint32_t m = __ballot_sync(0xffffffffu, cls == k);
-        rank_in_warp[k] = __popc(m & ((1u << lane) - 1u));
-        if (lane == 0) s_warp[warp][k] = __popc(m);
+        uint32_t c = 0;
+        #pragma unroll
+        for (int j = 0; j < kPosPerThread; ++j) c += (((uint32_t)(cls >> (4 * j)) & 0xfu) == (uint32_t)k);
+        uint32_t incl = c;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp][k] = incl;
+        rk[k] = incl - c;
     }
     __syncthreads();
-    if (warp == 0) {
-        #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            uint32_t v = s_warp[lane][k];
-            uint32_t incl = v;
-            #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
-                if ((int)lane >= off) incl += t;
-            }
-            s_warp[lane][k] = incl - v;  // exclusive
+    if (threadIdx.x < 4) {
+        uint32_t run = 0;
+        for (int w = 0; w < kFrontThreads / 32; ++w) {
+            const uint32_t v = s_warp[w][threadIdx.x];
+            s_warp[w][threadIdx.x] = run;
+            run += v;
         }
     }
     __syncthreads();
-    if (cls < 0) return;
-    uint32_t rk[4];
+    if (cls == ~0ull) return;
     #pragma unroll
-    for (int k = 0; k < 4; ++k) rk[k] = s_warp[warp][k] + rank_in_warp[k];
+    for (int k = 0; k < 4; ++k) rk[k] += s_warp[warp][k];
 
     const ClassCount pc = pref[blockIdx.x];
-    const ClassCount p0 = pref[read_first_chunk[r]];
-    const ClassCount p1 = pref[read_first_chunk[r + 1]];
+    const ClassCount q0 = pref[read_first_chunk[r]];
+    const ClassCount q1 = pref[read_first_chunk[r + 1]];
     const ClassCount tot = pref[n_chunks];
-    const uint32_t call_base = p0.c[0] + p0.c[1] + p0.c[2] + p0.c[3];
-    uint32_t out;
-    if (cls < 3) {
-        uint32_t fwd_before = (pc.c[0] + pc.c[1] + pc.c[2]) - (p0.c[0] + p0.c[1] + p0.c[2]);
-        out = call_base + fwd_before + rk[0] + rk[1] + rk[2];
-    } else {
-        uint32_t nfwd = (p1.c[0] + p1.c[1] + p1.c[2]) - (p0.c[0] + p0.c[1] + p0.c[2]);
-        out = call_base + nfwd + (pc.c[3] - p0.c[3]) + rk[3];
-    }
-    qoff[out] = (int32_t)p;
-    call_ctx[out] = (uint8_t)(cls == 3 ? 2 : cls);
-    uint32_t region = 0;
+    const uint32_t call_base = q0.c[0] + q0.c[1] + q0.c[2] + q0.c[3];
+    const uint32_t fwd_before = (pc.c[0] + pc.c[1] + pc.c[2]) - (q0.c[0] + q0.c[1] + q0.c[2]);
+    const uint32_t nfwd = (q1.c[0] + q1.c[1] + q1.c[2]) - (q0.c[0] + q0.c[1] + q0.c[2]);
+    const uint32_t region[4] = {0, tot.c[0], tot.c[0] + tot.c[1], tot.c[0] + tot.c[1] + tot.c[2]};
     #pragma unroll
-    for (int k = 0; k < 3; ++k) if (k < cls) region += tot.c[k];
-    const uint32_t slot = region + pc.c[cls] + rk[cls];
-    site_read[slot] = r;
-    site_pos[slot] = p | (cls == 3 ? 0x80000000u : 0u);
-    site_out[slot] = out;
+    for (int j = 0; j < kPosPerThread; ++j) {
+        const uint32_t c = (uint32_t)(cls >> (4 * j)) & 0xfu;
+        if (c > 3u) continue;
+        const uint32_t p = p0 + threadIdx.x * kPosPerThread + j;
+        uint32_t out;
+        if (c < 3u) out = call_base + fwd_before + rk[0] + rk[1] + rk[2];
+        else out = call_base + nfwd + (pc.c[3] - q0.c[3]) + rk[3];
+        qoff[out] = (int32_t)p;
+        call_ctx[out] = (uint8_t)(c == 3u ? 2u : c);
+        const uint32_t slot = region[c] + pc.c[c] + rk[c];
+        site_read[slot] = r;
+        site_pos[slot] = p | (c == 3u ? 0x80000000u : 0u);
+        site_out[slot] = out;
+        ++rk[c];
+    }
 }
 
 // A4: one block per site, 128 threads; thread w writes window row w (8 floats, 32 B).
