@@ -10,7 +10,8 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libhm_engine.so"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["engine.cu", "cnn_tensor.cu", "onnx_weights.cpp", "host_record.cpp"]
+SOURCES = ["engine.cu", "cnn_tensor.cu", "onnx_weights.cpp", "host_record.cpp", "bgzf_bam.cpp", "call_main.cpp"]
+EXE = PKG / "bin" / "hifimeth-b200"
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
@@ -42,11 +43,18 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     # Link with the host compiler and the static CUDA runtime: nvcc's own link step would embed a default
     # sm_52 device-link stub, and a shared libcudart could collide with the one torch bundles.
     cuda_lib = str(Path(NVCC).resolve().parent.parent / "lib64")
-    r = subprocess.run(["g++", "-shared", "-o", str(LIB), *objs, "-L" + cuda_lib, "-lcudart_static", "-ldl", "-lrt", "-lpthread"],
+    r = subprocess.run(["g++", "-shared", "-o", str(LIB), *objs, "-L" + cuda_lib, "-lcudart_static", "-ldl", "-lrt", "-lpthread", "-lz"],
                        capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
+    # the CLI: main.cpp against the shared library (rpath = the package directory)
+    EXE.parent.mkdir(exist_ok=True)
+    r = subprocess.run(["g++", "-O2", "-std=c++17", "-o", str(EXE), str(CSRC / "main.cpp"), "-L" + str(PKG), "-lhm_engine",
+                        "-Wl,-rpath,$ORIGIN/.."], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link of the CLI failed")
     (build_dir / "ptxas.log").write_text("\n".join(log))
     if verbose:
         print("\n".join(log))

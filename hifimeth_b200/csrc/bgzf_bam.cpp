@@ -1,0 +1,282 @@
+// bgzf_bam.cpp -- see bgzf_bam.h.  Block-parallel inflate / deflate with zlib; nothing here touches the GPU.
+#include <functional>
+
+#include "bgzf_bam.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <thread>
+
+#include <zlib.h>
+
+namespace hm {
+
+namespace {
+constexpr size_t kBlockPayload = 0xff00;      // uncompressed bytes per BGZF block (htslib's BGZF_BLOCK_SIZE)
+constexpr size_t kReadSlab = 32u << 20;       // compressed bytes read per refill
+constexpr size_t kWriteBatch = 1024;          // blocks deflated per parallel batch (~64 MB)
+
+uint16_t rd16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+uint32_t rd32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+void wr16(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
+void wr32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
+
+// Total size of the BGZF block starting at p (n bytes available), or 0 if the header is incomplete / not BGZF.
+size_t bgzf_block_size(const uint8_t* p, size_t n, bool& bad)
+{
+    bad = false;
+    if (n < 18) return 0;
+    if (p[0] != 31 || p[1] != 139 || p[2] != 8 || !(p[3] & 4)) { bad = true; return 0; }
+    const size_t xlen = rd16(p + 10);
+    if (n < 12 + xlen) return 0;
+    size_t off = 12;
+    while (off + 4 <= 12 + xlen) {
+        const uint16_t slen = rd16(p + off + 2);
+        if (p[off] == 'B' && p[off + 1] == 'C' && slen == 2) return (size_t)rd16(p + off + 4) + 1;
+        off += 4 + slen;
+    }
+    bad = true;
+    return 0;
+}
+}  // namespace
+
+void parallel_for(size_t n, int threads, const std::function<void(size_t)>& fn)
+{
+    if (n == 0) return;
+    const size_t t = std::min<size_t>(std::max(threads, 1), n);
+    if (t == 1) {
+        for (size_t i = 0; i < n; ++i) fn(i);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> pool;
+    for (size_t k = 0; k < t; ++k)
+        pool.emplace_back([&] {
+            for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
+        });
+    for (auto& th : pool) th.join();
+}
+
+// ---- BgzfReader ----------------------------------------------------------------------------------------------------------
+BgzfReader::~BgzfReader() { close(); }
+void BgzfReader::close()
+{
+    if (f_) fclose(f_);
+    f_ = nullptr;
+}
+
+bool BgzfReader::open(const char* path, int threads, std::string& err)
+{
+    close();
+    f_ = fopen(path, "rb");
+    if (!f_) { err = std::string("cannot open ") + path; return false; }
+    threads_ = std::max(threads, 1);
+    raw_.clear();
+    eof_ = false;
+    return true;
+}
+
+bool BgzfReader::read_more(std::vector<uint8_t>& out, std::string& err)
+{
+    for (;;) {
+        // complete blocks currently buffered
+        struct Blk { size_t off, size, isize, dst; };
+        std::vector<Blk> blks;
+        size_t off = 0, total = 0;
+        while (off < raw_.size()) {
+            bool bad;
+            const size_t bs = bgzf_block_size(raw_.data() + off, raw_.size() - off, bad);
+            if (bad) { err = "not a BGZF block (is the input a BAM file?)"; return false; }
+            if (!bs || off + bs > raw_.size()) break;
+            if (bs < 26) { err = "corrupt BGZF block"; return false; }
+            const size_t isize = rd32(raw_.data() + off + bs - 4);
+            blks.push_back({off, bs, isize, total});
+            total += isize;
+            off += bs;
+        }
+        if (!blks.empty()) {
+            const size_t base = out.size();
+            out.resize(base + total);
+            std::atomic<bool> ok{true};
+            parallel_for(blks.size(), threads_, [&](size_t i) {
+                const Blk& b = blks[i];
+                if (!b.isize) return;
+                const uint8_t* p = raw_.data() + b.off;
+                const size_t xlen = rd16(p + 10);
+                z_stream zs{};
+                if (inflateInit2(&zs, -15) != Z_OK) { ok = false; return; }
+                zs.next_in = const_cast<Bytef*>(p + 12 + xlen);
+                zs.avail_in = (uInt)(b.size - 12 - xlen - 8);
+                zs.next_out = out.data() + base + b.dst;
+                zs.avail_out = (uInt)b.isize;
+                const int rc = inflate(&zs, Z_FINISH);
+                inflateEnd(&zs);
+                if (rc != Z_STREAM_END || zs.total_out != b.isize ||
+                    crc32(crc32(0L, Z_NULL, 0), out.data() + base + b.dst, (uInt)b.isize) != rd32(p + b.size - 8))
+                    ok = false;
+            });
+            if (!ok) { err = "BGZF block failed to inflate or its CRC does not match"; return false; }
+            raw_.erase(raw_.begin(), raw_.begin() + off);
+            if (total) return true;
+            continue;  // only empty blocks (EOF markers): look for more
+        }
+        if (eof_) {
+            if (!raw_.empty()) { err = "truncated BGZF block at end of file"; return false; }
+            return false;
+        }
+        const size_t have = raw_.size();
+        raw_.resize(have + kReadSlab);
+        const size_t got = fread(raw_.data() + have, 1, kReadSlab, f_);
+        raw_.resize(have + got);
+        if (got < kReadSlab) eof_ = true;
+    }
+}
+
+// ---- BgzfWriter ----------------------------------------------------------------------------------------------------------
+BgzfWriter::~BgzfWriter()
+{
+    if (f_) fclose(f_);
+}
+
+bool BgzfWriter::open(const char* path, int threads, int level, std::string& err)
+{
+    f_ = fopen(path, "wb");
+    if (!f_) { err = std::string("cannot create ") + path; return false; }
+    threads_ = std::max(threads, 1);
+    level_ = level;
+    pending_.clear();
+    return true;
+}
+
+bool BgzfWriter::write(const void* data, size_t n, std::string& err)
+{
+    const uint8_t* p = static_cast<const uint8_t*>(data);
+    pending_.insert(pending_.end(), p, p + n);
+    if (pending_.size() >= kWriteBatch * kBlockPayload) return flush(false, err);
+    return true;
+}
+
+bool BgzfWriter::flush(bool all, std::string& err)
+{
+    size_t nblk = pending_.size() / kBlockPayload;
+    if (all && pending_.size() % kBlockPayload) ++nblk;
+    if (!nblk) return true;
+    std::vector<std::vector<uint8_t>> comp(nblk);
+    std::atomic<bool> ok{true};
+    parallel_for(nblk, threads_, [&](size_t i) {
+        const size_t off = i * kBlockPayload;
+        const size_t len = std::min(kBlockPayload, pending_.size() - off);
+        std::vector<uint8_t>& c = comp[i];
+        c.resize(18 + compressBound((uLong)len) + 8);
+        z_stream zs{};
+        if (deflateInit2(&zs, level_, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { ok = false; return; }
+        zs.next_in = const_cast<Bytef*>(pending_.data() + off);
+        zs.avail_in = (uInt)len;
+        zs.next_out = c.data() + 18;
+        zs.avail_out = (uInt)(c.size() - 18 - 8);
+        const int rc = deflate(&zs, Z_FINISH);
+        const size_t clen = zs.total_out;
+        deflateEnd(&zs);
+        if (rc != Z_STREAM_END || 18 + clen + 8 > 65536) { ok = false; return; }
+        static const uint8_t hdr[12] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0};
+        memcpy(c.data(), hdr, 12);
+        c[12] = 'B'; c[13] = 'C';
+        wr16(c.data() + 14, 2);
+        wr16(c.data() + 16, (uint32_t)(18 + clen + 8 - 1));
+        wr32(c.data() + 18 + clen, (uint32_t)crc32(crc32(0L, Z_NULL, 0), pending_.data() + off, (uInt)len));
+        wr32(c.data() + 18 + clen + 4, (uint32_t)len);
+        c.resize(18 + clen + 8);
+    });
+    if (!ok) { err = "deflate failed"; return false; }
+    for (auto& c : comp)
+        if (fwrite(c.data(), 1, c.size(), f_) != c.size()) { err = "write error"; return false; }
+    const size_t used = std::min(pending_.size(), nblk * kBlockPayload);
+    pending_.erase(pending_.begin(), pending_.begin() + used);
+    return true;
+}
+
+bool BgzfWriter::close(std::string& err)
+{
+    if (!f_) return true;
+    bool ok = flush(true, err);
+    static const uint8_t eof_marker[28] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (ok && fwrite(eof_marker, 1, 28, f_) != 28) { err = "write error"; ok = false; }
+    if (fclose(f_) != 0 && ok) { err = "close error"; ok = false; }
+    f_ = nullptr;
+    return ok;
+}
+
+// ---- BamReader / BamWriter -------------------------------------------------------------------------------------------------
+bool BamReader::need(size_t n, std::string& err)
+{
+    while (buf_.size() - pos_ < n) {
+        if (pos_ > (64u << 20)) {  // drop consumed bytes now and then
+            buf_.erase(buf_.begin(), buf_.begin() + pos_);
+            pos_ = 0;
+        }
+        if (!z_.read_more(buf_, err)) return false;
+    }
+    return true;
+}
+
+bool BamReader::open(const char* path, int threads, BamHeader& hdr, std::string& err)
+{
+    if (!z_.open(path, threads, err)) return false;
+    buf_.clear();
+    pos_ = 0;
+    if (!need(12, err)) { if (err.empty()) err = "empty BAM file"; return false; }
+    if (memcmp(buf_.data(), "BAM\1", 4) != 0) { err = "bad BAM magic"; return false; }
+    const uint32_t l_text = rd32(buf_.data() + 4);
+    if (!need(8 + (size_t)l_text + 4, err)) { if (err.empty()) err = "truncated BAM header"; return false; }
+    hdr.text.assign(reinterpret_cast<const char*>(buf_.data() + 8), l_text);
+    while (!hdr.text.empty() && hdr.text.back() == '\0') hdr.text.pop_back();
+    size_t p = 8 + (size_t)l_text;
+    const uint32_t n_ref = rd32(buf_.data() + p);
+    size_t q = p + 4;
+    for (uint32_t i = 0; i < n_ref; ++i) {
+        if (!need(q + 4, err)) { if (err.empty()) err = "truncated BAM references"; return false; }
+        const uint32_t l_name = rd32(buf_.data() + q);
+        if (!need(q + 4 + (size_t)l_name + 4, err)) { if (err.empty()) err = "truncated BAM references"; return false; }
+        q += 4 + (size_t)l_name + 4;
+    }
+    hdr.refs.assign(buf_.begin() + p, buf_.begin() + q);
+    pos_ = q;
+    return true;
+}
+
+bool BamReader::next(const uint8_t*& body, size_t& len, std::string& err)
+{
+    err.clear();
+    if (!need(4, err)) return false;
+    const uint32_t bs = rd32(buf_.data() + pos_);
+    if (bs < 32) { err = "corrupt BAM record"; return false; }
+    if (!need(4 + (size_t)bs, err)) { if (err.empty()) err = "truncated BAM record"; return false; }
+    body = buf_.data() + pos_ + 4;
+    len = bs;
+    pos_ += 4 + (size_t)bs;
+    return true;
+}
+
+bool BamWriter::open(const char* path, int threads, int level, const BamHeader& hdr, std::string& err)
+{
+    if (!z_.open(path, threads, level, err)) return false;
+    std::vector<uint8_t> h(8);
+    memcpy(h.data(), "BAM\1", 4);
+    wr32(h.data() + 4, (uint32_t)hdr.text.size());
+    h.insert(h.end(), hdr.text.begin(), hdr.text.end());
+    h.insert(h.end(), hdr.refs.begin(), hdr.refs.end());
+    if (hdr.refs.empty()) { uint8_t z[4] = {0, 0, 0, 0}; h.insert(h.end(), z, z + 4); }
+    return z_.write(h.data(), h.size(), err);
+}
+
+bool BamWriter::write_record(const uint8_t* body, size_t len, std::string& err)
+{
+    uint8_t bs[4];
+    wr32(bs, (uint32_t)len);
+    return z_.write(bs, 4, err) && z_.write(body, len, err);
+}
+
+bool BamWriter::close(std::string& err) { return z_.close(err); }
+
+}  // namespace hm

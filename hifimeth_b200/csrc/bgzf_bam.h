@@ -1,0 +1,78 @@
+// bgzf_bam.h -- minimal block-parallel BGZF + BAM record reader / writer over zlib.
+//
+// Replaces the reference's use of htslib for the `call` path: sam_open / hts_set_threads(8) / sam_hdr_read / sam_read1
+// (src/corelib/sam_batch.hpp:12-54) and sam_open("wb") / sam_hdr_write / sam_write1 (src/app/hifimeth/mod_main.cpp:316-321,
+// 353-362).  Written from the SAM/BAM specification (SAMv1 section 4: BGZF blocks are gzip members with a BC extra field
+// holding BSIZE; a BAM file is magic, l_text, text, n_ref, references, then block_size-prefixed records).  Only what `call`
+// needs: sequential reading of records, header pass-through with one @PG line appended, sequential writing.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <functional>
+#include <string>
+#include <vector>
+
+namespace hm {
+
+// Runs fn(i) for i in [0, n) on up to `threads` threads (inline when n or threads is small).
+void parallel_for(size_t n, int threads, const std::function<void(size_t)>& fn);
+
+class BgzfReader {
+public:
+    ~BgzfReader();
+    bool open(const char* path, int threads, std::string& err);
+    // Appends the inflated payload of the next group of blocks to `out`; false at end of file or on error (err set).
+    bool read_more(std::vector<uint8_t>& out, std::string& err);
+    void close();
+
+private:
+    FILE* f_ = nullptr;
+    int threads_ = 1;
+    std::vector<uint8_t> raw_;  // compressed bytes not yet consumed
+    bool eof_ = false;
+};
+
+class BgzfWriter {
+public:
+    ~BgzfWriter();
+    bool open(const char* path, int threads, int level, std::string& err);
+    bool write(const void* data, size_t n, std::string& err);
+    bool close(std::string& err);  // flushes, writes the BGZF end-of-file marker
+
+private:
+    bool flush(bool all, std::string& err);
+    FILE* f_ = nullptr;
+    int threads_ = 1, level_ = 6;
+    std::vector<uint8_t> pending_;
+};
+
+struct BamHeader {
+    std::string text;              // SAM header text (without the NUL padding some writers add)
+    std::vector<uint8_t> refs;     // n_ref + reference records, verbatim
+};
+
+class BamReader {
+public:
+    bool open(const char* path, int threads, BamHeader& hdr, std::string& err);
+    // Next alignment record body (SAMv1 4.2 without block_size).  The pointer stays valid until the next call that returns
+    // a record from a different buffer refill; copy it if it must outlive the batch.  false at end of file (err empty) or error.
+    bool next(const uint8_t*& body, size_t& len, std::string& err);
+
+private:
+    bool need(size_t n, std::string& err);
+    BgzfReader z_;
+    std::vector<uint8_t> buf_;
+    size_t pos_ = 0;
+};
+
+class BamWriter {
+public:
+    bool open(const char* path, int threads, int level, const BamHeader& hdr, std::string& err);
+    bool write_record(const uint8_t* body, size_t len, std::string& err);
+    bool close(std::string& err);
+
+private:
+    BgzfWriter z_;
+};
+
+}  // namespace hm

@@ -132,3 +132,50 @@ def codev1_decode_table() -> np.ndarray:
     """PacBio CodecV1 8-bit code -> frames (the 256-entry table of src/corelib/bam_info.cpp:562-570)."""
     c = np.arange(256, dtype=np.int32)
     return np.where(c < 64, c, np.where(c < 128, (c - 64) * 2 + 64, np.where(c < 192, (c - 128) * 4 + 192, (c - 192) * 8 + 448))).astype(np.int32)
+
+
+# ---- BAM files (BGZF per SAMv1 section 4) for the `call` driver tests and benchmarks -------------------------------------
+
+def write_bam(path, bodies, header_text: str = "@HD\tVN:1.6\tSO:unknown\n@RG\tID:synth\tPL:PACBIO\n", level: int = 1,
+              block: int = 0xff00) -> int:
+    """Writes unaligned records (bodies without block_size) as a BGZF-compressed BAM file.  Returns the file size."""
+    import zlib
+
+    text = header_text.encode()
+    stream = bytearray(b"BAM\1" + struct.pack("<i", len(text)) + text + struct.pack("<i", 0))
+    for b in bodies:
+        stream += struct.pack("<i", len(b)) + b
+    out = bytearray()
+    for off in range(0, len(stream), block):
+        chunk = bytes(stream[off:off + block])
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        comp = co.compress(chunk) + co.flush()
+        out += struct.pack("<BBBBIBBH", 31, 139, 8, 4, 0, 0, 255, 6) + b"BC" + struct.pack("<HH", 2, len(comp) + 25)
+        out += comp + struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk))
+    out += bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0])
+    with open(path, "wb") as f:
+        f.write(out)
+    return len(out)
+
+
+def read_bam(path):
+    """Returns (header_text, reference_block_bytes, [record bodies]) of a BAM file (any gzip-member layout)."""
+    import gzip
+
+    data = gzip.decompress(open(path, "rb").read())
+    assert data[:4] == b"BAM\1", "bad BAM magic"
+    l_text = struct.unpack_from("<i", data, 4)[0]
+    text = data[8:8 + l_text].rstrip(b"\0").decode()
+    p = 8 + l_text
+    n_ref = struct.unpack_from("<i", data, p)[0]
+    q = p + 4
+    for _ in range(n_ref):
+        l_name = struct.unpack_from("<i", data, q)[0]
+        q += 4 + l_name + 4
+    refs = data[p:q]
+    bodies = []
+    while q < len(data):
+        n = struct.unpack_from("<i", data, q)[0]
+        bodies.append(data[q + 4:q + 4 + n])
+        q += 4 + n
+    return text, refs, bodies

@@ -159,6 +159,16 @@ int hm_build_mod_record_mm(const uint8_t* body, size_t len, int keep_kinetics, c
                            const uint8_t* mm_rev, uint32_t mm_rev_len, const uint8_t* ml, uint32_t n_fwd, uint32_t n_rev,
                            uint8_t* out, size_t* out_len);
 
+/* ---- the `call` driver and its BAM codec ------------------------------------------------------- */
+
+/* `hifimeth call [-m dir] [-l 1000] [-s 32] [-b 10000] [-k] [-c cpg,chg,chh] [-t N] in.bam out.bam` on this engine
+ * (src/app/hifimeth/mod_main.cpp:303-412, options src/app/hifimeth/mod_options.cpp:61-181).  argv[0] = program name,
+ * argv[1] = "call".  Returns EXIT_SUCCESS / EXIT_FAILURE like the reference's main(). */
+int hm_call_main(int argc, char** argv);
+/* Reads every record of a BAM file and writes it unchanged (block-parallel BGZF inflate / deflate); returns the number of
+ * records or a negative hm_status.  Test hook for the codec. */
+int hm_bam_copy(const char* in_path, const char* out_path, int threads, int level);
+
 /* ---- validation hooks (parity tests; need cfg.keep_debug = 1, call after hm_batch_collect) ------------ */
 
 /* Decoded kinetics as frames, u16, each [n_bases]: fi, fp in forward coordinates, ri, rp in reverse-strand

@@ -239,3 +239,55 @@ def test_mm_text_built_on_device(eng, models):
     short, _ = synth.make_reads(2, 400, seed=3)
     g3 = eng.call(short, slot=1, flags=hme.HM_SUBMIT_MM_TEXT)
     assert g3.n_calls == 0 and int(g3.mm_off[-1]) == 0
+
+
+def test_call_cli_end_to_end(lib_built, models, tmp_path):
+    """`hifimeth-b200 call in.bam out.bam`: input order kept, every record written, tags stripped, MM/ML/MN equal to what the
+    oracle's build_one_mod_bam restatement makes of the engine's calls, ML within +-1 of the CPU oracle's, @PG line added."""
+    import subprocess
+
+    reads = golden_reads()
+    _, more = synth.make_reads(9, (900, 2600), seed=404, flag_rev_every=4)
+    all_reads = reads + more
+    bodies = golden_bodies(reads) + [synth.record_body(r) for r in more]
+    src, dst = tmp_path / "in.bam", tmp_path / "mod.bam"
+    synth.write_bam(src, bodies)
+    exe = hme.PKG / "bin" / "hifimeth-b200"
+    # small batches (-b 4, 8 kb of bases) force several batches, a batch cut by bases, and the two-slot pipeline
+    r = subprocess.run([str(exe), "call", "-b", "4", "--max-bases", "8192", "-t", "3", str(src), str(dst)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    text, _, got = synth.read_bam(dst)
+    assert "@PG\tID:hifimeth\tPN:hifimeth\tVN:1.1.0\tCL:" in text and text.startswith("@HD")
+    assert len(got) == len(bodies)
+    # expected records: engine calls through the Python mirror + the oracle's record builder
+    batch = hme.pack_records_host(bodies, min_read_len=1000)
+    eng = hme.Engine(max_reads=64, max_bases=1 << 20)
+    try:
+        calls = eng.call(batch)
+    finally:
+        eng.close()
+    O = hmoracle.oracle()
+    want = O.batch_call(batch, models)
+    n_called = 0
+    for i, body in enumerate(bodies):
+        fq, fml, rq, rml = calls.read_calls(i)
+        assert got[i] == O.build_mod_record(body, False, fq, fml, rq, rml), i
+        if len(fq) + len(rq):
+            n_called += 1
+            ml_cli = np.frombuffer(got[i][got[i].index(b"MLBC") + 8:][:len(fq) + len(rq)], np.uint8)
+            assert np.abs(ml_cli.astype(int) - want[i]["ml"].astype(int)).max() <= ML_TOL
+            assert b"fiBC" not in got[i] and b"MMZC+m" in got[i]
+    assert n_called >= 10
+    # -k keeps the kinetics, -c cpg restricts the contexts
+    r = subprocess.run([str(exe), "call", "-k", "-c", "cpg", str(src), str(dst)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    _, _, got_k = synth.read_bam(dst)
+    assert len(got_k) == len(bodies) and any(b"fiBC" in g for g in got_k)
+    e1 = hme.Engine(ctx_mask=1, max_reads=64, max_bases=1 << 20)
+    try:
+        c1 = e1.call(batch)
+    finally:
+        e1.close()
+    for i, body in enumerate(bodies):
+        fq, fml, rq, rml = c1.read_calls(i)
+        assert got_k[i] == O.build_mod_record(body, True, fq, fml, rq, rml), i
