@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -14,7 +15,8 @@ namespace hm {
 
 namespace {
 constexpr size_t kBlockPayload = 0xff00;      // uncompressed bytes per BGZF block (htslib's BGZF_BLOCK_SIZE)
-constexpr size_t kReadSlab = 32u << 20;       // compressed bytes read per refill
+constexpr size_t kReadSlab = 8u << 20;        // compressed bytes read per slab (~130 blocks: enough to spread over the threads)
+constexpr size_t kReadAhead = 3;              // inflated slabs queued ahead of the consumer
 constexpr size_t kWriteBatch = 1024;          // blocks deflated per parallel batch (~64 MB)
 
 uint16_t rd16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
@@ -62,8 +64,17 @@ void parallel_for(size_t n, int threads, const std::function<void(size_t)>& fn)
 BgzfReader::~BgzfReader() { close(); }
 void BgzfReader::close()
 {
+    if (worker_.joinable()) {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+            cv_.notify_all();
+        }
+        worker_.join();
+    }
     if (f_) fclose(f_);
     f_ = nullptr;
+    ready_.clear();
 }
 
 bool BgzfReader::open(const char* path, int threads, std::string& err)
@@ -72,12 +83,51 @@ bool BgzfReader::open(const char* path, int threads, std::string& err)
     f_ = fopen(path, "rb");
     if (!f_) { err = std::string("cannot open ") + path; return false; }
     threads_ = std::max(threads, 1);
+    slab_bytes_ = kReadSlab;
+    if (const char* e = getenv("HM_BGZF_SLAB")) slab_bytes_ = std::max<size_t>(1024, (size_t)atoll(e));  // tests: force records to straddle slabs
     raw_.clear();
-    eof_ = false;
+    eof_ = done_ = stop_ = false;
+    worker_err_.clear();
+    worker_ = std::thread(&BgzfReader::run, this);
     return true;
 }
 
-bool BgzfReader::read_more(std::vector<uint8_t>& out, std::string& err)
+void BgzfReader::run()
+{
+    for (;;) {
+        auto slab = std::make_shared<Slab>();
+        std::string err;
+        const bool more = inflate_more(slab->data, err);
+        std::unique_lock<std::mutex> lk(m_);
+        if (!more) {
+            worker_err_ = err;
+            done_ = true;
+            cv_.notify_all();
+            return;
+        }
+        cv_.wait(lk, [&] { return ready_.size() < kReadAhead || stop_; });
+        if (stop_) return;
+        ready_.push_back(std::move(slab));
+        cv_.notify_all();
+    }
+}
+
+std::shared_ptr<Slab> BgzfReader::next_slab(std::string& err)
+{
+    std::unique_lock<std::mutex> lk(m_);
+    cv_.wait(lk, [&] { return !ready_.empty() || done_; });
+    if (ready_.empty()) {
+        err = worker_err_;
+        return nullptr;
+    }
+    std::shared_ptr<Slab> s = std::move(ready_.front());
+    ready_.pop_front();
+    cv_.notify_all();
+    return s;
+}
+
+// Appends the inflated payload of the next group of complete blocks to `out`; false at end of file or on error (err set).
+bool BgzfReader::inflate_more(std::vector<uint8_t>& out, std::string& err)
 {
     for (;;) {
         // complete blocks currently buffered
@@ -126,10 +176,10 @@ bool BgzfReader::read_more(std::vector<uint8_t>& out, std::string& err)
             return false;
         }
         const size_t have = raw_.size();
-        raw_.resize(have + kReadSlab);
-        const size_t got = fread(raw_.data() + have, 1, kReadSlab, f_);
+        raw_.resize(have + slab_bytes_);
+        const size_t got = fread(raw_.data() + have, 1, slab_bytes_, f_);
         raw_.resize(have + got);
-        if (got < kReadSlab) eof_ = true;
+        if (got < slab_bytes_) eof_ = true;
     }
 }
 
@@ -208,14 +258,27 @@ bool BgzfWriter::close(std::string& err)
 }
 
 // ---- BamReader / BamWriter -------------------------------------------------------------------------------------------------
-bool BamReader::need(size_t n, std::string& err)
+bool BamReader::advance(std::string& err)
 {
-    while (buf_.size() - pos_ < n) {
-        if (pos_ > (64u << 20)) {  // drop consumed bytes now and then
-            buf_.erase(buf_.begin(), buf_.begin() + pos_);
-            pos_ = 0;
+    std::shared_ptr<Slab> nx = z_.next_slab(err);
+    if (!nx) return false;
+    cur_ = std::move(nx);
+    pos_ = 0;
+    return true;
+}
+
+bool BamReader::read_bytes(uint8_t* dst, size_t n, std::string& err)
+{
+    while (n) {
+        if (!cur_ || pos_ == cur_->data.size()) {
+            if (!advance(err)) return false;
+            continue;
         }
-        if (!z_.read_more(buf_, err)) return false;
+        const size_t k = std::min(n, cur_->data.size() - pos_);
+        memcpy(dst, cur_->data.data() + pos_, k);
+        dst += k;
+        pos_ += k;
+        n -= k;
     }
     return true;
 }
@@ -223,38 +286,61 @@ bool BamReader::need(size_t n, std::string& err)
 bool BamReader::open(const char* path, int threads, BamHeader& hdr, std::string& err)
 {
     if (!z_.open(path, threads, err)) return false;
-    buf_.clear();
+    cur_.reset();
     pos_ = 0;
-    if (!need(12, err)) { if (err.empty()) err = "empty BAM file"; return false; }
-    if (memcmp(buf_.data(), "BAM\1", 4) != 0) { err = "bad BAM magic"; return false; }
-    const uint32_t l_text = rd32(buf_.data() + 4);
-    if (!need(8 + (size_t)l_text + 4, err)) { if (err.empty()) err = "truncated BAM header"; return false; }
-    hdr.text.assign(reinterpret_cast<const char*>(buf_.data() + 8), l_text);
+    uint8_t h[8];
+    if (!read_bytes(h, 8, err)) { if (err.empty()) err = "empty BAM file"; return false; }
+    if (memcmp(h, "BAM\1", 4) != 0) { err = "bad BAM magic"; return false; }
+    const uint32_t l_text = rd32(h + 4);
+    hdr.text.assign(l_text, '\0');
+    uint8_t nr[4];
+    if (!read_bytes(reinterpret_cast<uint8_t*>(&hdr.text[0]), l_text, err) || !read_bytes(nr, 4, err)) { if (err.empty()) err = "truncated BAM header"; return false; }
     while (!hdr.text.empty() && hdr.text.back() == '\0') hdr.text.pop_back();
-    size_t p = 8 + (size_t)l_text;
-    const uint32_t n_ref = rd32(buf_.data() + p);
-    size_t q = p + 4;
+    const uint32_t n_ref = rd32(nr);
+    hdr.refs.assign(nr, nr + 4);
     for (uint32_t i = 0; i < n_ref; ++i) {
-        if (!need(q + 4, err)) { if (err.empty()) err = "truncated BAM references"; return false; }
-        const uint32_t l_name = rd32(buf_.data() + q);
-        if (!need(q + 4 + (size_t)l_name + 4, err)) { if (err.empty()) err = "truncated BAM references"; return false; }
-        q += 4 + (size_t)l_name + 4;
+        uint8_t ln[4];
+        if (!read_bytes(ln, 4, err)) { if (err.empty()) err = "truncated BAM references"; return false; }
+        const uint32_t l_name = rd32(ln);
+        const size_t at = hdr.refs.size();
+        hdr.refs.resize(at + 4 + (size_t)l_name + 4);
+        memcpy(hdr.refs.data() + at, ln, 4);
+        if (!read_bytes(hdr.refs.data() + at + 4, (size_t)l_name + 4, err)) { if (err.empty()) err = "truncated BAM references"; return false; }
     }
-    hdr.refs.assign(buf_.begin() + p, buf_.begin() + q);
-    pos_ = q;
     return true;
 }
 
 bool BamReader::next(const uint8_t*& body, size_t& len, std::string& err)
 {
     err.clear();
-    if (!need(4, err)) return false;
-    const uint32_t bs = rd32(buf_.data() + pos_);
+    for (;;) {
+        if (!cur_ || pos_ == cur_->data.size()) {  // a clean end of file lands here: advance fails with err empty
+            if (!advance(err)) return false;
+            continue;
+        }
+        const size_t avail = cur_->data.size() - pos_;
+        if (avail >= 4) {
+            const uint32_t bs = rd32(cur_->data.data() + pos_);
+            if (bs < 32) { err = "corrupt BAM record"; return false; }
+            if (avail >= 4 + (size_t)bs) {  // fast path: the record lies inside the current slab
+                body = cur_->data.data() + pos_ + 4;
+                len = bs;
+                pos_ += 4 + (size_t)bs;
+                return true;
+            }
+        }
+        break;
+    }
+    // the record (or its length word) straddles slabs: gather it into a buffer owned by the slab it ends in
+    uint8_t lw[4];
+    if (!read_bytes(lw, 4, err)) { if (err.empty()) err = "truncated BAM record"; return false; }
+    const uint32_t bs = rd32(lw);
     if (bs < 32) { err = "corrupt BAM record"; return false; }
-    if (!need(4 + (size_t)bs, err)) { if (err.empty()) err = "truncated BAM record"; return false; }
-    body = buf_.data() + pos_ + 4;
+    std::vector<uint8_t> tmp(bs);
+    if (!read_bytes(tmp.data(), bs, err)) { if (err.empty()) err = "truncated BAM record"; return false; }
+    cur_->extra.push_back(std::move(tmp));
+    body = cur_->extra.back().data();
     len = bs;
-    pos_ += 4 + (size_t)bs;
     return true;
 }
 

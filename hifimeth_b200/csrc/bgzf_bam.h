@@ -7,9 +7,14 @@
 // needs: sequential reading of records, header pass-through with one @PG line appended, sequential writing.
 #pragma once
 #include <cstdint>
+#include <condition_variable>
 #include <cstdio>
+#include <deque>
 #include <functional>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace hm {
@@ -17,19 +22,37 @@ namespace hm {
 // Runs fn(i) for i in [0, n) on up to `threads` threads (inline when n or threads is small).
 void parallel_for(size_t n, int threads, const std::function<void(size_t)>& fn);
 
+// One inflated stretch of the input.  Record bodies handed out by BamReader point into `data`, or -- for a record that
+// straddles two slabs -- into one of the `extra` buffers of the slab it ends in; both stay valid while the slab is alive.
+struct Slab {
+    std::vector<uint8_t> data;
+    std::deque<std::vector<uint8_t>> extra;
+};
+
+// Sequential BGZF inflater with read-ahead: a background thread reads compressed slabs, inflates their blocks on `threads`
+// threads and queues the results, so that inflation overlaps whatever the consumer does with the previous slab.
 class BgzfReader {
 public:
     ~BgzfReader();
     bool open(const char* path, int threads, std::string& err);
-    // Appends the inflated payload of the next group of blocks to `out`; false at end of file or on error (err set).
-    bool read_more(std::vector<uint8_t>& out, std::string& err);
+    // Next inflated slab (never empty); nullptr at end of file (err empty) or on error (err set).
+    std::shared_ptr<Slab> next_slab(std::string& err);
     void close();
 
 private:
+    void run();
+    bool inflate_more(std::vector<uint8_t>& out, std::string& err);
     FILE* f_ = nullptr;
     int threads_ = 1;
+    size_t slab_bytes_ = 0;     // compressed bytes read per slab
     std::vector<uint8_t> raw_;  // compressed bytes not yet consumed
     bool eof_ = false;
+    std::thread worker_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<std::shared_ptr<Slab>> ready_;
+    bool done_ = false, stop_ = false;
+    std::string worker_err_;
 };
 
 class BgzfWriter {
@@ -54,14 +77,17 @@ struct BamHeader {
 class BamReader {
 public:
     bool open(const char* path, int threads, BamHeader& hdr, std::string& err);
-    // Next alignment record body (SAMv1 4.2 without block_size).  The pointer stays valid until the next call that returns
-    // a record from a different buffer refill; copy it if it must outlive the batch.  false at end of file (err empty) or error.
+    // Next alignment record body (SAMv1 4.2 without block_size).  The pointer stays valid as long as slab() -- the slab the
+    // record ends in -- is kept alive; nothing is copied except records that straddle two slabs.  false at end of file
+    // (err empty) or on error.
     bool next(const uint8_t*& body, size_t& len, std::string& err);
+    const std::shared_ptr<Slab>& slab() const { return cur_; }
 
 private:
-    bool need(size_t n, std::string& err);
+    bool advance(std::string& err);                                 // cur_ exhausted: take the next slab
+    bool read_bytes(uint8_t* dst, size_t n, std::string& err);      // gathers across slabs
     BgzfReader z_;
-    std::vector<uint8_t> buf_;
+    std::shared_ptr<Slab> cur_;
     size_t pos_ = 0;
 };
 

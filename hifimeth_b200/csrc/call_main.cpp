@@ -2,16 +2,26 @@
 // (src/app/hifimeth/mod_main.cpp:303-412) with its worker pool replaced by the C ABI of include/hm_engine.h.
 //
 //   reference                                              here
-//   SAM_Batch + sam_read1 under a mutex (sam_batch.hpp)     BamReader: block-parallel BGZF inflate, records copied to a batch arena
+//   SAM_Batch + sam_read1 under a mutex (sam_batch.hpp)     BamReader: read-ahead block-parallel BGZF inflate, zero-copy record framing
 //   -t worker threads: features + OpenVINO infer()          hm_pack_record -> hm_batch_submit (MM text on device) -> hm_batch_collect
 //   build_one_mod_bam per read (build_mod_bam.cpp:125-248)  hm_build_mod_record_mm per read on -t host threads (bytes only)
 //   pdqsort by read id + sam_write1 (mod_main.cpp:353-362)  batches are emitted in input order; BamWriter: parallel BGZF deflate
 //
-// Two staging slots: while the GPU works on batch k the host emits batch k-1 and packs batch k+1.
+// Threads: one reader (inflate + batch cutting) -> bounded queue of raw batches -> one worker per entry of --devices (each owns an
+// engine with two staging slots: while its GPU works on batch k it assembles the records of batch k-1 and packs batch k+1) ->
+// ordered outbox -> one writer (deflate).  Reads are independent, so this host work queue is the whole multi-GPU story of the
+// path: no collective, weights replicated per engine, batches carry a sequence number and the writer restores
+// input order (the reference sorts by read id, mod_main.cpp:353-354).
 // Options follow src/app/hifimeth/mod_options.cpp:61-181: -m -l -s -b -k -c -t -v -h; -s is accepted and ignored (the site
-// batch is an OpenVINO notion).  Extensions: --device N, --max-bases N, --level N.
+// batch is an OpenVINO notion).  Extensions: --devices LIST, --max-bases N, --level N.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -20,6 +30,7 @@
 #include <vector>
 
 #include <dlfcn.h>
+#include <sys/stat.h>
 
 #include "../../include/hm_engine.h"
 #include "bgzf_bam.h"
@@ -29,8 +40,9 @@ namespace {
 struct Options {
     std::string model_dir, in_path, out_path;
     int min_read_len = 1000, site_batch = 32, reads_per_batch = 10000, keep_kinetics = 0, threads = 0, ctx_mask = 7;
-    int device = 0, level = 6;
-    long long max_bases = 64ll << 20;
+    int level = 6;
+    std::vector<int> devices;   // one worker (engine) per entry; an ordinal may repeat
+    long long max_bases = 0;    // 0 = chosen from the input size
 };
 
 std::string default_model_dir()
@@ -57,7 +69,8 @@ void usage(const char* prog, const char* cmd)
                     "  -k  Keep kinetic values (fi, ri, fp, rp) in modified BAM output\n"
                     "  -c <string>  5mC contexts to detect; comma separated. Default = cpg,chg,chh\n"
                     "  -t <Integer>  Number of CPU threads used for BAM inflate/deflate and record assembly\n"
-                    "  --device <Integer>  CUDA device. Default = 0\n  --max-bases <Integer>  Bases per batch. Default = 67108864\n"
+                    "  --devices <list>  CUDA devices, comma separated; batches are dealt to one worker per entry. Default = 0\n"
+                    "  --max-bases <Integer>  Bases per batch. Default: from the input size, 2 Mi .. 24 Mi\n"
                     "  --level <Integer>  BGZF compression level. Default = 6\n",
             default_model_dir().c_str());
 }
@@ -78,6 +91,21 @@ bool parse_ctx(const std::string& s, int& mask)
         a = b + 1;
     }
     return mask != 0;
+}
+
+bool parse_devices(const std::string& s, std::vector<int>& out)
+{
+    out.clear();
+    size_t a = 0;
+    while (a <= s.size()) {
+        size_t b = s.find(',', a);
+        if (b == std::string::npos) b = s.size();
+        const std::string t = s.substr(a, b - a);
+        if (t.empty() || t.find_first_not_of("0123456789") != std::string::npos || t.size() > 3) return false;
+        out.push_back(atoi(t.c_str()));
+        a = b + 1;
+    }
+    return !out.empty() && out.size() <= 64;
 }
 
 // 0 = ok, 1 = exit success (help / version), -1 = usage error
@@ -102,7 +130,8 @@ int parse(int argc, char** argv, Options& o)
         if (a == "-s") { if (!val(v) || v < 1) return -1; o.site_batch = (int)v; continue; }
         if (a == "-b") { if (!val(v) || v < 1) return -1; o.reads_per_batch = (int)v; continue; }
         if (a == "-t") { if (!val(v) || v < 1) return -1; o.threads = (int)v; continue; }
-        if (a == "--device") { if (!val(v) || v < 0) return -1; o.device = (int)v; continue; }
+        if (a == "--device") { if (!val(v) || v < 0) return -1; o.devices.assign(1, (int)v); continue; }
+        if (a == "--devices") { if (i + 1 >= argc || !parse_devices(argv[++i], o.devices)) return -1; continue; }
         if (a == "--level") { if (!val(v) || v < 0 || v > 9) return -1; o.level = (int)v; continue; }
         if (a == "--max-bases") { if (!val(v) || v < 1024 || v >= 0x7fffffffll) return -1; o.max_bases = v; continue; }
         if (a.size() > 1 && a[0] == '-') { fprintf(stderr, "unrecognised option '%s'\n", a.c_str()); return -1; }
@@ -112,21 +141,314 @@ int parse(int argc, char** argv, Options& o)
     o.in_path = pos[0];
     o.out_path = pos[1];
     if (o.model_dir.empty()) o.model_dir = default_model_dir();
+    if (o.devices.empty()) o.devices.assign(1, 0);
     if (o.threads <= 0) o.threads = (int)std::max(1u, std::thread::hardware_concurrency());
     return 0;
 }
 
 struct Entry {
-    size_t off, len;   // record body in the batch arena
-    int32_t gpu_read;  // index in the submitted batch, or -1: emitted with tags stripped only
+    const uint8_t* body;  // inside one of the batch's slabs
+    size_t len;
 };
 
-struct Batch {
-    std::vector<uint8_t> arena;
+// A run of consecutive input records; `seq` is its position in the input, which the writer restores.  Record bodies are not
+// copied: they point into the inflated slabs, which the batch keeps alive.
+struct RawBatch {
+    uint64_t seq = 0;
+    std::vector<std::shared_ptr<hm::Slab>> slabs;
     std::vector<Entry> entries;
-    uint32_t n_gpu = 0;
-    bool submitted = false;
+    uint64_t bases = 0;
 };
+
+// The records of one batch after the engine: assembled output bodies, ready to be written in order.
+struct OutBatch {
+    uint64_t seq = 0;
+    std::vector<uint8_t> obuf;
+    std::vector<size_t> ooff, olen;
+};
+
+// Bounded multi-producer / multi-consumer queue; close() wakes everybody (pop then drains what is left).
+template <class T>
+class BoundedQueue {
+public:
+    explicit BoundedQueue(size_t cap) : cap_(cap) {}
+    bool push(T&& v)
+    {
+        std::unique_lock<std::mutex> lk(m_);
+        not_full_.wait(lk, [&] { return q_.size() < cap_ || closed_; });
+        if (closed_) return false;
+        q_.push_back(std::move(v));
+        not_empty_.notify_one();
+        return true;
+    }
+    bool pop(T& v)
+    {
+        std::unique_lock<std::mutex> lk(m_);
+        not_empty_.wait(lk, [&] { return !q_.empty() || closed_; });
+        if (q_.empty()) return false;
+        v = std::move(q_.front());
+        q_.pop_front();
+        not_full_.notify_one();
+        return true;
+    }
+    void close()
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        closed_ = true;
+        not_full_.notify_all();
+        not_empty_.notify_all();
+    }
+    void abort()  // close and drop what is queued
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        closed_ = true;
+        q_.clear();
+        not_full_.notify_all();
+        not_empty_.notify_all();
+    }
+
+private:
+    std::mutex m_;
+    std::condition_variable not_full_, not_empty_;
+    std::deque<T> q_;
+    size_t cap_;
+    bool closed_ = false;
+};
+
+// Finished batches arrive in any order (one producer per GPU); the writer takes them in input order.
+class OrderedOutbox {
+public:
+    void put(OutBatch&& b)
+    {
+        std::unique_lock<std::mutex> lk(m_);
+        const uint64_t k = b.seq;
+        ready_.emplace(k, std::move(b));
+        cv_.notify_all();
+    }
+    // Blocks until batch `seq` is there; false once finish() was called and it never will be.
+    bool take(uint64_t seq, OutBatch& b)
+    {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return ready_.count(seq) || done_; });
+        auto it = ready_.find(seq);
+        if (it == ready_.end()) return false;
+        b = std::move(it->second);
+        ready_.erase(it);
+        return true;
+    }
+    void finish()
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        done_ = true;
+        cv_.notify_all();
+    }
+
+private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::map<uint64_t, OutBatch> ready_;
+    bool done_ = false;
+};
+
+struct Shared {
+    Options opt;
+    BoundedQueue<RawBatch> raw;
+    OrderedOutbox outbox;
+    std::atomic<bool> failed{false};
+    std::mutex err_m;
+    std::string err;
+    std::atomic<uint64_t> n_sites[3];
+    std::atomic<uint64_t> n_reads{0}, n_bases{0}, n_batches{0};
+    // phase clocks, seconds summed over threads (report only)
+    std::atomic<uint64_t> us_read{0}, us_create{0}, us_pack{0}, us_submit{0}, us_collect{0}, us_assemble{0}, us_write{0};
+    explicit Shared(const Options& o, size_t depth) : opt(o), raw(depth) { for (auto& v : n_sites) v = 0; }
+    void fail(const std::string& msg)
+    {
+        {
+            std::lock_guard<std::mutex> lk(err_m);
+            if (err.empty()) err = msg;
+        }
+        failed = true;
+        raw.abort();
+        outbox.finish();
+    }
+};
+
+struct Stopwatch {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    uint64_t lap_us()
+    {
+        const auto t1 = std::chrono::steady_clock::now();
+        const uint64_t us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+        t0 = t1;
+        return us;
+    }
+};
+
+// Reader: inflates the input (block-parallel) and cuts it into batches by read count and by bases.
+void reader_thread(Shared& S, hm::BamReader& in)
+{
+    std::string err;
+    RawBatch cur;
+    uint64_t seq = 0;
+    Stopwatch sw;
+    auto flush = [&]() {
+        if (cur.entries.empty()) return true;
+        cur.seq = seq++;
+        S.n_batches = seq;
+        S.us_read += sw.lap_us();
+        const bool ok = S.raw.push(std::move(cur));
+        sw.lap_us();  // time blocked on a full queue is not reading time
+        cur = RawBatch{};
+        return ok;
+    };
+    const uint8_t* body;
+    size_t len;
+    while (!S.failed) {
+        if (!in.next(body, len, err)) {
+            if (!err.empty()) { S.fail(S.opt.in_path + ": " + err); return; }
+            break;
+        }
+        uint32_t l = 0;
+        memcpy(&l, body + 16, 4);  // l_seq (BamReader guarantees >= 32 bytes)
+        if (l > 0x7fffffffu) l = 0;
+        if (!cur.entries.empty() && (cur.entries.size() >= (size_t)S.opt.reads_per_batch || cur.bases + l > (uint64_t)S.opt.max_bases))
+            if (!flush()) return;
+        cur.entries.push_back(Entry{body, len});
+        if (cur.slabs.empty() || cur.slabs.back() != in.slab()) cur.slabs.push_back(in.slab());
+        if (l <= (uint64_t)S.opt.max_bases) cur.bases += l;  // longer records are passed through, they take no staging space
+        S.n_reads++;
+        S.n_bases += l;
+    }
+    flush();
+    S.raw.close();
+}
+
+// One worker per entry of --devices: owns an engine with two staging slots.  While the GPU works on batch k the worker
+// assembles the records of batch k-1 and packs batch k+1.
+void gpu_worker(Shared& S, int device, int threads)
+{
+    const Options& opt = S.opt;
+    Stopwatch sw;
+    hm_config cfg{};
+    cfg.model_dir = opt.model_dir.c_str();
+    cfg.ctx_mask = opt.ctx_mask;
+    cfg.min_read_len = opt.min_read_len;
+    cfg.device = device;
+    cfg.n_slots = 2;
+    cfg.max_reads = (uint32_t)opt.reads_per_batch;
+    cfg.max_bases = (uint32_t)opt.max_bases;
+    cfg.cnn_mode = HM_CNN_TENSOR;
+    hm_engine* eng = nullptr;
+    if (hm_engine_create(&cfg, &eng) != HM_OK) { S.fail(std::string("device ") + std::to_string(device) + ": " + hm_last_error(nullptr)); return; }
+    S.us_create += sw.lap_us();
+
+    struct InFlight {
+        RawBatch raw;
+        std::vector<int32_t> read_index;
+        bool live = false;
+    } fl[2];
+
+    auto finish = [&](int slot) -> bool {
+        InFlight& f = fl[slot];
+        Stopwatch w;
+        hm_call_batch calls{};
+        if (hm_batch_collect(eng, slot, &calls) != HM_OK) { S.fail(hm_last_error(eng)); return false; }
+        S.us_collect += w.lap_us();
+        for (int c = 0; c < 3; ++c) S.n_sites[c] += calls.n_sites[c];
+        const size_t n = f.raw.entries.size();
+        OutBatch ob;
+        ob.seq = f.raw.seq;
+        ob.ooff.assign(n + 1, 0);
+        ob.olen.assign(n, 0);
+        for (size_t i = 0; i < n; ++i) {
+            uint32_t nc = 0, text = 0;
+            const int32_t r = f.read_index[i];
+            if (r >= 0) {
+                nc = calls.call_off[r + 1] - calls.call_off[r];
+                text = calls.mm_off[r + 1] - calls.mm_off[r];
+            }
+            ob.ooff[i + 1] = ob.ooff[i] + f.raw.entries[i].len + 64 + nc + text;
+        }
+        ob.obuf.resize(ob.ooff.back());
+        std::atomic<int> bad{-1};
+        hm::parallel_for(n, threads, [&](size_t i) {
+            const Entry& e = f.raw.entries[i];
+            const uint8_t* body = e.body;
+            uint8_t* dst = ob.obuf.data() + ob.ooff[i];
+            const int32_t ri = f.read_index[i];
+            int rc;
+            if (ri < 0) {
+                rc = hm_build_mod_record_mm(body, e.len, opt.keep_kinetics, nullptr, 0, nullptr, 0, nullptr, 0, 0, dst, &ob.olen[i]);
+                if (rc == HM_ERR_FORMAT) {  // not parseable as a record: pass the bytes through untouched
+                    memcpy(dst, body, e.len);
+                    ob.olen[i] = e.len;
+                    rc = 0;
+                }
+            } else {
+                const uint32_t r = (uint32_t)ri, a = calls.call_off[r], nc = calls.call_off[r + 1] - a, nf = calls.n_fwd[r];
+                const uint8_t* mm = calls.mm_text + calls.mm_off[r];
+                const uint32_t fl_ = calls.mm_fwd_len[r], rl = calls.mm_off[r + 1] - calls.mm_off[r] - fl_;
+                rc = hm_build_mod_record_mm(body, e.len, opt.keep_kinetics, mm, fl_, mm + fl_, rl, calls.ml + a, nf, nc - nf, dst, &ob.olen[i]);
+            }
+            if (rc != 0) bad = (int)i;
+        });
+        if (bad >= 0) { S.fail("cannot assemble output record " + std::to_string(bad.load()) + " of batch " + std::to_string(ob.seq)); return false; }
+        f.raw = RawBatch{};
+        f.live = false;
+        S.us_assemble += w.lap_us();
+        S.outbox.put(std::move(ob));
+        return true;
+    };
+
+    int cur = 0;
+    bool ok = true;
+    while (ok && !S.failed) {
+        RawBatch rb;
+        sw.lap_us();
+        if (!S.raw.pop(rb)) break;
+        sw.lap_us();
+        InFlight& f = fl[cur];
+        hm_read_batch hb{};
+        if (hm_batch_acquire(eng, cur, &hb) != HM_OK) { S.fail(hm_last_error(eng)); ok = false; break; }
+        const size_t n = rb.entries.size();
+        std::vector<const uint8_t*> bodies(n);
+        std::vector<size_t> lens(n);
+        for (size_t i = 0; i < n; ++i) { bodies[i] = rb.entries[i].body; lens[i] = rb.entries[i].len; }
+        f.read_index.assign(n, -1);
+        uint32_t n_packed = 0;
+        if (hm_pack_records(&hb, (uint32_t)n, bodies.data(), lens.data(), opt.min_read_len, threads, f.read_index.data(), &n_packed) != HM_OK) {
+            S.fail("internal: a batch does not fit its staging slot");
+            ok = false;
+            break;
+        }
+        S.us_pack += sw.lap_us();
+        if (hm_batch_submit(eng, cur, n_packed, HM_SUBMIT_MM_TEXT) != HM_OK) { S.fail(hm_last_error(eng)); ok = false; break; }
+        S.us_submit += sw.lap_us();
+        f.raw = std::move(rb);
+        f.live = true;
+        if (fl[cur ^ 1].live && !finish(cur ^ 1)) { ok = false; break; }
+        cur ^= 1;
+    }
+    // drain, older batch first: slot `cur` was finished inside the loop unless it ended early, slot cur ^ 1 holds the newest
+    for (int k = 0; k < 2 && ok && !S.failed; ++k)
+        if (fl[cur ^ k].live) ok = finish(cur ^ k);
+    hm_engine_destroy(eng);
+}
+
+void writer_thread(Shared& S, hm::BamWriter& out)
+{
+    std::string err;
+    Stopwatch sw;
+    for (uint64_t seq = 0;; ++seq) {
+        OutBatch b;
+        if (!S.outbox.take(seq, b)) break;
+        sw.lap_us();
+        for (size_t i = 0; i < b.olen.size(); ++i)
+            if (!out.write_record(b.obuf.data() + b.ooff[i], b.olen[i], err)) { S.fail(S.opt.out_path + ": " + err); return; }
+        S.us_write += sw.lap_us();
+    }
+}
 
 }  // namespace
 
@@ -150,123 +472,37 @@ extern "C" int hm_call_main(int argc, char** argv)
     hm::BamWriter out;
     if (!out.open(opt.out_path.c_str(), opt.threads, opt.level, hdr, err)) { fprintf(stderr, "[hifimeth-b200] %s: %s\n", opt.out_path.c_str(), err.c_str()); return EXIT_FAILURE; }
 
-    hm_config cfg{};
-    cfg.model_dir = opt.model_dir.c_str();
-    cfg.ctx_mask = opt.ctx_mask;
-    cfg.min_read_len = opt.min_read_len;
-    cfg.device = opt.device;
-    cfg.n_slots = 2;
-    cfg.max_reads = (uint32_t)opt.reads_per_batch;
-    cfg.max_bases = (uint32_t)opt.max_bases;
-    cfg.cnn_mode = HM_CNN_TENSOR;
-    hm_engine* eng = nullptr;
-    if (hm_engine_create(&cfg, &eng) != HM_OK) { fprintf(stderr, "[hifimeth-b200] %s\n", hm_last_error(nullptr)); return EXIT_FAILURE; }
-
-    Batch batches[2];
-    uint64_t n_reads = 0, n_bases = 0, n_sites[3] = {0, 0, 0};
-    bool eof = false, failed = false;
-    const uint8_t* pending_body = nullptr;  // a record that did not fit the previous batch
-    size_t pending_len = 0;
-    std::vector<uint8_t> pending_copy;
-
-    auto emit = [&](int slot) -> bool {
-        Batch& b = batches[slot];
-        hm_call_batch calls{};
-        if (b.submitted && hm_batch_collect(eng, slot, &calls) != HM_OK) { fprintf(stderr, "[hifimeth-b200] %s\n", hm_last_error(eng)); return false; }
-        if (b.submitted)
-            for (int c = 0; c < 3; ++c) n_sites[c] += calls.n_sites[c];
-        // output arena: one bounded region per record, filled in parallel, written in order
-        std::vector<size_t> ooff(b.entries.size() + 1, 0), olen(b.entries.size(), 0);
-        for (size_t i = 0; i < b.entries.size(); ++i) {
-            const Entry& e = b.entries[i];
-            uint32_t nc = 0, text = 0;
-            if (e.gpu_read >= 0) {
-                nc = calls.call_off[e.gpu_read + 1] - calls.call_off[e.gpu_read];
-                text = calls.mm_off[e.gpu_read + 1] - calls.mm_off[e.gpu_read];
-            }
-            ooff[i + 1] = ooff[i] + e.len + 64 + nc + text;
-        }
-        std::vector<uint8_t> obuf(ooff.back());
-        std::vector<int> rcs(b.entries.size(), 0);
-        hm::parallel_for(b.entries.size(), opt.threads, [&](size_t i) {
-            const Entry& e = b.entries[i];
-            const uint8_t* body = b.arena.data() + e.off;
-            if (e.gpu_read < 0) {
-                rcs[i] = hm_build_mod_record_mm(body, e.len, opt.keep_kinetics, nullptr, 0, nullptr, 0, nullptr, 0, 0, obuf.data() + ooff[i], &olen[i]);
-                if (rcs[i] == HM_ERR_FORMAT) {  // not parseable as a record: pass the bytes through untouched
-                    memcpy(obuf.data() + ooff[i], body, e.len);
-                    olen[i] = e.len;
-                    rcs[i] = 0;
-                }
-                return;
-            }
-            const uint32_t r = (uint32_t)e.gpu_read, a = calls.call_off[r], nc = calls.call_off[r + 1] - a, nf = calls.n_fwd[r];
-            const uint8_t* mm = calls.mm_text + calls.mm_off[r];
-            const uint32_t fl = calls.mm_fwd_len[r], rl = calls.mm_off[r + 1] - calls.mm_off[r] - fl;
-            rcs[i] = hm_build_mod_record_mm(body, e.len, opt.keep_kinetics, mm, fl, mm + fl, rl, calls.ml + a, nf, nc - nf, obuf.data() + ooff[i], &olen[i]);
-        });
-        for (size_t i = 0; i < b.entries.size(); ++i) {
-            if (rcs[i] != 0) { fprintf(stderr, "[hifimeth-b200] cannot assemble output record %zu of a batch (%d)\n", i, rcs[i]); return false; }
-            if (!out.write_record(obuf.data() + ooff[i], olen[i], err)) { fprintf(stderr, "[hifimeth-b200] %s\n", err.c_str()); return false; }
-        }
-        b.entries.clear();
-        b.arena.clear();
-        b.submitted = false;
-        b.n_gpu = 0;
-        return true;
-    };
-
-    int cur = 0, prev = -1;
-    while (!failed) {
-        Batch& b = batches[cur];
-        hm_read_batch rb{};
-        if (hm_batch_acquire(eng, cur, &rb) != HM_OK) { fprintf(stderr, "[hifimeth-b200] %s\n", hm_last_error(eng)); failed = true; break; }
-        uint32_t n = 0;
-        while (!eof && b.entries.size() < (size_t)opt.reads_per_batch) {
-            const uint8_t* body;
-            size_t len;
-            if (pending_body) { body = pending_body; len = pending_len; pending_body = nullptr; }
-            else if (!in.next(body, len, err)) {
-                if (!err.empty()) { fprintf(stderr, "[hifimeth-b200] %s: %s\n", opt.in_path.c_str(), err.c_str()); failed = true; }
-                eof = true;
-                break;
-            }
-            const int rc = hm_pack_record(&rb, &n, body, len, opt.min_read_len);
-            if (rc == HM_ERR_ARG && n > 0) {  // batch full (bases): this record opens the next batch
-                pending_copy.assign(body, body + len);
-                pending_body = pending_copy.data();
-                pending_len = len;
-                break;
-            }
-            Entry e{b.arena.size(), len, rc == HM_OK ? (int32_t)(n - 1) : -1};  // too long for any batch / malformed: pass through
-            b.arena.insert(b.arena.end(), body, body + len);
-            b.entries.push_back(e);
-            if (len >= 32) { uint32_t l; memcpy(&l, body + 16, 4); n_bases += l; }
-            ++n_reads;
-        }
-        if (failed) break;
-        b.n_gpu = n;
-        if (!b.entries.empty()) {
-            if (hm_batch_submit(eng, cur, n, HM_SUBMIT_MM_TEXT) != HM_OK) { fprintf(stderr, "[hifimeth-b200] %s\n", hm_last_error(eng)); failed = true; break; }
-            b.submitted = true;
-        }
-        if (prev >= 0 && !emit(prev)) { failed = true; break; }
-        prev = b.entries.empty() ? -1 : cur;
-        cur ^= 1;
-        if (eof && !pending_body && prev < 0) break;
-        if (eof && !pending_body) {
-            if (!emit(prev)) failed = true;
-            break;
-        }
+    const int n_workers = (int)opt.devices.size();
+    if (opt.max_bases <= 0) {
+        // Batch size from the input size: BAM with kinetics is ~3.7 compressed bytes per base; aim at >= 3 batches per worker so
+        // that reading, the GPU and writing overlap, within [2 Mi, 24 Mi] bases (sub-batches of the CNN stage hold ~1 Mi bases).
+        struct stat sb;
+        long long est = 24ll << 20;
+        if (stat(opt.in_path.c_str(), &sb) == 0 && S_ISREG(sb.st_mode)) est = (long long)(sb.st_size / 3.7) / (3ll * n_workers);
+        opt.max_bases = std::min<long long>(24ll << 20, std::max<long long>(2ll << 20, est));
     }
-    hm_engine_destroy(eng);
-    if (!failed && !out.close(err)) { fprintf(stderr, "[hifimeth-b200] %s\n", err.c_str()); failed = true; }
-    if (failed) return EXIT_FAILURE;
+    Shared S(opt, (size_t)2 * n_workers);
+    std::thread reader(reader_thread, std::ref(S), std::ref(in));
+    std::vector<std::thread> workers;
+    const int worker_threads = std::max(1, opt.threads / n_workers);
+    for (int d : opt.devices) workers.emplace_back(gpu_worker, std::ref(S), d, worker_threads);
+    std::thread writer(writer_thread, std::ref(S), std::ref(out));
+    reader.join();
+    for (auto& w : workers) w.join();
+    S.outbox.finish();
+    writer.join();
+    bool failed = S.failed;
+    if (!failed && !out.close(err)) { S.err = opt.out_path + ": " + err; failed = true; }
+    if (failed) { fprintf(stderr, "[hifimeth-b200] %s\n", S.err.c_str()); return EXIT_FAILURE; }
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
-    const uint64_t sites = n_sites[0] + n_sites[1] + n_sites[2];
+    const uint64_t sites = S.n_sites[0] + S.n_sites[1] + S.n_sites[2];
+    fprintf(stderr, "[hifimeth-b200] phases (s, summed per thread role): read+inflate %.2f, engine create %.2f, pack %.2f, submit %.2f, "
+                    "collect(wait) %.2f, assemble %.2f, write+deflate %.2f; %llu batches of <= %lld bases on %d worker(s), %d host threads\n",
+            S.us_read / 1e6, S.us_create / 1e6, S.us_pack / 1e6, S.us_submit / 1e6, S.us_collect / 1e6, S.us_assemble / 1e6, S.us_write / 1e6,
+            (unsigned long long)S.n_batches.load(), opt.max_bases, n_workers, opt.threads);
     fprintf(stderr, "[hifimeth-b200] %llu reads, %llu bases, CpG %llu, CHG %llu, CHH %llu samples in %.2f s (%.3g sites/s, %.3g reads/s)\n",
-            (unsigned long long)n_reads, (unsigned long long)n_bases, (unsigned long long)n_sites[0], (unsigned long long)n_sites[1],
-            (unsigned long long)n_sites[2], secs, sites / secs, n_reads / secs);
+            (unsigned long long)S.n_reads.load(), (unsigned long long)S.n_bases.load(), (unsigned long long)S.n_sites[0].load(),
+            (unsigned long long)S.n_sites[1].load(), (unsigned long long)S.n_sites[2].load(), secs, sites / secs, S.n_reads.load() / secs);
     return EXIT_SUCCESS;
 }
 

@@ -4,6 +4,7 @@
 // Reference control flow being replaced: s_worker_thread, src/app/hifimeth/mod_main.cpp:145-262.
 #include <algorithm>
 #include <cstdarg>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -213,6 +214,7 @@ int alloc_slot(hm_engine* e, Slot& s)
     const size_t seq_cap = B / 2 + R + 16;
     s.max_chunks = (uint32_t)(B / hm::kChunk + R + 1);
     const char* st = "slot allocation";
+    const auto ta = std::chrono::steady_clock::now();
     HM_CUDA(e, st, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     for (auto& ev : s.ev) HM_CUDA(e, st, cudaEventCreate(&ev));
     s.host.max_reads = (uint32_t)R;
@@ -286,8 +288,12 @@ int alloc_slot(hm_engine* e, Slot& s)
         }
         for (int l = 0; l < 8; ++l) HM_CUDA(e, st, dmalloc(&s.d_act[l], S * (size_t)lmax[l] * cmax[l]));
     } else {
+        const auto tb = std::chrono::steady_clock::now();
         int rc = hm::tensor_workspace_alloc(s.tws, e->cfg.max_bases, e->cfg.max_reads, 0);
         if (rc) return fail(e, HM_ERR_CUDA, "CUDA error in tensor workspace allocation: %s", hm::tensor_last_error());
+        if (getenv("HM_VERBOSE"))
+            fprintf(stderr, "[hm_engine_create]   slot: staging + lists %.3f s, tensor workspace %.3f s\n", std::chrono::duration<double>(tb - ta).count(),
+                    std::chrono::duration<double>(std::chrono::steady_clock::now() - tb).count());
     }
     return HM_OK;
 }
@@ -443,6 +449,13 @@ int hm_engine_create(const hm_config* cfg, hm_engine** out)
     if (prop.major != 10) return fail(nullptr, HM_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
     if ((st = cudaSetDevice(cfg->device)) != cudaSuccess) return fail(nullptr, HM_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(st));
 
+    // HM_VERBOSE=1: wall-clock of the creation stages on stderr (context, models + plan lowering, slot allocation)
+    const bool verbose = getenv("HM_VERBOSE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    const auto t0 = now();
+    cudaFree(nullptr);  // forces context creation here so that it is timed on its own
+    const auto t1 = now();
     hm_engine* e = new hm_engine();
     e->cfg = *cfg;
     e->model_dir = cfg->model_dir;
@@ -461,11 +474,15 @@ int hm_engine_create(const hm_config* cfg, hm_engine** out)
         if (cfg->cnn_mode == HM_CNN_FP32_SIMT) rc = build_fp32_model(e, c);
         else if (hm::tensor_model_build(e->tensor[c], e->host_model[c])) rc = fail(e, HM_ERR_CUDA, "CUDA error in tensor model build: %s", hm::tensor_last_error());
     }
+    const auto t2 = now();
     if (rc == HM_OK) {
         e->slots.resize(e->n_slots);
         for (auto& s : e->slots)
             if ((rc = alloc_slot(e, s))) break;
     }
+    if (verbose)
+        fprintf(stderr, "[hm_engine_create] device %d: context %.3f s, models + plan %.3f s, %d slot(s) %.3f s\n", cfg->device, secs(t0, t1), secs(t1, t2),
+                e->n_slots, secs(t2, now()));
     if (rc != HM_OK) {
         fail(nullptr, rc, "%s", e->err.c_str());
         hm_engine_destroy(e);

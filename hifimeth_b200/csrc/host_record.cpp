@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/hm_engine.h"
+#include "bgzf_bam.h"
 
 namespace {
 
@@ -113,18 +114,11 @@ uint16_t hm_codev1_decode(uint8_t code)
     return (uint16_t)((c - 192) * 8 + 448);
 }
 
-int hm_pack_record(hm_read_batch* b, uint32_t* n_reads, const uint8_t* body, size_t len, int32_t min_read_len)
+// Writes record `body` as read i of the batch at base offset b0 / packed-SEQ offset s0 (both already known to fit).
+static void pack_at(hm_read_batch* b, uint32_t i, uint32_t b0, uint32_t s0, const uint8_t* body, size_t len, const RecLayout& r,
+                    int32_t min_read_len)
 {
-    if (!b || !n_reads || !body) return HM_ERR_ARG;
-    RecLayout r;
-    if (!layout_of(body, len, r)) return HM_ERR_FORMAT;
-    uint32_t i = *n_reads;
-    uint32_t l = (uint32_t)r.l_seq;
-    if (i >= b->max_reads) return HM_ERR_ARG;
-    uint32_t b0 = i ? b->base_off[i] : 0, s0 = i ? b->seq_off[i] : 0;
-    if ((uint64_t)b0 + l > b->max_bases) return HM_ERR_ARG;
-    if (i == 0) { b->base_off[0] = 0; b->seq_off[0] = 0; }
-
+    const uint32_t l = (uint32_t)r.l_seq;
     // locate the four kinetics tags (first occurrence wins, as bam_aux_get does)
     const uint8_t* tag[4] = {nullptr, nullptr, nullptr, nullptr};
     static const char names[4][2] = {{'f', 'i'}, {'f', 'p'}, {'r', 'i'}, {'r', 'p'}};
@@ -161,9 +155,54 @@ int hm_pack_record(hm_read_batch* b, uint32_t* n_reads, const uint8_t* body, siz
     memcpy(b->seq4 + s0, body + r.seq_off, (l + 1) >> 1);
     b->flag[i] = r.flag;
     b->valid[i] = ok ? 1 : 0;
+}
+
+int hm_pack_record(hm_read_batch* b, uint32_t* n_reads, const uint8_t* body, size_t len, int32_t min_read_len)
+{
+    if (!b || !n_reads || !body) return HM_ERR_ARG;
+    RecLayout r;
+    if (!layout_of(body, len, r)) return HM_ERR_FORMAT;
+    uint32_t i = *n_reads;
+    uint32_t l = (uint32_t)r.l_seq;
+    if (i >= b->max_reads) return HM_ERR_ARG;
+    uint32_t b0 = i ? b->base_off[i] : 0, s0 = i ? b->seq_off[i] : 0;
+    if ((uint64_t)b0 + l > b->max_bases) return HM_ERR_ARG;
+    if (i == 0) { b->base_off[0] = 0; b->seq_off[0] = 0; }
+    pack_at(b, i, b0, s0, body, len, r, min_read_len);
     b->base_off[i + 1] = b0 + l;
     b->seq_off[i + 1] = s0 + ((l + 1) >> 1);
     *n_reads = i + 1;
+    return HM_OK;
+}
+
+int hm_pack_records(hm_read_batch* b, uint32_t n, const uint8_t* const* bodies, const size_t* lens, int32_t min_read_len, int threads,
+                    int32_t* read_index, uint32_t* n_packed)
+{
+    if (!b || (n && (!bodies || !lens || !read_index)) || !n_packed) return HM_ERR_ARG;
+    // pass 1 (serial, touches 32 bytes per record): layouts and offsets
+    std::vector<RecLayout> lay(n);
+    uint32_t m = 0, b0 = 0, s0 = 0;
+    b->base_off[0] = 0;
+    b->seq_off[0] = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        read_index[k] = -1;
+        if (!layout_of(bodies[k], lens[k], lay[k])) continue;  // malformed: the caller passes the bytes through
+        const uint32_t l = (uint32_t)lay[k].l_seq;
+        if (l > b->max_bases) continue;                         // longer than any batch: passed through uncalled
+        if (m >= b->max_reads || (uint64_t)b0 + l > b->max_bases) return HM_ERR_ARG;
+        read_index[k] = (int32_t)m;
+        b0 += l;
+        s0 += (l + 1) >> 1;
+        ++m;
+        b->base_off[m] = b0;
+        b->seq_off[m] = s0;
+    }
+    // pass 2 (parallel): the copies
+    hm::parallel_for(n, threads, [&](size_t k) {
+        const int32_t i = read_index[k];
+        if (i >= 0) pack_at(b, (uint32_t)i, b->base_off[i], b->seq_off[i], bodies[k], lens[k], lay[k], min_read_len);
+    });
+    *n_packed = m;
     return HM_OK;
 }
 

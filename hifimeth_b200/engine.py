@@ -55,7 +55,7 @@ class hm_timing(C.Structure):
 
 
 ABI_SYMBOLS = ["hm_engine_create", "hm_engine_destroy", "hm_last_error", "hm_version", "hm_batch_acquire", "hm_batch_submit",
-               "hm_batch_collect", "hm_batch_timing", "hm_codev1_encode", "hm_codev1_decode", "hm_pack_record",
+               "hm_batch_collect", "hm_batch_timing", "hm_codev1_encode", "hm_codev1_decode", "hm_pack_record", "hm_pack_records",
                "hm_mod_record_bound", "hm_build_mod_record", "hm_build_mod_record_mm", "hm_call_main", "hm_bam_copy", "hm_debug_dump_decode", "hm_debug_dump_ctx",
                "hm_debug_dump_features", "hm_debug_dump_logits", "hm_debug_dense_op", "hm_debug_last_op_ms", "hm_microbench"]
 
@@ -91,6 +91,8 @@ def load_library() -> C.CDLL:
                                       C.POINTER(C.c_size_t)]
     L.hm_build_mod_record_mm.argtypes = [_u8p, C.c_size_t, C.c_int, _u8p, C.c_uint32, _u8p, C.c_uint32, _u8p, C.c_uint32, C.c_uint32, _u8p,
                                          C.POINTER(C.c_size_t)]
+    L.hm_pack_records.argtypes = [C.POINTER(hm_read_batch), C.c_uint32, C.POINTER(_u8p), C.POINTER(C.c_size_t), C.c_int32, C.c_int,
+                                  _i32p, _u32p]
     L.hm_call_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
     L.hm_bam_copy.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int]
     L.hm_debug_dump_decode.argtypes = [C.c_void_p, C.c_int, _u16p, _u16p, _u16p, _u16p, _u8p, _u8p]
@@ -275,8 +277,9 @@ def build_mod_record(body: bytes, keep_kinetics: bool, fwd_qoff, fwd_ml, rev_qof
     return out[:n.value].tobytes()
 
 
-def pack_records_host(bodies, min_read_len: int = 1000, max_bases: int = None):
-    """hm_pack_record into plain numpy buffers (no GPU needed): returns a synth.ReadBatch."""
+def pack_records_host(bodies, min_read_len: int = 1000, max_bases: int = None, threads: int = 0):
+    """hm_pack_record into plain numpy buffers (no GPU needed): returns a synth.ReadBatch.  threads > 0 packs the whole list
+    with one hm_pack_records call instead (the `call` driver's path); records it refuses (-1) are left out."""
     from .synth import ReadBatch
 
     L = load_library()
@@ -289,11 +292,21 @@ def pack_records_host(bodies, min_read_len: int = 1000, max_bases: int = None):
                       arr["flag"].ctypes.data_as(_u16p), arr["valid"].ctypes.data_as(_u8p), arr["fi"].ctypes.data_as(_u8p),
                       arr["fp"].ctypes.data_as(_u8p), arr["ri"].ctypes.data_as(_u8p), arr["rp"].ctypes.data_as(_u8p))
     n = C.c_uint32(0)
-    for body in bodies:
-        src = np.frombuffer(body, np.uint8)
-        rc = L.hm_pack_record(C.byref(b), C.byref(n), src.ctypes.data_as(_u8p), len(body), min_read_len)
+    if threads > 0:
+        keep = [np.frombuffer(body, np.uint8) for body in bodies]
+        ptrs = (_u8p * len(keep))(*[k.ctypes.data_as(_u8p) for k in keep])
+        lens = (C.c_size_t * len(keep))(*[len(body) for body in bodies])
+        idx = np.full(len(keep), -2, np.int32)
+        rc = L.hm_pack_records(C.byref(b), len(keep), ptrs, lens, min_read_len, threads, idx.ctypes.data_as(_i32p), C.byref(n))
         if rc != 0:
-            raise HmError(f"hm_pack_record failed ({rc})")
+            raise HmError(f"hm_pack_records failed ({rc})")
+        assert (idx[idx >= 0] == np.arange(n.value)).all()
+    else:
+        for body in bodies:
+            src = np.frombuffer(body, np.uint8)
+            rc = L.hm_pack_record(C.byref(b), C.byref(n), src.ctypes.data_as(_u8p), len(body), min_read_len)
+            if rc != 0:
+                raise HmError(f"hm_pack_record failed ({rc})")
     nb = int(arr["base_off"][n.value])
     ns = int(arr["seq_off"][n.value])
     return ReadBatch(n.value, arr["base_off"][:n.value + 1], arr["seq_off"][:n.value + 1], arr["seq4"][:ns], arr["flag"][:n.value],

@@ -143,6 +143,11 @@ uint16_t hm_codev1_decode(uint8_t code);
  * present as B:C or B:S with count == l_seq (src/app/hifimeth/mod_main.cpp:189-196,
  * src/corelib/bam_info.cpp:443-453).  Returns HM_ERR_ARG (and appends nothing) when the batch is full. */
 int hm_pack_record(hm_read_batch* b, uint32_t* n_reads, const uint8_t* body, size_t len, int32_t min_read_len);
+/* The same for a whole batch, copying on up to `threads` host threads: records bodies[0..n) become reads 0..*n_packed of an
+ * EMPTY staging batch in order; read_index[k] = the read index of record k, or -1 for a record that is malformed or longer
+ * than max_bases (the caller passes those through).  HM_ERR_ARG when the records do not fit the batch. */
+int hm_pack_records(hm_read_batch* b, uint32_t n, const uint8_t* const* bodies, const size_t* lens, int32_t min_read_len,
+                    int threads, int32_t* read_index, uint32_t* n_packed);
 
 /* build_one_mod_bam, src/corelib/build_mod_bam.cpp:125-248, on a record body: strips fi/ri/fp/rp unless
  * keep_kinetics, strips old ML/MM, appends MM:Z ML:B:C MN when there are calls.  out needs

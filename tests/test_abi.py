@@ -90,6 +90,31 @@ def test_pack_record_rejects_overflow_and_garbage(lib_built):
     assert lib.hm_pack_record(C.byref(b), C.byref(n), junk.ctypes.data_as(C.POINTER(C.c_uint8)), 8, 1000) != 0
 
 
+def test_pack_records_batched_equals_one_by_one(lib_built):
+    """hm_pack_records (the `call` driver's parallel packer) fills the staging arrays exactly like repeated hm_pack_record;
+    malformed and over-long records get index -1 and take no space; a batch that does not fit is refused."""
+    _, reads = synth.make_reads(23, (300, 5000), seed=77, flag_rev_every=3, short_every=5)
+    bodies = golden_bodies(golden_reads()) + [synth.record_body(r, kinetics_as_u16=(i % 4 == 1)) for i, r in enumerate(reads)]
+    one = hme.pack_records_host(bodies, min_read_len=1000)
+    for threads in (1, 5):
+        many = hme.pack_records_host(bodies, min_read_len=1000, threads=threads)
+        assert many.n_reads == one.n_reads == len(bodies)
+        for k in ("base_off", "seq_off", "seq4", "flag", "valid", "fi", "fp", "ri", "rp"):
+            assert (getattr(many, k) == getattr(one, k)).all(), k
+    junk = bytes(40)  # l_seq 0 with a name length of 0: parses as an empty record; a truncated one does not
+    with_bad = [bodies[0], bodies[1][:50], bodies[2]]
+    got = hme.pack_records_host(with_bad, min_read_len=1000, threads=2)
+    assert got.n_reads == 2 and (got.fi == hme.pack_records_host([bodies[0], bodies[2]]).fi).all()
+    lens = [len(r["seq"]) for r in golden_reads()]
+    i_long, i_short = int(np.argmax(lens)), int(np.argmin(lens))
+    gb = golden_bodies(golden_reads())
+    got = hme.pack_records_host([gb[i_long], gb[i_short]], min_read_len=1000, threads=2, max_bases=lens[i_long] - 1)
+    assert got.n_reads == 1 and got.n_bases == lens[i_short]  # the long record can never be staged: left out, not an error
+    with pytest.raises(hme.HmError):
+        hme.pack_records_host([bodies[0], bodies[0]], threads=2, max_bases=len(golden_reads()[0]["seq"]) + 10)
+    del junk
+
+
 def test_build_mod_record_vs_golden(lib_built, golden):
     for i in range(int(golden["n_reads"])):
         body = golden[f"body{i}"].tobytes()

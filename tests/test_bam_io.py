@@ -26,6 +26,25 @@ def test_bam_round_trip_parallel_codec(lib_built, tmp_path):
         assert raw[-28:] == bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0])  # EOF marker
 
 
+def test_bam_records_straddling_slabs(lib_built, tmp_path, monkeypatch):
+    """The reader hands out records without copying them; one that straddles two (or, with tiny slabs, many) inflated slabs is
+    gathered into a side buffer.  HM_BGZF_SLAB shrinks the slabs so that most records straddle."""
+    _, reads = synth.make_reads(25, (200, 7000), seed=11)
+    bodies = [synth.record_body(r) for r in reads]
+    src, dst = tmp_path / "in.bam", tmp_path / "out.bam"
+    synth.write_bam(src, bodies, level=1, block=5000)
+    lib = hme.load_library()
+    for slab in ("1024", "9000", "70000"):
+        monkeypatch.setenv("HM_BGZF_SLAB", slab)
+        assert lib.hm_bam_copy(str(src).encode(), str(dst).encode(), 3, 1) == len(bodies)
+        assert synth.read_bam(dst)[2] == bodies
+    # a file cut in the middle of a record is an error, not a short read
+    raw = src.read_bytes()
+    cut = tmp_path / "cut.bam"
+    cut.write_bytes(raw[:len(raw) // 2])
+    assert lib.hm_bam_copy(str(cut).encode(), str(dst).encode(), 2, 1) < 0
+
+
 def test_bam_copy_rejects_garbage(lib_built, tmp_path):
     bad = tmp_path / "bad.bam"
     bad.write_bytes(b"this is not a BAM file at all" * 10)

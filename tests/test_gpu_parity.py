@@ -253,9 +253,12 @@ def test_call_cli_end_to_end(lib_built, models, tmp_path):
     src, dst = tmp_path / "in.bam", tmp_path / "mod.bam"
     synth.write_bam(src, bodies)
     exe = hme.PKG / "bin" / "hifimeth-b200"
-    # small batches (-b 4, 8 kb of bases) force several batches, a batch cut by bases, and the two-slot pipeline
-    r = subprocess.run([str(exe), "call", "-b", "4", "--max-bases", "8192", "-t", "3", str(src), str(dst)], capture_output=True, text=True, timeout=300)
+    # small batches (-b 4, 8 kb of bases) force several batches, a batch cut by bases, and the two-slot pipeline; two workers on
+    # the same device finish batches out of order, the writer must restore the input order
+    r = subprocess.run([str(exe), "call", "-b", "4", "--max-bases", "8192", "-t", "3", "--devices", "0,0", str(src), str(dst)],
+                       capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
+    assert "on 2 worker(s)" in r.stderr
     text, _, got = synth.read_bam(dst)
     assert "@PG\tID:hifimeth\tPN:hifimeth\tVN:1.1.0\tCL:" in text and text.startswith("@HD")
     assert len(got) == len(bodies)
