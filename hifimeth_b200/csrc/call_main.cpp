@@ -261,6 +261,10 @@ struct Shared {
     std::atomic<uint64_t> n_reads{0}, n_bases{0}, n_batches{0};
     // phase clocks, seconds summed over threads (report only)
     std::atomic<uint64_t> us_read{0}, us_create{0}, us_pack{0}, us_submit{0}, us_collect{0}, us_assemble{0}, us_write{0};
+    // timeline, microseconds since start: last engine ready, input exhausted, last batch collected, engines destroyed
+    std::chrono::steady_clock::time_point t_start = std::chrono::steady_clock::now();
+    std::atomic<uint64_t> at_ready{0}, at_input_done{0}, at_last_collect{0}, at_destroyed{0};
+    uint64_t since_start() const { return (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_start).count(); }
     explicit Shared(const Options& o, size_t depth) : opt(o), raw(depth) { for (auto& v : n_sites) v = 0; }
     void fail(const std::string& msg)
     {
@@ -321,6 +325,7 @@ void reader_thread(Shared& S, hm::BamReader& in)
         S.n_bases += l;
     }
     flush();
+    S.at_input_done = S.since_start();
     S.raw.close();
 }
 
@@ -342,6 +347,7 @@ void gpu_worker(Shared& S, int device, int threads)
     hm_engine* eng = nullptr;
     if (hm_engine_create(&cfg, &eng) != HM_OK) { S.fail(std::string("device ") + std::to_string(device) + ": " + hm_last_error(nullptr)); return; }
     S.us_create += sw.lap_us();
+    S.at_ready = S.since_start();
 
     struct InFlight {
         RawBatch raw;
@@ -355,6 +361,7 @@ void gpu_worker(Shared& S, int device, int threads)
         hm_call_batch calls{};
         if (hm_batch_collect(eng, slot, &calls) != HM_OK) { S.fail(hm_last_error(eng)); return false; }
         S.us_collect += w.lap_us();
+        S.at_last_collect = S.since_start();
         for (int c = 0; c < 3; ++c) S.n_sites[c] += calls.n_sites[c];
         const size_t n = f.raw.entries.size();
         OutBatch ob;
@@ -434,6 +441,7 @@ void gpu_worker(Shared& S, int device, int threads)
     for (int k = 0; k < 2 && ok && !S.failed; ++k)
         if (fl[cur ^ k].live) ok = finish(cur ^ k);
     hm_engine_destroy(eng);
+    S.at_destroyed = S.since_start();
 }
 
 void writer_thread(Shared& S, hm::BamWriter& out)
@@ -500,6 +508,9 @@ extern "C" int hm_call_main(int argc, char** argv)
                     "collect(wait) %.2f, assemble %.2f, write+deflate %.2f; %llu batches of <= %lld bases on %d worker(s), %d host threads\n",
             S.us_read / 1e6, S.us_create / 1e6, S.us_pack / 1e6, S.us_submit / 1e6, S.us_collect / 1e6, S.us_assemble / 1e6, S.us_write / 1e6,
             (unsigned long long)S.n_batches.load(), opt.max_bases, n_workers, opt.threads);
+    fprintf(stderr, "[hifimeth-b200] timeline (s since start): engines ready %.2f, input inflated %.2f, last batch collected %.2f, engines "
+                    "destroyed %.2f, output closed %.2f\n",
+            S.at_ready / 1e6, S.at_input_done / 1e6, S.at_last_collect / 1e6, S.at_destroyed / 1e6, secs);
     fprintf(stderr, "[hifimeth-b200] %llu reads, %llu bases, CpG %llu, CHG %llu, CHH %llu samples in %.2f s (%.3g sites/s, %.3g reads/s)\n",
             (unsigned long long)S.n_reads.load(), (unsigned long long)S.n_bases.load(), (unsigned long long)S.n_sites[0].load(),
             (unsigned long long)S.n_sites[1].load(), (unsigned long long)S.n_sites[2].load(), secs, sites / secs, S.n_reads.load() / secs);

@@ -51,6 +51,7 @@ struct Slot {
     uint8_t* d_bcode = nullptr;
     ushort4* d_kinf = nullptr;
     hm::ClassCount *d_chunk_cnt = nullptr, *d_pref = nullptr;
+    uint64_t* d_cls = nullptr;  // site classes of every position, 4 bits each (decode_kernel -> scan_write_kernel)
     uint32_t* d_totals = nullptr;
     uint32_t *d_site_read = nullptr, *d_site_pos = nullptr, *d_site_out = nullptr;
     // device outputs
@@ -199,7 +200,7 @@ void free_slot(Slot& s)
     cudaFree(s.d_mm_text); cudaFreeHost(s.h_mm_off); cudaFreeHost(s.h_mm_fwd_len); cudaFreeHost(s.h_mm_total); cudaFreeHost(s.h_mm_text);
     cudaFreeHost(s.h_call_off); cudaFreeHost(s.h_n_fwd); cudaFreeHost(s.h_totals); cudaFreeHost(s.h_qoff); cudaFreeHost(s.h_ml);
     void* dev[] = {s.d_seq4, s.d_fi, s.d_fp, s.d_ri, s.d_rp, s.d_valid, s.d_base_off, s.d_seq_off, s.d_flag, s.d_chunk_read,
-                   s.d_chunk_pos, s.d_read_first_chunk, s.d_bcode, s.d_kinf, s.d_chunk_cnt, s.d_pref, s.d_totals, s.d_site_read,
+                   s.d_chunk_pos, s.d_read_first_chunk, s.d_bcode, s.d_kinf, s.d_chunk_cnt, s.d_cls, s.d_pref, s.d_totals, s.d_site_read,
                    s.d_site_pos, s.d_site_out, s.d_call_off, s.d_n_fwd, s.d_qoff, s.d_ml, s.d_call_ctx, s.d_logits, s.d_feat};
     for (void* p : dev) cudaFree(p);
     for (float* p : s.d_act) cudaFree(p);
@@ -254,6 +255,7 @@ int alloc_slot(hm_engine* e, Slot& s)
     HM_CUDA(e, st, dmalloc(&s.d_bcode, B));
     HM_CUDA(e, st, dmalloc(&s.d_kinf, B));
     HM_CUDA(e, st, dmalloc(&s.d_chunk_cnt, s.max_chunks));
+    HM_CUDA(e, st, dmalloc(&s.d_cls, (size_t)s.max_chunks * hm::kFrontThreads));
     HM_CUDA(e, st, dmalloc(&s.d_pref, s.max_chunks + 1));
     HM_CUDA(e, st, dmalloc(&s.d_totals, 8));
     HM_CUDA(e, st, dmalloc(&s.d_site_read, B));
@@ -355,22 +357,18 @@ int stage_front(hm_engine* e, Slot& s, uint32_t& launches)
     const uint32_t nc = s.n_chunks;
     if (nc) {
         hm::decode_kernel<<<nc, hm::kFrontThreads, 0, s.stream>>>(s.d_seq4, s.d_fi, s.d_fp, s.d_ri, s.d_rp, s.d_base_off, s.d_seq_off, s.d_flag,
-                                                     s.d_chunk_read, s.d_chunk_pos, s.d_bcode, s.d_kinf);
+                                                                 s.d_valid, s.d_chunk_read, s.d_chunk_pos, e->ctx_mask, s.d_bcode, s.d_kinf,
+                                                                 s.d_chunk_cnt, s.d_cls);
         ++launches;
     }
     HM_CUDA(e, "decode", cudaGetLastError());
     HM_CUDA(e, "decode", cudaEventRecord(s.ev[2], s.stream));
+    hm::scan_offsets_kernel<<<1, 1024, 0, s.stream>>>(s.d_chunk_cnt, nc, s.d_read_first_chunk, s.n_reads, s.d_pref, s.d_totals, s.d_call_off,
+                                                      s.d_n_fwd, s.d_read_pref);
+    ++launches;
     if (nc) {
-        hm::scan_count_kernel<<<nc, hm::kFrontThreads, 0, s.stream>>>(s.d_bcode, s.d_base_off, s.d_valid, s.d_chunk_read, s.d_chunk_pos, e->ctx_mask, s.d_chunk_cnt);
-        ++launches;
-    }
-    hm::scan_offsets_kernel<<<1, 1024, 0, s.stream>>>(s.d_chunk_cnt, nc, s.d_pref, s.d_totals);
-    hm::read_offsets_kernel<<<(s.n_reads + 256) / 256, 256, 0, s.stream>>>(s.d_pref, s.d_read_first_chunk, s.n_reads, s.d_call_off, s.d_n_fwd, s.d_read_pref);
-    launches += 2;
-    if (nc) {
-        hm::scan_write_kernel<<<nc, hm::kFrontThreads, 0, s.stream>>>(s.d_bcode, s.d_base_off, s.d_valid, s.d_chunk_read, s.d_chunk_pos,
-                                                               s.d_read_first_chunk, s.d_pref, nc, e->ctx_mask, s.d_qoff, s.d_call_ctx,
-                                                               s.d_site_read, s.d_site_pos, s.d_site_out);
+        hm::scan_write_kernel<<<nc, hm::kFrontThreads, 0, s.stream>>>(s.d_cls, s.d_chunk_read, s.d_chunk_pos, s.d_read_first_chunk, s.d_pref, nc,
+                                                                     s.d_qoff, s.d_call_ctx, s.d_site_read, s.d_site_pos, s.d_site_out);
         ++launches;
     }
     HM_CUDA(e, "scan", cudaGetLastError());
@@ -755,20 +753,20 @@ int hm_microbench(hm_engine* e, int slot, const char* name, uint32_t n_sites, in
     for (int it = -1; it < iters; ++it) {  // it = -1: warm-up
         if (it == 0) HM_CUDA(e, "microbench", cudaEventRecord(a, st));
         if (k == "decode") {
+            // decode_kernel also classifies the positions it has in shared memory (0.5 B/base of class nibbles, not counted)
             if (s.n_chunks)
                 hm::decode_kernel<<<s.n_chunks, hm::kFrontThreads, 0, st>>>(s.d_seq4, s.d_fi, s.d_fp, s.d_ri, s.d_rp, s.d_base_off, s.d_seq_off, s.d_flag,
-                                                              s.d_chunk_read, s.d_chunk_pos, s.d_bcode, s.d_kinf);
+                                                                         s.d_valid, s.d_chunk_read, s.d_chunk_pos, e->ctx_mask, s.d_bcode, s.d_kinf,
+                                                                         s.d_chunk_cnt, s.d_cls);
             bytes = 12.0 * s.n_bases;  // 4 code planes in, 4 x u16 frames out
         } else if (k == "scan") {
-            hm_timing keep = s.timing;
-            hm::scan_count_kernel<<<std::max(s.n_chunks, 1u), hm::kFrontThreads, 0, st>>>(s.d_bcode, s.d_base_off, s.d_valid, s.d_chunk_read, s.d_chunk_pos, e->ctx_mask, s.d_chunk_cnt);
-            hm::scan_offsets_kernel<<<1, 1024, 0, st>>>(s.d_chunk_cnt, s.n_chunks, s.d_pref, s.d_totals);
-            hm::read_offsets_kernel<<<(s.n_reads + 256) / 256, 256, 0, st>>>(s.d_pref, s.d_read_first_chunk, s.n_reads, s.d_call_off, s.d_n_fwd, s.d_read_pref);
-            hm::scan_write_kernel<<<std::max(s.n_chunks, 1u), hm::kFrontThreads, 0, st>>>(s.d_bcode, s.d_base_off, s.d_valid, s.d_chunk_read, s.d_chunk_pos,
-                                                                                  s.d_read_first_chunk, s.d_pref, s.n_chunks, e->ctx_mask, s.d_qoff,
-                                                                                  s.d_call_ctx, s.d_site_read, s.d_site_pos, s.d_site_out);
-            s.timing = keep;
-            bytes = 0.5 * s.n_bases + 5.0 * s.n_calls;
+            // the part of the site scan that is its own launches: prefix over chunks + site lists from the class nibbles
+            hm::scan_offsets_kernel<<<1, 1024, 0, st>>>(s.d_chunk_cnt, s.n_chunks, s.d_read_first_chunk, s.n_reads, s.d_pref, s.d_totals, s.d_call_off,
+                                                        s.d_n_fwd, s.d_read_pref);
+            if (s.n_chunks)
+                hm::scan_write_kernel<<<s.n_chunks, hm::kFrontThreads, 0, st>>>(s.d_cls, s.d_chunk_read, s.d_chunk_pos, s.d_read_first_chunk, s.d_pref,
+                                                                             s.n_chunks, s.d_qoff, s.d_call_ctx, s.d_site_read, s.d_site_pos, s.d_site_out);
+            bytes = 0.5 * s.n_bases + 5.0 * s.n_calls;  // SURVEY s8d; the lists the engine really writes are 17 B/site
         } else if (k == "gather") {
             if (ns) hm::gather_features_kernel<<<ns, 128, 0, st>>>(s.d_bcode, s.d_kinf, s.d_base_off, s.d_site_read, s.d_site_pos, 0, ns, d_tmp);
             bytes = 12832.0 * ns;

@@ -332,4 +332,177 @@ int hm_build_mod_record_mm(const uint8_t* body, size_t len, int keep_kinetics, c
     return HM_OK;
 }
 
+// ---- row N4: MM/ML parser (round-trip validator of the tags this engine writes) ------------------------------------------
+
+namespace {
+
+// Forward-strand base at forward offset i as a letter (BamQuerySequence::get_bam_fwd_strand_base, src/corelib/bam_info.cpp:
+// 224-232): the stored base, or under flag 0x10 the complement of the stored base at l_seq - 1 - i.  0 for an illegal nibble.
+char fwd_strand_base(const uint8_t* body, const RecLayout& r, int32_t i)
+{
+    const bool rev = (r.flag & 16) != 0;
+    const int32_t q = rev ? r.l_seq - 1 - i : i;
+    const uint32_t nib = (body[r.seq_off + ((size_t)q >> 1)] >> ((~q & 1) << 2)) & 0xfu;
+    switch (nib) {
+    case 1: return rev ? 'T' : 'A';
+    case 2: return rev ? 'G' : 'C';
+    case 4: return rev ? 'C' : 'G';
+    case 8: return rev ? 'A' : 'T';
+    case 15: return 'N';
+    default: return 0;
+    }
+}
+
+// s_chebi_to_iupac_code, src/corelib/bam_mod_parser.cpp:36-76
+char chebi_code(long c)
+{
+    switch (c) {
+    case 27551: return 'm'; case 76792: return 'h'; case 76794: return 'f'; case 76793: return 'c'; case 16964: return 'g';
+    case 80961: return 'e'; case 17477: return 'b'; case 28871: return 'a'; case 44605: return 'o'; case 18107: return 'n';
+    default: return 0;
+    }
+}
+
+// s_is_valid_unmod_base_and_code, src/corelib/bam_mod_parser.cpp:101-139
+bool code_fits_base(char base, char c)
+{
+    if (c == 'm' || c == 'h' || c == 'f' || c == 'c' || c == 'C') return base == 'C' || base == 'G';
+    if (c == 'g' || c == 'e' || c == 'b' || c == 'T') return base == 'T' || base == 'A';
+    if (c == 'U') return base == 'U';
+    if (c == 'a' || c == 'A') return base == 'A' || base == 'T';
+    if (c == 'o' || c == 'G') return base == 'G' || base == 'C';
+    if (c == 'n' || c == 'N') return base == 'N';
+    return true;
+}
+
+const uint8_t* find_tag(const uint8_t* body, size_t len, const RecLayout& r, char t0, char t1)
+{
+    size_t p = r.aux_off;
+    AuxField f;
+    while (p < len && next_aux(body, p, len, f)) {
+        if (body[p] == (uint8_t)t0 && body[p + 1] == (uint8_t)t1) return body + p + 2;  // at the type byte
+        p = f.end_off;
+    }
+    return nullptr;
+}
+
+}  // namespace
+
+int hm_parse_mod_record(const uint8_t* body, size_t len, int32_t* qoff, uint8_t* strand, uint8_t* prob, char* code, uint32_t cap,
+                        uint32_t* n_mods)
+{
+    if (!body || !n_mods) return HM_ERR_ARG;
+    *n_mods = 0;
+    RecLayout r;
+    if (!layout_of(body, len, r)) return HM_ERR_FORMAT;
+    // ML: any integer B array, every value in [0, 255] (s_extract_bam_mod_scaled_probs, bam_mod_parser.cpp:8-34)
+    const uint8_t* ml = find_tag(body, len, r, 'M', 'L');
+    if (!ml) return HM_OK;
+    if (ml[0] != 'B') return HM_ERR_FORMAT;
+    uint32_t n_probs;
+    memcpy(&n_probs, ml + 2, 4);
+    const char sub = (char)ml[1];
+    const size_t es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : (sub == 'i' || sub == 'I') ? 4 : 0;
+    if (!es) return HM_ERR_FORMAT;
+    auto prob_at = [&](uint32_t i, uint8_t& out) {
+        const uint8_t* p = ml + 6 + es * (size_t)i;
+        long long v;
+        switch (sub) {
+        case 'c': v = (int8_t)p[0]; break;
+        case 'C': v = p[0]; break;
+        case 's': { int16_t t; memcpy(&t, p, 2); v = t; break; }
+        case 'S': { uint16_t t; memcpy(&t, p, 2); v = t; break; }
+        case 'i': { int32_t t; memcpy(&t, p, 4); v = t; break; }
+        default: { uint32_t t; memcpy(&t, p, 4); v = t; break; }
+        }
+        if (v < 0 || v > 255) return false;
+        out = (uint8_t)v;
+        return true;
+    };
+    if (n_probs == 0) return HM_OK;
+    const uint8_t* mm = find_tag(body, len, r, 'M', 'M');
+    if (!mm) return HM_OK;
+    if (mm[0] != 'Z') return HM_ERR_FORMAT;
+    const char* s = reinterpret_cast<const char*>(mm + 1);
+    const size_t sl = strlen(s);
+    if (sl == 0 || s[sl - 1] != ';') return HM_ERR_FORMAT;  // "The MM aux tag must end with ';'"
+    uint32_t prob_idx = 0, n_out = 0;
+    size_t i = 0;
+    while (i < sl) {
+        size_t j = i + 1;
+        while (j < sl && s[j] != ';') ++j;
+        ++j;  // one past the ';' (the string ends with one)
+        // ---- one edit series s[i, j): base, strand, codes, skip counts (s_parse_one_mod_list, bam_mod_parser.cpp:141-229) ----
+        const char* e = s + i;
+        const size_t el = j - i;
+        if (el < 4) return HM_ERR_FORMAT;
+        const char base = e[0];
+        if (base != 'C' && base != 'G' && base != 'T' && base != 'A' && base != 'U' && base != 'N') return HM_ERR_FORMAT;
+        if (e[1] != '+' && e[1] != '-') return HM_ERR_FORMAT;
+        const uint8_t st = e[1] == '+' ? 0 : 1;  // FWD / REV, src/corelib/hbn_aux.hpp:60-63
+        char codes[16];
+        int n_code = 0;
+        size_t k = 2;
+        if (e[2] >= '0' && e[2] <= '9') {
+            long c = 0;
+            while (k < el && e[k] >= '0' && e[k] <= '9') { c = c * 10 + (e[k] - '0'); if (c > 100000000) return HM_ERR_FORMAT; ++k; }
+            const char cc = chebi_code(c);
+            if (!cc) return HM_ERR_FORMAT;
+            codes[n_code++] = cc;
+        } else {
+            for (; k < el; ++k) {
+                if (e[k] == ',' || e[k] == ';') break;
+                if (e[k] != '.' && e[k] != '?') {
+                    if (n_code == 16) return HM_ERR_FORMAT;
+                    codes[n_code++] = e[k];
+                }
+            }
+        }
+        for (int c = 0; c < n_code; ++c)
+            if (!code_fits_base(base, codes[c])) return HM_ERR_FORMAT;
+        if (k >= el || (e[k] != ',' && e[k] != ';')) return HM_ERR_FORMAT;
+        ++k;
+        int32_t q = 0;
+        while (k < el) {
+            if (e[k] < '0' || e[k] > '9') return HM_ERR_FORMAT;
+            long long d = 0;
+            while (k < el && e[k] != ',' && e[k] != ';') {
+                if (e[k] < '0' || e[k] > '9') return HM_ERR_FORMAT;
+                d = d * 10 + (e[k] - '0');
+                if (d > 0x7fffffff) return HM_ERR_FORMAT;
+                ++k;
+            }
+            ++k;
+            // skip d occurrences of the unmodified base, then land on the next one
+            long long cnt = 0;
+            while (cnt < d) {
+                if (q >= r.l_seq) return HM_ERR_FORMAT;
+                if (fwd_strand_base(body, r, q) == base) ++cnt;
+                ++q;
+            }
+            for (;;) {
+                if (q >= r.l_seq) return HM_ERR_FORMAT;
+                if (fwd_strand_base(body, r, q) == base) break;
+                ++q;
+            }
+            for (int c = 0; c < n_code; ++c) {
+                if (prob_idx >= n_probs) return HM_ERR_FORMAT;
+                uint8_t pv;
+                if (!prob_at(prob_idx++, pv)) return HM_ERR_FORMAT;
+                if (n_out < cap) {
+                    if (qoff) qoff[n_out] = q;
+                    if (strand) strand[n_out] = st;
+                    if (prob) prob[n_out] = pv;
+                    if (code) code[n_out] = codes[c];
+                }
+                ++n_out;
+            }
+            ++q;
+        }
+        i = j;
+    }
+    *n_mods = n_out;
+    return HM_OK;
+}
+
 }  // extern "C"

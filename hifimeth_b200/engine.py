@@ -56,7 +56,7 @@ class hm_timing(C.Structure):
 
 ABI_SYMBOLS = ["hm_engine_create", "hm_engine_destroy", "hm_last_error", "hm_version", "hm_batch_acquire", "hm_batch_submit",
                "hm_batch_collect", "hm_batch_timing", "hm_codev1_encode", "hm_codev1_decode", "hm_pack_record", "hm_pack_records",
-               "hm_mod_record_bound", "hm_build_mod_record", "hm_build_mod_record_mm", "hm_call_main", "hm_bam_copy", "hm_debug_dump_decode", "hm_debug_dump_ctx",
+               "hm_mod_record_bound", "hm_build_mod_record", "hm_build_mod_record_mm", "hm_parse_mod_record", "hm_call_main", "hm_bam_copy", "hm_debug_dump_decode", "hm_debug_dump_ctx",
                "hm_debug_dump_features", "hm_debug_dump_logits", "hm_debug_dense_op", "hm_debug_last_op_ms", "hm_microbench"]
 
 _lib = None
@@ -91,6 +91,7 @@ def load_library() -> C.CDLL:
                                       C.POINTER(C.c_size_t)]
     L.hm_build_mod_record_mm.argtypes = [_u8p, C.c_size_t, C.c_int, _u8p, C.c_uint32, _u8p, C.c_uint32, _u8p, C.c_uint32, C.c_uint32, _u8p,
                                          C.POINTER(C.c_size_t)]
+    L.hm_parse_mod_record.argtypes = [_u8p, C.c_size_t, _i32p, _u8p, _u8p, C.c_char_p, C.c_uint32, _u32p]
     L.hm_pack_records.argtypes = [C.POINTER(hm_read_batch), C.c_uint32, C.POINTER(_u8p), C.POINTER(C.c_size_t), C.c_int32, C.c_int,
                                   _i32p, _u32p]
     L.hm_call_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
@@ -275,6 +276,23 @@ def build_mod_record(body: bytes, keep_kinetics: bool, fwd_qoff, fwd_ml, rev_qof
     if rc != 0:
         raise HmError(f"hm_build_mod_record failed ({rc})")
     return out[:n.value].tobytes()
+
+
+def parse_mod_record(body: bytes):
+    """hm_parse_mod_record: (qoff i32[], strand u8[], prob u8[], codes bytes) of a record's MM/ML tags."""
+    L = load_library()
+    src = np.frombuffer(body, np.uint8)
+    n = C.c_uint32(0)
+    rc = L.hm_parse_mod_record(src.ctypes.data_as(_u8p), len(body), None, None, None, None, 0, C.byref(n))
+    if rc != 0:
+        raise HmError(f"hm_parse_mod_record failed ({rc})")
+    q, s, p = np.zeros(n.value, np.int32), np.zeros(n.value, np.uint8), np.zeros(n.value, np.uint8)
+    codes = C.create_string_buffer(max(n.value, 1))
+    rc = L.hm_parse_mod_record(src.ctypes.data_as(_u8p), len(body), q.ctypes.data_as(_i32p), s.ctypes.data_as(_u8p), p.ctypes.data_as(_u8p),
+                               codes, n.value, C.byref(n))
+    if rc != 0:
+        raise HmError(f"hm_parse_mod_record failed ({rc})")
+    return q, s, p, codes.raw[:n.value]
 
 
 def pack_records_host(bodies, min_read_len: int = 1000, max_bases: int = None, threads: int = 0):

@@ -164,6 +164,15 @@ int hm_build_mod_record_mm(const uint8_t* body, size_t len, int keep_kinetics, c
                            const uint8_t* mm_rev, uint32_t mm_rev_len, const uint8_t* ml, uint32_t n_fwd, uint32_t n_rev,
                            uint8_t* out, size_t* out_len);
 
+/* extract_bam_base_mods, src/corelib/bam_mod_parser.cpp:231-286, on a record body (round-trip validator
+ * of the tags above): parses ML (any integer B array, values 0..255) and MM:Z (edit series "<base><+|-><codes|ChEBI>,d,d,...;")
+ * and returns one entry per (position, code) in tag order -- qoff in forward-strand coordinates, strand 0 for '+' / 1 for '-',
+ * the scaled probability and the code letter.  Arrays may be NULL; at most `cap` entries are written, *n_mods is the full
+ * count.  Where the reference aborts (malformed series, skip counts running past the read, too few ML values) this returns
+ * HM_ERR_FORMAT. */
+int hm_parse_mod_record(const uint8_t* body, size_t len, int32_t* qoff, uint8_t* strand, uint8_t* prob, char* code, uint32_t cap,
+                        uint32_t* n_mods);
+
 /* ---- the `call` driver and its BAM codec ------------------------------------------------------- */
 
 /* `hifimeth call [-m dir] [-l 1000] [-s 32] [-b 10000] [-k] [-c cpg,chg,chh] [-t N] in.bam out.bam` on this engine
