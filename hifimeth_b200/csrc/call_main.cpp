@@ -13,7 +13,7 @@
 // path: no collective, weights replicated per engine, batches carry a sequence number and the writer restores
 // input order (the reference sorts by read id, mod_main.cpp:353-354).
 // Options follow src/app/hifimeth/mod_options.cpp:61-181: -m -l -s -b -k -c -t -v -h; -s is accepted and ignored (the site
-// batch is an OpenVINO notion).  Extensions: --devices LIST, --max-bases N, --level N.
+// batch is an OpenVINO notion).  Extensions: --devices LIST, --max-bases N, --level N, --hist FILE.
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -38,7 +38,7 @@
 namespace {
 
 struct Options {
-    std::string model_dir, in_path, out_path;
+    std::string model_dir, in_path, out_path, hist_path;
     int min_read_len = 1000, site_batch = 32, reads_per_batch = 10000, keep_kinetics = 0, threads = 0, ctx_mask = 7;
     int level = 6;
     std::vector<int> devices;   // one worker (engine) per entry; an ordinal may repeat
@@ -71,7 +71,8 @@ void usage(const char* prog, const char* cmd)
                     "  -t <Integer>  Number of CPU threads used for BAM inflate/deflate and record assembly\n"
                     "  --devices <list>  CUDA devices, comma separated; batches are dealt to one worker per entry. Default = 0\n"
                     "  --max-bases <Integer>  Bases per batch. Default: from the input size, 2 Mi .. 24 Mi\n"
-                    "  --level <Integer>  BGZF compression level. Default = 6\n",
+                    "  --level <Integer>  BGZF compression level. Default = 6\n"
+                    "  --hist <File>  Write the per-context histograms of the ML bytes (the input of pileup's threshold rule) as TSV\n",
             default_model_dir().c_str());
 }
 
@@ -132,6 +133,7 @@ int parse(int argc, char** argv, Options& o)
         if (a == "-t") { if (!val(v) || v < 1) return -1; o.threads = (int)v; continue; }
         if (a == "--device") { if (!val(v) || v < 0) return -1; o.devices.assign(1, (int)v); continue; }
         if (a == "--devices") { if (i + 1 >= argc || !parse_devices(argv[++i], o.devices)) return -1; continue; }
+        if (a == "--hist") { if (i + 1 >= argc) return -1; o.hist_path = argv[++i]; continue; }
         if (a == "--level") { if (!val(v) || v < 0 || v > 9) return -1; o.level = (int)v; continue; }
         if (a == "--max-bases") { if (!val(v) || v < 1024 || v >= 0x7fffffffll) return -1; o.max_bases = v; continue; }
         if (a.size() > 1 && a[0] == '-') { fprintf(stderr, "unrecognised option '%s'\n", a.c_str()); return -1; }
@@ -259,6 +261,8 @@ struct Shared {
     std::string err;
     std::atomic<uint64_t> n_sites[3];
     std::atomic<uint64_t> n_reads{0}, n_bases{0}, n_batches{0};
+    std::mutex hist_m;
+    uint64_t ml_hist[3][256] = {};  // row N3: ML histograms per context over the whole run
     // phase clocks, seconds summed over threads (report only)
     std::atomic<uint64_t> us_read{0}, us_create{0}, us_pack{0}, us_submit{0}, us_collect{0}, us_assemble{0}, us_write{0};
     // timeline, microseconds since start: last engine ready, input exhausted, last batch collected, engines destroyed
@@ -363,6 +367,11 @@ void gpu_worker(Shared& S, int device, int threads)
         S.us_collect += w.lap_us();
         S.at_last_collect = S.since_start();
         for (int c = 0; c < 3; ++c) S.n_sites[c] += calls.n_sites[c];
+        if (calls.ml_hist) {
+            std::lock_guard<std::mutex> lk(S.hist_m);
+            for (int c = 0; c < 3; ++c)
+                for (int b = 0; b < 256; ++b) S.ml_hist[c][b] += calls.ml_hist[c * 256 + b];
+        }
         const size_t n = f.raw.entries.size();
         OutBatch ob;
         ob.seq = f.raw.seq;
@@ -430,7 +439,7 @@ void gpu_worker(Shared& S, int device, int threads)
             break;
         }
         S.us_pack += sw.lap_us();
-        if (hm_batch_submit(eng, cur, n_packed, HM_SUBMIT_MM_TEXT) != HM_OK) { S.fail(hm_last_error(eng)); ok = false; break; }
+        if (hm_batch_submit(eng, cur, n_packed, HM_SUBMIT_MM_TEXT | HM_SUBMIT_ML_HIST) != HM_OK) { S.fail(hm_last_error(eng)); ok = false; break; }
         S.us_submit += sw.lap_us();
         f.raw = std::move(rb);
         f.live = true;
@@ -514,6 +523,23 @@ extern "C" int hm_call_main(int argc, char** argv)
     fprintf(stderr, "[hifimeth-b200] %llu reads, %llu bases, CpG %llu, CHG %llu, CHH %llu samples in %.2f s (%.3g sites/s, %.3g reads/s)\n",
             (unsigned long long)S.n_reads.load(), (unsigned long long)S.n_bases.load(), (unsigned long long)S.n_sites[0].load(),
             (unsigned long long)S.n_sites[1].load(), (unsigned long long)S.n_sites[2].load(), secs, sites / secs, S.n_reads.load() / secs);
+    // Row N3: the scaled-probability thresholds `hifimeth pileup` would infer from this output (pileup.cpp:355-436), from the
+    // histograms the device kept while the ML bytes were resident; --hist FILE also writes the bins.
+    static const char* ctx_name[3] = {"CpG", "CHG", "CHH"};
+    for (int c = 0; c < 3; ++c) {
+        if (!(opt.ctx_mask & (1 << c))) continue;
+        uint64_t n = 0;
+        const unsigned t = hm_ml_threshold(S.ml_hist[c], &n);
+        fprintf(stderr, "[hifimeth-b200] %s scaled probability threshold (pileup rule): %u (%llu samples in range)\n", ctx_name[c], t, (unsigned long long)n);
+    }
+    if (!opt.hist_path.empty()) {
+        FILE* hf = fopen(opt.hist_path.c_str(), "w");
+        if (!hf) { fprintf(stderr, "[hifimeth-b200] cannot create %s\n", opt.hist_path.c_str()); return EXIT_FAILURE; }
+        fprintf(hf, "scaled_prob\tCpG\tCHG\tCHH\n");
+        for (int b = 0; b < 256; ++b)
+            fprintf(hf, "%d\t%llu\t%llu\t%llu\n", b, (unsigned long long)S.ml_hist[0][b], (unsigned long long)S.ml_hist[1][b], (unsigned long long)S.ml_hist[2][b]);
+        fclose(hf);
+    }
     return EXIT_SUCCESS;
 }
 

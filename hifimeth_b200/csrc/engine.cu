@@ -70,6 +70,8 @@ struct Slot {
     uint8_t* h_mm_text = nullptr;
     size_t mm_text_cap = 0;
     bool mm_valid = false;
+    uint32_t *d_ml_hist = nullptr, *h_ml_hist = nullptr;  // [3][256]
+    bool hist_valid = false;
     // fp32 CNN workspace (site chunk)
     float* d_feat = nullptr;
     float* d_act[8] = {};
@@ -197,6 +199,7 @@ void free_slot(Slot& s)
     cudaFreeHost(s.h_chunk_read); cudaFreeHost(s.h_chunk_pos); cudaFreeHost(s.h_read_first_chunk);
     cudaFreeHost(s.h_read_pref); cudaFree(s.d_read_pref);
     cudaFree(s.d_mm_delta); cudaFree(s.d_mm_bsum); cudaFree(s.d_mm_boff); cudaFree(s.d_mm_toff); cudaFree(s.d_mm_off); cudaFree(s.d_mm_fwd_len);
+    cudaFree(s.d_ml_hist); cudaFreeHost(s.h_ml_hist);
     cudaFree(s.d_mm_text); cudaFreeHost(s.h_mm_off); cudaFreeHost(s.h_mm_fwd_len); cudaFreeHost(s.h_mm_total); cudaFreeHost(s.h_mm_text);
     cudaFreeHost(s.h_call_off); cudaFreeHost(s.h_n_fwd); cudaFreeHost(s.h_totals); cudaFreeHost(s.h_qoff); cudaFreeHost(s.h_ml);
     void* dev[] = {s.d_seq4, s.d_fi, s.d_fp, s.d_ri, s.d_rp, s.d_valid, s.d_base_off, s.d_seq_off, s.d_flag, s.d_chunk_read,
@@ -278,6 +281,8 @@ int alloc_slot(hm_engine* e, Slot& s)
     HM_CUDA(e, st, hmalloc(&s.h_mm_off, R + 1));
     HM_CUDA(e, st, hmalloc(&s.h_mm_fwd_len, R));
     HM_CUDA(e, st, hmalloc(&s.h_mm_total, 1));
+    HM_CUDA(e, st, dmalloc(&s.d_ml_hist, 3 * 256));
+    HM_CUDA(e, st, hmalloc(&s.h_ml_hist, 3 * 256));
     HM_CUDA(e, st, hmalloc(&s.h_mm_text, s.mm_text_cap));
     if (e->cfg.cnn_mode == HM_CNN_FP32_SIMT) {
         const size_t S = e->site_chunk;
@@ -576,6 +581,18 @@ int hm_batch_submit(hm_engine* e, int slot, uint32_t n_reads, uint32_t flags)
         HM_CUDA(e, "MM text", cudaEventRecord(s.ev[6], st));
     }
     if ((rc = stage_cnn(e, s, launches))) return rc;
+    s.hist_valid = false;
+    const bool want_hist = (flags & HM_SUBMIT_ML_HIST) != 0;
+    if (want_hist) {
+        // row N3: per-context histograms of the ML bytes while they are on the device
+        HM_CUDA(e, "ML histogram", cudaMemsetAsync(s.d_ml_hist, 0, 3 * 256 * sizeof(uint32_t), st));
+        if (s.n_calls) {
+            const uint32_t nb = std::min<uint32_t>((s.n_calls + 255u) / 256u, (uint32_t)e->sm_count * 8u);
+            hm::ml_hist_kernel<<<nb, 256, 0, st>>>(s.d_site_read, s.d_site_out, s.d_ml, s.d_flag, s.d_totals, s.n_calls, s.d_ml_hist);
+            ++launches;
+            HM_CUDA(e, "ML histogram", cudaGetLastError());
+        }
+    }
     HM_CUDA(e, "CNN", cudaEventRecord(s.ev[4], st));
     if (!(flags & HM_SUBMIT_SKIP_D2H)) {
         const char* stg = "D2H";
@@ -592,6 +609,10 @@ int hm_batch_submit(hm_engine* e, int slot, uint32_t n_reads, uint32_t flags)
             HM_CUDA(e, stg, cp(s.h_mm_off, s.d_mm_off, (s.n_reads + 1) * sizeof(uint32_t)));
             HM_CUDA(e, stg, cp(s.h_mm_fwd_len, s.d_mm_fwd_len, s.n_reads * sizeof(uint32_t)));
             s.mm_valid = true;
+        }
+        if (want_hist) {
+            HM_CUDA(e, stg, cp(s.h_ml_hist, s.d_ml_hist, 3 * 256 * sizeof(uint32_t)));
+            s.hist_valid = true;
         }
         s.timing.d2h_bytes = bytes + 5 * sizeof(uint32_t);
     }
@@ -630,6 +651,7 @@ int hm_batch_collect(hm_engine* e, int slot, hm_call_batch* out)
     out->mm_text = s.mm_valid ? s.h_mm_text : nullptr;
     out->mm_off = s.mm_valid ? s.h_mm_off : nullptr;
     out->mm_fwd_len = s.mm_valid ? s.h_mm_fwd_len : nullptr;
+    out->ml_hist = s.hist_valid ? s.h_ml_hist : nullptr;
     s.collected = true;
     return HM_OK;
 }

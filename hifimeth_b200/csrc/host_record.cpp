@@ -505,4 +505,22 @@ int hm_parse_mod_record(const uint8_t* body, size_t len, int32_t* qoff, uint8_t*
     return HM_OK;
 }
 
+uint8_t hm_ml_threshold(const uint64_t bins[256], uint64_t* n_samples)
+{
+    if (n_samples) *n_samples = 0;
+    if (!bins) return 128;
+    int st = 20, en = 256 - 20;
+    while (st < 256 && bins[st] < 10) ++st;
+    while (en && bins[en - 1] < 10) --en;
+    uint64_t sum = 0, min_cnt = ~(uint64_t)0;
+    int min_i = -1;
+    if (en - st >= 50)
+        for (int i = st; i < en; ++i) {
+            sum += bins[i];
+            if (min_cnt > bins[i]) { min_cnt = bins[i]; min_i = i; }  // first of equal minima, as the reference's strict '>'
+        }
+    if (n_samples) *n_samples = sum;
+    return (sum < 10000 || min_i == -1) ? (uint8_t)128 : (uint8_t)min_i;
+}
+
 }  // extern "C"

@@ -19,7 +19,7 @@ DEFAULT_MODEL_DIR = PKG.parent / "models"
 
 HM_CTX_CPG, HM_CTX_CHG, HM_CTX_CHH = 1, 2, 4
 HM_CNN_TENSOR, HM_CNN_FP32_SIMT = 0, 1
-HM_SUBMIT_SKIP_H2D, HM_SUBMIT_SKIP_D2H, HM_SUBMIT_MM_TEXT = 1, 2, 4
+HM_SUBMIT_SKIP_H2D, HM_SUBMIT_SKIP_D2H, HM_SUBMIT_MM_TEXT, HM_SUBMIT_ML_HIST = 1, 2, 4, 8
 
 _u8p = C.POINTER(C.c_uint8)
 _u16p = C.POINTER(C.c_uint16)
@@ -45,7 +45,7 @@ class hm_read_batch(C.Structure):
 
 class hm_call_batch(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_calls", C.c_uint32), ("call_off", _u32p), ("n_fwd", _u32p), ("qoff", _i32p),
-                ("ml", _u8p), ("n_sites", C.c_uint64 * 3), ("mm_text", _u8p), ("mm_off", _u32p), ("mm_fwd_len", _u32p)]
+                ("ml", _u8p), ("n_sites", C.c_uint64 * 3), ("mm_text", _u8p), ("mm_off", _u32p), ("mm_fwd_len", _u32p), ("ml_hist", _u32p)]
 
 
 class hm_timing(C.Structure):
@@ -56,7 +56,7 @@ class hm_timing(C.Structure):
 
 ABI_SYMBOLS = ["hm_engine_create", "hm_engine_destroy", "hm_last_error", "hm_version", "hm_batch_acquire", "hm_batch_submit",
                "hm_batch_collect", "hm_batch_timing", "hm_codev1_encode", "hm_codev1_decode", "hm_pack_record", "hm_pack_records",
-               "hm_mod_record_bound", "hm_build_mod_record", "hm_build_mod_record_mm", "hm_parse_mod_record", "hm_call_main", "hm_bam_copy", "hm_debug_dump_decode", "hm_debug_dump_ctx",
+               "hm_mod_record_bound", "hm_build_mod_record", "hm_build_mod_record_mm", "hm_parse_mod_record", "hm_ml_threshold", "hm_call_main", "hm_bam_copy", "hm_debug_dump_decode", "hm_debug_dump_ctx",
                "hm_debug_dump_features", "hm_debug_dump_logits", "hm_debug_dense_op", "hm_debug_last_op_ms", "hm_microbench"]
 
 _lib = None
@@ -91,6 +91,8 @@ def load_library() -> C.CDLL:
                                       C.POINTER(C.c_size_t)]
     L.hm_build_mod_record_mm.argtypes = [_u8p, C.c_size_t, C.c_int, _u8p, C.c_uint32, _u8p, C.c_uint32, _u8p, C.c_uint32, C.c_uint32, _u8p,
                                          C.POINTER(C.c_size_t)]
+    L.hm_ml_threshold.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.hm_ml_threshold.restype = C.c_uint8
     L.hm_parse_mod_record.argtypes = [_u8p, C.c_size_t, _i32p, _u8p, _u8p, C.c_char_p, C.c_uint32, _u32p]
     L.hm_pack_records.argtypes = [C.POINTER(hm_read_batch), C.c_uint32, C.POINTER(_u8p), C.POINTER(C.c_size_t), C.c_int32, C.c_int,
                                   _i32p, _u32p]
@@ -127,6 +129,7 @@ class CallBatch:
     mm_text: np.ndarray = None     # HM_SUBMIT_MM_TEXT: device-built MM skip-count text
     mm_off: np.ndarray = None
     mm_fwd_len: np.ndarray = None
+    ml_hist: np.ndarray = None     # HM_SUBMIT_ML_HIST: [3, 256] ML histograms per context (CpG, CHG, CHH)
 
     def read_mm(self, r: int):
         """(fwd text, rev text) of read r: the ",d,d,..." runs that follow "C+m" and "G-m" in its MM tag."""
@@ -215,6 +218,8 @@ class Engine:
             out.mm_off = f(_view(c.mm_off, c.n_reads + 1, np.uint32))
             out.mm_fwd_len = f(_view(c.mm_fwd_len, c.n_reads, np.uint32))
             out.mm_text = f(_view(c.mm_text, int(out.mm_off[-1]), np.uint8))
+        if c.ml_hist:
+            out.ml_hist = f(_view(c.ml_hist, 3 * 256, np.uint32)).reshape(3, 256)
         return out
 
     def timing(self, slot: int) -> hm_timing:
@@ -276,6 +281,16 @@ def build_mod_record(body: bytes, keep_kinetics: bool, fwd_qoff, fwd_ml, rev_qof
     if rc != 0:
         raise HmError(f"hm_build_mod_record failed ({rc})")
     return out[:n.value].tobytes()
+
+
+def ml_threshold(bins):
+    """hm_ml_threshold: (threshold, samples in range) for one context's 256-bin ML histogram."""
+    L = load_library()
+    b = np.ascontiguousarray(bins, np.uint64)
+    assert b.shape == (256,)
+    n = C.c_uint64(0)
+    t = L.hm_ml_threshold(b.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(n))
+    return int(t), int(n.value)
 
 
 def parse_mod_record(body: bytes):

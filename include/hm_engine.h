@@ -104,6 +104,9 @@ typedef struct hm_call_batch {
     const uint8_t* mm_text;
     const uint32_t* mm_off;     /* [n_reads+1] */
     const uint32_t* mm_fwd_len; /* [n_reads] */
+    /* HM_SUBMIT_ML_HIST only (else NULL): [3][256] histogram of this batch's ML bytes per context (CpG, CHG, CHH) over reads
+     * without flag 0x900 -- what `hifimeth pileup` accumulates to infer its thresholds (src/app/hifimeth/pileup.cpp:237-272). */
+    const uint32_t* ml_hist;
 } hm_call_batch;
 
 /* Device-side timing of the last submit of a slot (CUDA events on the slot's stream). */
@@ -118,6 +121,7 @@ typedef struct hm_timing {
 #define HM_SUBMIT_SKIP_H2D 1u   /* inputs of this slot are already resident in HBM (re-run) */
 #define HM_SUBMIT_SKIP_D2H 2u   /* leave results on the device (kernel-only timing) */
 #define HM_SUBMIT_MM_TEXT 4u    /* also build the MM skip-count text on the device (hm_call_batch.mm_*) */
+#define HM_SUBMIT_ML_HIST 8u    /* also histogram the ML bytes per context on the device (hm_call_batch.ml_hist) */
 
 typedef struct hm_engine hm_engine;
 
@@ -172,6 +176,11 @@ int hm_build_mod_record_mm(const uint8_t* body, size_t len, int keep_kinetics, c
  * HM_ERR_FORMAT. */
 int hm_parse_mod_record(const uint8_t* body, size_t len, int32_t* qoff, uint8_t* strand, uint8_t* prob, char* code, uint32_t cap,
                         uint32_t* n_mods);
+
+/* s_resolve_scaled_prob_threshold, src/app/hifimeth/pileup.cpp:355-436, for one context: the scaled-probability threshold is
+ * the emptiest bin of the histogram between its outermost bins (inside [20, 236)) holding >= 10 samples, provided that range
+ * spans >= 50 bins and holds >= 10000 samples; otherwise 128.  *n_samples (may be NULL) = the samples in that range. */
+uint8_t hm_ml_threshold(const uint64_t bins[256], uint64_t* n_samples);
 
 /* ---- the `call` driver and its BAM codec ------------------------------------------------------- */
 

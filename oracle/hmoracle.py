@@ -48,6 +48,25 @@ class _Oracle:
         L.hmo_build_mm.argtypes = [_u8p, _i32p, C.c_int, _i32p, C.c_int, C.c_char_p]
         L.hmo_build_mod_record.argtypes = [_u8p, C.c_size_t, C.c_int, _i32p, _u8p, C.c_int, _i32p, _u8p, C.c_int, _u8p]
         L.hmo_build_mod_record.restype = C.c_size_t
+        L.hmo_ml_histogram.argtypes = [_u8p, _u8p, C.POINTER(C.c_uint16), C.POINTER(C.c_uint32), C.c_int64, C.POINTER(C.c_uint64)]
+        L.hmo_ml_threshold.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.hmo_ml_threshold.restype = C.c_int
+
+    def ml_histogram(self, ml, ctx, read_flag, call_read) -> np.ndarray:
+        """[3, 256] u64 histograms of the ML bytes per context over reads without flag 0x900 (pileup.cpp:237-272)."""
+        ml = np.ascontiguousarray(ml, np.uint8)
+        ctx = np.ascontiguousarray(ctx, np.uint8)
+        fl = np.ascontiguousarray(read_flag, np.uint16)
+        rd = np.ascontiguousarray(call_read, np.uint32)
+        bins = np.zeros((3, 256), np.uint64)
+        self.lib.hmo_ml_histogram(_p(ml, _u8p), _p(ctx, _u8p), _p(fl, C.POINTER(C.c_uint16)), _p(rd, C.POINTER(C.c_uint32)), len(ml),
+                                  _p(bins, C.POINTER(C.c_uint64)))
+        return bins
+
+    def ml_threshold(self, bins):
+        b = np.ascontiguousarray(bins, np.uint64)
+        n = C.c_uint64(0)
+        return int(self.lib.hmo_ml_threshold(_p(b, C.POINTER(C.c_uint64)), C.byref(n))), int(n.value)
 
     # -- per-read primitives ---------------------------------------------------------------------------------
     def decode_seq(self, seq4: np.ndarray, l: int, flag: int):

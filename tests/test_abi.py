@@ -223,3 +223,32 @@ def test_parse_mod_record_general_series_and_errors(lib_built):
                    (b"C+m,1;", b"MLBS" + struct.pack("<I", 1) + struct.pack("<H", 256))):  # probability out of range
         with pytest.raises(hme.HmError):
             hme.parse_mod_record(with_tags(mm, ml))
+
+
+def test_ml_threshold_rule_matches_oracle(lib_built):
+    """Row N3: hm_ml_threshold against the oracle's restatement of s_resolve_scaled_prob_threshold (pileup.cpp:355-436) on
+    bimodal, flat, sparse, narrow and empty histograms."""
+    O = hmoracle.oracle()
+    rng = np.random.default_rng(5)
+    cases = []
+    x = np.arange(256)
+    bimodal = (40000 * np.exp(-x / 12.0) + 30000 * np.exp(-(255 - x) / 9.0) + 15).astype(np.uint64)
+    cases.append(bimodal)
+    cases.append(np.full(256, 100, np.uint64))                       # flat: first minimum of the range wins
+    cases.append(np.zeros(256, np.uint64))                           # empty -> 128
+    sparse = np.zeros(256, np.uint64); sparse[100:140] = 5000        # range narrower than 50 bins -> 128
+    cases.append(sparse)
+    few = np.zeros(256, np.uint64); few[30:200] = 12                 # wide enough but < 10000 samples -> 128
+    cases.append(few)
+    edge = bimodal.copy(); edge[:60] = 3; edge[200:] = 9             # outer bins below 10 shrink the range
+    cases.append(edge)
+    for _ in range(40):
+        cases.append(rng.integers(0, 400, 256).astype(np.uint64) * rng.integers(0, 2, 256).astype(np.uint64))
+        cases.append((rng.integers(0, 3000, 256) + 10).astype(np.uint64))
+    seen = set()
+    for b in cases:
+        got, want = hme.ml_threshold(b), O.ml_threshold(b)
+        assert got == want, (got, want)
+        seen.add(got[0])
+    assert 128 in seen and len(seen) > 5
+    assert hme.ml_threshold(bimodal)[0] == int(np.argmin(bimodal[20:236])) + 20

@@ -258,7 +258,7 @@ def test_call_cli_end_to_end(lib_built, models, tmp_path):
     r = subprocess.run([str(exe), "call", "-b", "4", "--max-bases", "8192", "-t", "3", "--devices", "0,0", str(src), str(dst)],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
-    assert "on 2 worker(s)" in r.stderr
+    assert "on 2 worker(s)" in r.stderr and "CpG scaled probability threshold (pileup rule): 128" in r.stderr
     text, _, got = synth.read_bam(dst)
     assert "@PG\tID:hifimeth\tPN:hifimeth\tVN:1.1.0\tCL:" in text and text.startswith("@HD")
     assert len(got) == len(bodies)
@@ -294,3 +294,22 @@ def test_call_cli_end_to_end(lib_built, models, tmp_path):
     for i, body in enumerate(bodies):
         fq, fml, rq, rml = c1.read_calls(i)
         assert got_k[i] == O.build_mod_record(body, True, fq, fml, rq, rml), i
+
+
+def test_ml_histogram_on_device(eng, models):
+    """Row N3: HM_SUBMIT_ML_HIST returns the per-context histograms of the batch's ML bytes over reads without flag 0x900, equal
+    to the oracle's accumulation over the engine's own calls; without the flag the pointer is NULL."""
+    batch, reads = synth.make_reads(12, (1000, 5000), seed=909, flag_rev_every=3)
+    batch.flag[2] |= 0x100   # secondary and supplementary records are left out of the histograms (pileup.cpp:237)
+    batch.flag[7] |= 0x800
+    got = eng.call(batch, flags=hme.HM_SUBMIT_ML_HIST)
+    assert got.ml_hist is not None and got.ml_hist.shape == (3, 256)
+    ctx = eng.dump_ctx(0, got.n_calls)
+    call_read = np.repeat(np.arange(got.n_reads, dtype=np.uint32), np.diff(got.call_off.astype(np.int64)))
+    want = hmoracle.oracle().ml_histogram(got.ml, ctx, batch.flag, call_read)
+    assert (got.ml_hist.astype(np.uint64) == want).all()
+    keep = ~np.isin(call_read, [2, 7])
+    assert int(got.ml_hist.sum()) == int(keep.sum()) < got.n_calls
+    for c in range(3):
+        assert (got.ml_hist[c] == np.bincount(got.ml[keep & (ctx == c)], minlength=256)).all()
+    assert eng.call(batch, slot=1).ml_hist is None

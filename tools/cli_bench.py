@@ -61,7 +61,7 @@ def main():
         m = re.search(r"CpG (\d+), CHG (\d+), CHH (\d+)", r.stderr)
         sites = sum(int(x) for x in m.groups())
         if best is None or wall < best["wall_s"]:
-            best = {"wall_s": wall, "sites": sites, "stderr": r.stderr.strip().splitlines()[-4:]}
+            best = {"wall_s": wall, "sites": sites, "stderr": r.stderr.strip().splitlines()[-7:]}
     print(json.dumps({"workload": f"{a.reads} reads x {a.len} b BAM -> mod BAM through the CLI", "cmd": " ".join(cmd[1:-2]),
                       "in_bam_bytes": in_bytes, "in_raw_bytes": raw_bytes, "out_bam_bytes": dst.stat().st_size,
                       "wall_s": best["wall_s"], "sites": best["sites"], "sites_per_s": best["sites"] / best["wall_s"],
