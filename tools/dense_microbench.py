@@ -60,6 +60,16 @@ if __name__ == "__main__":
         for v in (0, 8, 10):
             run(64, 64, [0, 0], v)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "conv1":
+        # where conv1-form tiles spend their time: 0 = all, 2 = no MMA, 4 = no epilogue stores, 8 = no epilogue work
+        for v in (0, 2, 4, 8, 10):
+            run(8, 128, [0], v, conv1=11)
+        for v in (0, 4, 8):
+            run(96, 96, [0, 32, 64], v)
+        os.environ["HM_DENSE_2CTA"] = "1"
+        for v in (0, 4, 8):
+            run(96, 96, [0, 32, 64], v)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "pair":
         for two in (0, 1):
             if two:
