@@ -28,6 +28,7 @@
 
 #include "dense_gemm.cuh"
 #include "dense_gemm2.cuh"
+#include "dense_fused12.cuh"
 #include "postprocess.cuh"
 
 namespace hm {
@@ -257,7 +258,8 @@ struct DevOp {
 
 // Lowers output channels [n0, n0 + n) of a plan op to kernel parameters + packed weights.  Returns false with
 // err = "fit" when the slice's resident weights leave no room for a 2-deep ring (the caller then splits it).
-bool lower_op(const HostOp& h, int n0, int n, DevOp& d, std::vector<uint8_t>& blob, std::string& err, bool two_cta = false)
+bool lower_op(const HostOp& h, int n0, int n, DevOp& d, std::vector<uint8_t>& blob, std::string& err, bool two_cta = false,
+              bool conv1_pair = false)
 {
     DenseOp& p = d.p;
     p = DenseOp{};
@@ -278,7 +280,7 @@ bool lower_op(const HostOp& h, int n0, int n, DevOp& d, std::vector<uint8_t>& bl
     for (int k = 0; k < p.n_scatter; ++k) { p.sc_shift[k] = h.scatter[k].first; d.sc_map[k] = h.scatter[k].second; }
     if (p.n_scatter && (n0 != 0 || n != h.cout)) { err = "a scattering op cannot be split over output channels"; return false; }
     for (const HostTerm& t : h.terms) if (two_cta && t.gather) { err = "op not eligible for the CTA-pair form"; return false; }
-    if (two_cta && (h.head || h.conv1_taps > 0 || n0 != 0 || n != h.cout || n % 32)) { err = "op not eligible for the CTA-pair form"; return false; }
+    if (two_cta && (h.head || (h.conv1_taps > 0 && !conv1_pair) || n0 != 0 || n != h.cout || n % 32)) { err = "op not eligible for the CTA-pair form"; return false; }
     p.gather_taps = 0;
     p.gather_rows = nullptr;
     if (h.conv1_taps > 0) {
@@ -406,6 +408,13 @@ bool pair_compact()
     return v;
 }
 
+// conv1 + conv2 in one kernel (dense_fused12.cuh); HM_NO_FUSE12=1 runs them as two launches (A/B measurements)
+bool fuse12_enabled()
+{
+    static const bool v = getenv("HM_NO_FUSE12") == nullptr;
+    return v;
+}
+
 bool two_cta_enabled()
 {
     static const bool v = getenv("HM_NO_2CTA") == nullptr;
@@ -419,6 +428,7 @@ int ensure_kernel_attr()
     if (g_attr_set) return 0;
     TCUDA("dense kernel attribute", cudaFuncSetAttribute(dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     TCUDA("dense kernel attribute", cudaFuncSetAttribute(dense_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    TCUDA("dense kernel attribute", cudaFuncSetAttribute(dense_fused12_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     g_attr_set = true;
     return 0;
 }
@@ -538,6 +548,10 @@ site_finish_kernel(const float2* __restrict__ clogit, const uint32_t* __restrict
 // ---- model ---------------------------------------------------------------------------------------------------------------
 struct TensorModel {
     std::vector<DevOp> ops;
+    // conv1 + conv2 fused (dense_fused12_kernel): launched in place of op i_y1, op i_y2 is skipped
+    bool fused12 = false;
+    DevOp f12_c1;
+    int i_y1 = -1, i_y2 = -1;
     uint8_t* d_blob = nullptr;
     double macs_per_row = 0;  // executed, one precision pass, all ops
 };
@@ -581,10 +595,27 @@ int tensor_model_build(TensorModelHandle& m, const CnnModel& host)
         }
         if (parts > 4) { delete t; return tfail("dense plan lowering: " + (err == "fit" ? std::string("op does not fit shared memory") : err)); }
     }
+    if (compact_mode() && fuse12_enabled() && two_cta_enabled()) {
+        for (size_t i = 0; i < t->ops.size(); ++i) {
+            const DevOp& d = t->ops[i];
+            if (!d.compact && d.out_map == MAP_Y && d.p.n == 128 && d.p.out_g0 == 0) t->i_y1 = (int)i;
+            if (!d.compact && d.out_map == MAP_Y + 1 && d.two_cta && d.p.n == 128 && d.p.n_stages == 8 && d.p.n_terms == 3) t->i_y2 = (int)i;
+        }
+        const HostOp* h1 = nullptr;
+        for (const HostOp& h : plan)
+            if (!h.compact && h.out == MAP_Y && h.conv1_taps > 0) h1 = &h;
+        if (t->i_y1 >= 0 && t->i_y2 >= 0 && h1 && lower_op(*h1, 0, 128, t->f12_c1, blob, err, true, true)) {
+            Fused12Op probe{};
+            probe.c1 = t->f12_c1.p;
+            probe.c2 = t->ops[t->i_y2].p;
+            t->fused12 = fused12_smem_bytes(probe) <= kSmemMax;
+        }
+    }
     cudaError_t st = cudaMalloc((void**)&t->d_blob, blob.size());
     if (st == cudaSuccess) st = cudaMemcpy(t->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice);
     if (st != cudaSuccess) { cudaFree(t->d_blob); delete t; return tfail(std::string("weight upload: ") + cudaGetErrorString(st)); }
     for (DevOp& d : t->ops) bind_blob(d, t->d_blob);
+    if (t->fused12) bind_blob(t->f12_c1, t->d_blob);
     m.p = t;
     return ensure_kernel_attr();
 }
@@ -681,7 +712,8 @@ void tensor_workspace_free(TensorWorkspace& w)
 
 namespace {
 
-int launch_op(const DevOp& d, const TensorWorkspaceImpl& s, uint32_t n_tiles, float* logit_out, int sm_count, cudaStream_t stream)
+// Kernel parameters of an op with the workspace pointers of this sub-batch filled in.
+DenseOp patch_op(const DevOp& d, const TensorWorkspaceImpl& s, uint32_t n_tiles, float* logit_out)
 {
     DenseOp p = d.p;
     auto stride_of = [&](int map) { return (map < MAP_F || !compact_mode()) ? s.plane_stride : s.cplane_stride; };
@@ -700,6 +732,32 @@ int launch_op(const DevOp& d, const TensorWorkspaceImpl& s, uint32_t n_tiles, fl
     for (int k = 0; k < p.n_scatter; ++k) p.sc_out[k] = s.map[d.sc_map[k]];
     p.sc_plane_stride = s.cplane_stride;
     p.site_of_row = s.d_site_of_row;
+    return p;
+}
+
+// conv1 + conv2 of `rows` dense rows in one launch (dense_fused12_kernel): tiles of 124 output rows, CTA pairs.
+int launch_fused12(const DevOp& d1, const DevOp& d2, const TensorWorkspaceImpl& s, uint32_t rows, int sm_count, cudaStream_t stream)
+{
+    Fused12Op f{};
+    f.n_tiles = (rows + kF12OutRows - 1) / kF12OutRows;
+    f.c1 = patch_op(d1, s, f.n_tiles, nullptr);
+    f.c2 = patch_op(d2, s, f.n_tiles, nullptr);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(std::min<uint32_t>(((f.n_tiles + 1) / 2) * 2, (uint32_t)sm_count & ~1u));
+    cfg.blockDim = dim3(kF12Threads);
+    cfg.dynamicSmemBytes = fused12_smem_bytes(f);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, dense_fused12_kernel, f) == cudaSuccess ? 0 : -1;
+}
+
+int launch_op(const DevOp& d, const TensorWorkspaceImpl& s, uint32_t n_tiles, float* logit_out, int sm_count, cudaStream_t stream)
+{
+    DenseOp p = patch_op(d, s, n_tiles, logit_out);
     uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)sm_count);
     if (d.two_cta) grid = std::min<uint32_t>(((n_tiles + 1) / 2) * 2, (uint32_t)sm_count & ~1u);
     cudaLaunchConfig_t cfg{};
@@ -826,10 +884,16 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
                                                                       b.d_site_pos, first_a, n_a, first_b, n, n_pad, sb.gtile0 * kTileRows,
                                                                       s->d_site_rows, s->d_site_of_row);
             int op_i = 0;
-            for (const DevOp& d : models[c].p->ops) {
+            const TensorModel& tm = *models[c].p;
+            for (const DevOp& d : tm.ops) {
                 if (prof) { cudaEventCreate(&pe[np]); cudaEventRecord(pe[np], stream); pk[np++] = c * 64 + op_i; }
-                launch_op(d, *s, d.compact ? n_pad / kTileRows : nt, s->d_clogit, sm_count, stream);
-                ++dense_launches;
+                if (tm.fused12 && op_i == tm.i_y1) {
+                    launch_fused12(tm.f12_c1, tm.ops[tm.i_y2], *s, nt * kTileRows, sm_count, stream);
+                    ++dense_launches;
+                } else if (!(tm.fused12 && op_i == tm.i_y2)) {
+                    launch_op(d, *s, d.compact ? n_pad / kTileRows : nt, s->d_clogit, sm_count, stream);
+                    ++dense_launches;
+                }
                 ++op_i;
             }
             if (prof) { cudaEventCreate(&pe[np]); cudaEventRecord(pe[np], stream); pk[np++] = -1; }
