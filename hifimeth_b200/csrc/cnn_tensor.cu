@@ -505,10 +505,12 @@ __device__ __forceinline__ uint32_t run_site(uint32_t m, uint32_t first_a, uint3
     return m < n_a ? first_a + m : first_b + (m - n_a);
 }
 
+// Compact runs may span several sub-batches: this sub-batch's sites are compact rows m_off .. m_off + n.  rows[] holds the row of
+// the batch-wide X map (gathered conv1-form ops), site_of_row[] is indexed by the row local to the sub-batch's dense maps.
 __global__ void __launch_bounds__(256)
 site_rows_kernel(const uint32_t* __restrict__ track_row_fwd, const uint32_t* __restrict__ track_row_rev,
                  const uint32_t* __restrict__ base_off, const uint32_t* __restrict__ site_read, const uint32_t* __restrict__ site_pos,
-                 uint32_t first_a, uint32_t n_a, uint32_t first_b, uint32_t n, uint32_t n_pad, uint32_t row_base,
+                 uint32_t first_a, uint32_t n_a, uint32_t first_b, uint32_t n, uint32_t n_pad, uint32_t row_base, uint32_t m_off,
                  uint32_t* __restrict__ rows, int32_t* __restrict__ site_of_row)
 {
     const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -522,10 +524,10 @@ site_rows_kernel(const uint32_t* __restrict__ track_row_fwd, const uint32_t* __r
         const int p = (int)(sp & 0x7fffffffu);
         const int L = (int)(base_off[r + 1] - base_off[r]);
         const int o = rev ? L - 1 - p : p;
-        row = (rev ? track_row_rev[r] : track_row_fwd[r]) - row_base + (uint32_t)(kHaloL + o - 201);
-        site_of_row[row] = (int32_t)m;  // inverse map for the dense layers' scatter (cleared to -1 before this launch)
+        row = (rev ? track_row_rev[r] : track_row_fwd[r]) + (uint32_t)(kHaloL + o - 201);
+        site_of_row[row - row_base] = (int32_t)(m_off + m);  // inverse map for the dense layers' scatter (cleared to -1 before this launch)
     }
-    rows[m] = row;
+    rows[m_off + m] = row;
 }
 
 // logits of the compact rows -> per-site logits + ML byte in hm_call_batch order
@@ -641,7 +643,11 @@ struct TensorWorkspaceImpl {
     uint32_t tiles_cap = 0, reads_cap = 0;
     uint32_t *h_tile_read = nullptr, *h_tile_first = nullptr, *d_tile_read = nullptr, *d_tile_first = nullptr;
     uint32_t *h_track_row = nullptr, *d_track_row = nullptr;  // [2][reads_cap]
-    uint32_t* d_site_rows = nullptr;  // [rows_cap] compact row -> dense row
+    uint8_t* d_xg = nullptr;          // compact mode: X of the WHOLE batch, planes {hi, lo} of [total rows + slack][8] bf16
+    unsigned long long xg_stride = 0;
+    const uint8_t* x_cur = nullptr;   // X rows of the sub-batch being launched (points into d_xg) and their plane stride
+    unsigned long long x_stride_cur = 0;
+    uint32_t* d_site_rows = nullptr;  // [compact_cap] compact row -> X row (global)
     float* d_clogit = nullptr;        // [rows_cap][2] logits of the compact rows
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -677,6 +683,11 @@ int tensor_workspace_alloc(TensorWorkspace& w, uint32_t max_bases, uint32_t max_
         at += 2 * (size_t)map_channels(i) / 8 * (is_dense_map(i) ? s->plane_stride : s->cplane_stride);
     }
     TCUDA("site rows", cudaMalloc((void**)&s->d_site_of_row, (cap + kSlackRows) * sizeof(int32_t)));
+    if (compact_mode()) {
+        s->xg_stride = (unsigned long long)(total_rows + kSlackRows) * 16ull;
+        TCUDA("X map", cudaMalloc((void**)&s->d_xg, 2 * s->xg_stride));
+        TCUDA("X map", cudaMemset(s->d_xg, 0, 2 * s->xg_stride));
+    }
     s->logit_rows_cap = total_rows;
     if (!compact_mode())
         for (int c = 0; c < 3; ++c) TCUDA("logit rows", cudaMalloc((void**)&s->d_logit[c], total_rows * 2 * sizeof(float)));
@@ -701,7 +712,7 @@ void tensor_workspace_free(TensorWorkspace& w)
     if (!s) return;
     cudaFree(s->d_maps);
     for (float* p : s->d_logit) cudaFree(p);
-    cudaFree(s->d_site_rows); cudaFree(s->d_clogit); cudaFree(s->d_site_of_row);
+    cudaFree(s->d_site_rows); cudaFree(s->d_clogit); cudaFree(s->d_site_of_row); cudaFree(s->d_xg);
     cudaFreeHost(s->h_tile_read); cudaFreeHost(s->h_tile_first); cudaFree(s->d_tile_read); cudaFree(s->d_tile_first);
     cudaFreeHost(s->h_track_row); cudaFree(s->d_track_row);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -720,6 +731,11 @@ DenseOp patch_op(const DevOp& d, const TensorWorkspaceImpl& s, uint32_t n_tiles,
     for (int i = 0; i < p.n_segs; ++i) {
         p.seg[i].src = s.map[d.seg_map[i]];
         p.seg[i].plane_stride = stride_of(d.seg_map[i]);
+        if (d.seg_map[i] == MAP_X && s.x_cur) {
+            // compact mode keeps X of the whole batch: dense ops read the running sub-batch's rows, gathered ops index it globally
+            p.seg[i].src = p.seg[i].gather ? s.d_xg : s.x_cur;
+            p.seg[i].plane_stride = s.x_stride_cur;
+        }
     }
     p.n_tiles = n_tiles;
     p.gather_rows = s.d_site_rows;
@@ -852,56 +868,109 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
     size_t np = 0;
     const bool compact = compact_mode();
     const uint32_t first[4] = {0, b.class_count[0], b.class_count[0] + b.class_count[1], b.class_count[0] + b.class_count[1] + b.class_count[2]};
-    for (const SubBatch& sb : subs) {
-        track_features_kernel<<<sb.tiles, 128, 0, stream>>>(b.d_bcode, b.d_kinf, b.d_base_off, s->d_tile_read, s->d_tile_first, sb.gtile0,
-                                                          s->map[MAP_X], s->map[MAP_X] + s->plane_stride);
-        ++*launches;
-        for (int c = 0; c < 3; ++c) {
-            const uint32_t n_sites_c = b.class_count[c] + (c == 2 ? b.class_count[3] : 0u);
-            if (!(ctx_mask & (1u << c)) || !n_sites_c) continue;
-            if (!models[c].p) return tfail("model of an enabled context is missing");
-            const uint32_t nt = (c == 2) ? sb.tiles : sb.fwd_tiles;
-            if (!nt) continue;
-            if (!compact) {
+    auto stamp = [&](int key) {
+        if (!prof) return;
+        cudaEventCreate(&pe[np]);
+        cudaEventRecord(pe[np], stream);
+        pk[np++] = key;
+    };
+    if (!compact) {
+        // every op on every row (HM_DENSE_ALL, the first version of this path): sub-batch by sub-batch
+        s->x_cur = nullptr;
+        for (const SubBatch& sb : subs) {
+            track_features_kernel<<<sb.tiles, 128, 0, stream>>>(b.d_bcode, b.d_kinf, b.d_base_off, s->d_tile_read, s->d_tile_first, sb.gtile0,
+                                                              s->map[MAP_X], s->map[MAP_X] + s->plane_stride);
+            ++*launches;
+            for (int c = 0; c < 3; ++c) {
+                const uint32_t n_sites_c = b.class_count[c] + (c == 2 ? b.class_count[3] : 0u);
+                if (!(ctx_mask & (1u << c)) || !n_sites_c) continue;
+                if (!models[c].p) return tfail("model of an enabled context is missing");
+                const uint32_t nt = (c == 2) ? sb.tiles : sb.fwd_tiles;
+                if (!nt) continue;
                 float* lg = s->d_logit[c] + (size_t)sb.gtile0 * kTileRows * 2;
                 for (const DevOp& d : models[c].p->ops) {
                     launch_op(d, *s, nt, lg, sm_count, stream);
                     ++dense_launches;
                 }
-                continue;
             }
-            // sites of this context inside the sub-batch: class regions are ordered by read, so each is one range
-            const uint32_t* p0 = b.h_read_pref + 4 * (size_t)sb.r0;
-            const uint32_t* p1 = b.h_read_pref + 4 * (size_t)sb.r1;
-            const uint32_t first_a = first[c] + p0[c], n_a = p1[c] - p0[c];
-            const uint32_t first_b = c == 2 ? first[3] + p0[3] : 0u, n_b = c == 2 ? p1[3] - p0[3] : 0u;
-            const uint32_t n = n_a + n_b;
-            if (!n) continue;
-            if (n > s->compact_cap) return tfail("internal: more sites than compact rows in a sub-batch");
-            TCUDA("site rows", cudaMemsetAsync(s->d_site_of_row, 0xff, ((size_t)nt * kTileRows + kSlackRows) * sizeof(int32_t), stream));
-            const uint32_t n_pad = ((n + kTileRows - 1) / kTileRows) * kTileRows;
-            site_rows_kernel<<<(n_pad + 255) / 256, 256, 0, stream>>>(s->d_track_row, s->d_track_row + s->reads_cap, b.d_base_off, b.d_site_read,
-                                                                      b.d_site_pos, first_a, n_a, first_b, n, n_pad, sb.gtile0 * kTileRows,
-                                                                      s->d_site_rows, s->d_site_of_row);
-            int op_i = 0;
-            const TensorModel& tm = *models[c].p;
-            for (const DevOp& d : tm.ops) {
-                if (prof) { cudaEventCreate(&pe[np]); cudaEventRecord(pe[np], stream); pk[np++] = c * 64 + op_i; }
-                if (tm.fused12 && op_i == tm.i_y1) {
-                    launch_fused12(tm.f12_c1, tm.ops[tm.i_y2], *s, nt * kTileRows, sm_count, stream);
-                    ++dense_launches;
-                } else if (!(tm.fused12 && op_i == tm.i_y2)) {
-                    launch_op(d, *s, d.compact ? n_pad / kTileRows : nt, s->d_clogit, sm_count, stream);
-                    ++dense_launches;
-                }
-                ++op_i;
-            }
-            if (prof) { cudaEventCreate(&pe[np]); cudaEventRecord(pe[np], stream); pk[np++] = -1; }
-            site_finish_kernel<<<(n + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const float2*>(s->d_clogit), b.d_site_out, first_a, n_a, first_b, n,
-                                                                    b.d_logits, b.d_ml);
-            *launches += 2;
+            TCUDA("dense plan", cudaGetLastError());
         }
-        TCUDA("dense plan", cudaGetLastError());
+    } else if (gtile) {
+        // X of the whole batch once (32 B per row); then, context by context, GROUPS of consecutive sub-batches: the dense chain
+        // Y1 .. Y6 runs per sub-batch and scatters the rows sites need into the compact buffers, the compact chain (F, G, tail)
+        // runs once per group over all its sites -- as many sub-batches as the compact buffers hold, so that the sparse contexts
+        // (CpG, CHG: ~60 k sites per sub-batch) get launches of ~1 M rows instead of 15 short ones per op.
+        track_features_kernel<<<gtile, 128, 0, stream>>>(b.d_bcode, b.d_kinf, b.d_base_off, s->d_tile_read, s->d_tile_first, 0, s->d_xg,
+                                                        s->d_xg + s->xg_stride);
+        ++*launches;
+        s->x_stride_cur = s->xg_stride;
+        struct Seg { uint32_t first_a, n_a, first_b, n, m_off; };
+        for (int c = 0; c < 3; ++c) {
+            const uint32_t n_sites_c = b.class_count[c] + (c == 2 ? b.class_count[3] : 0u);
+            if (!(ctx_mask & (1u << c)) || !n_sites_c) continue;
+            if (!models[c].p) return tfail("model of an enabled context is missing");
+            const TensorModel& tm = *models[c].p;
+            size_t g0 = 0;
+            while (g0 < subs.size()) {
+                // ---- dense chains of the group's sub-batches ---------------------------------------------------------------
+                std::vector<Seg> segs;
+                uint32_t m_off = 0;
+                size_t g1 = g0;
+                for (; g1 < subs.size(); ++g1) {
+                    const SubBatch& sb = subs[g1];
+                    const uint32_t nt = (c == 2) ? sb.tiles : sb.fwd_tiles;
+                    // sites of this context inside the sub-batch: class regions are ordered by read, so each is one range
+                    const uint32_t* p0 = b.h_read_pref + 4 * (size_t)sb.r0;
+                    const uint32_t* p1 = b.h_read_pref + 4 * (size_t)sb.r1;
+                    const uint32_t first_a = first[c] + p0[c], n_a = p1[c] - p0[c];
+                    const uint32_t first_b = c == 2 ? first[3] + p0[3] : 0u, n_b = c == 2 ? p1[3] - p0[3] : 0u;
+                    const uint32_t n = n_a + n_b;
+                    if (!nt || !n) continue;
+                    if (n > s->compact_cap) return tfail("internal: more sites than compact rows in a sub-batch");
+                    if (m_off + n > s->compact_cap) break;  // the group is full: run its compact chain first
+                    TCUDA("site rows", cudaMemsetAsync(s->d_site_of_row, 0xff, ((size_t)nt * kTileRows + kSlackRows) * sizeof(int32_t), stream));
+                    const uint32_t n_pad = ((m_off + n + kTileRows - 1) / kTileRows) * kTileRows - m_off;
+                    site_rows_kernel<<<(n_pad + 255) / 256, 256, 0, stream>>>(s->d_track_row, s->d_track_row + s->reads_cap, b.d_base_off,
+                                                                              b.d_site_read, b.d_site_pos, first_a, n_a, first_b, n, n_pad,
+                                                                              sb.gtile0 * kTileRows, m_off, s->d_site_rows, s->d_site_of_row);
+                    ++*launches;
+                    s->x_cur = s->d_xg + (size_t)sb.gtile0 * kTileRows * 16;
+                    int op_i = 0;
+                    for (const DevOp& d : tm.ops) {
+                        if (!d.compact && !(tm.fused12 && op_i == tm.i_y2)) {
+                            stamp(c * 64 + op_i);
+                            if (tm.fused12 && op_i == tm.i_y1) launch_fused12(tm.f12_c1, tm.ops[tm.i_y2], *s, nt * kTileRows, sm_count, stream);
+                            else launch_op(d, *s, nt, nullptr, sm_count, stream);
+                            ++dense_launches;
+                        }
+                        ++op_i;
+                    }
+                    segs.push_back(Seg{first_a, n_a, first_b, n, m_off});
+                    m_off += n;
+                }
+                // ---- the compact chain over all sites of the group, then logits -> ML bytes per sub-batch segment --------------
+                if (m_off) {
+                    const uint32_t n_tiles = (m_off + kTileRows - 1) / kTileRows;
+                    int op_i = 0;
+                    for (const DevOp& d : tm.ops) {
+                        if (d.compact) {
+                            stamp(c * 64 + op_i);
+                            launch_op(d, *s, n_tiles, s->d_clogit, sm_count, stream);
+                            ++dense_launches;
+                        }
+                        ++op_i;
+                    }
+                    stamp(-1);
+                    for (const Seg& sg : segs) {
+                        site_finish_kernel<<<(sg.n + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const float2*>(s->d_clogit) + sg.m_off, b.d_site_out,
+                                                                                   sg.first_a, sg.n_a, sg.first_b, sg.n, b.d_logits, b.d_ml);
+                        ++*launches;
+                    }
+                }
+                TCUDA("dense plan", cudaGetLastError());
+                g0 = g1 > g0 ? g1 : g0 + 1;
+            }
+        }
     }
     TCUDA("dense plan", cudaEventRecord(s->ev1, stream));
     *launches += dense_launches;

@@ -313,3 +313,29 @@ def test_ml_histogram_on_device(eng, models):
     for c in range(3):
         assert (got.ml_hist[c] == np.bincount(got.ml[keep & (ctx == c)], minlength=256)).all()
     assert eng.call(batch, slot=1).ml_hist is None
+
+
+def test_sub_batches_and_compact_groups_do_not_change_results(lib_built, monkeypatch):
+    """A batch cut into many sub-batches (HM_DENSE_ROWS small: dense maps of 16 Ki rows, compact buffers of 8 Ki sites, so the
+    dense chains run per sub-batch and the compact chain per GROUP of sub-batches, several groups per context) gives
+    bit-identical calls and logits to the same batch evaluated in one piece."""
+    batch, _ = synth.make_reads(40, (1000, 6000), seed=31337, flag_rev_every=3, short_every=9)
+    whole = hme.Engine(max_reads=64, max_bases=1 << 19, keep_debug=True)
+    try:
+        a = whole.call(batch)
+        la = whole.dump_logits(0, a.n_calls)
+    finally:
+        whole.close()
+    monkeypatch.setenv("HM_DENSE_ROWS", "16384")
+    cut = hme.Engine(max_reads=64, max_bases=1 << 19, keep_debug=True)
+    try:
+        b = cut.call(batch)
+        lb = cut.dump_logits(0, b.n_calls)
+        launches = cut.timing(0).kernel_launches
+    finally:
+        cut.close()
+    assert a.n_calls == b.n_calls > 30000
+    assert (a.call_off == b.call_off).all() and (a.qoff == b.qoff).all()
+    assert (la.view(np.uint32) == lb.view(np.uint32)).all()
+    assert (a.ml == b.ml).all()
+    assert launches > 300  # really many sub-batches
