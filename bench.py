@@ -271,10 +271,10 @@ def main():
             "e2e": {"value": sites_all * args.steps / e2e_s, "unit": "sites/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         # DRAM read+write of the kernel family per step: ncu, profiles/r1_launches_v6_final.csv (58.2 GB for a
-                         # 128-read step, scaled by reads); algorithmic map traffic of the plan is ~5.5 KB per dense row and context
-                         "traffic": 58.2e9 * args.reads / 128.0, "traffic_unit": "bytes per step",
-                         "kernel": "dense_gemm2_kernel + dense_gemm_kernel (every op of the dense plan)", "launches_per_step": top_launches // max(args.steps, 1), "peak_source": peak_src,
+                         # DRAM read+write of the kernel family per step: ncu, profiles/r1_launches_v8_fused12_grouped.csv (51.3 GB
+                         # for a 128-read step, scaled by reads; 58.2 GB before conv1 + conv2 were fused)
+                         "traffic": 51.3e9 * args.reads / 128.0, "traffic_unit": "bytes per step",
+                         "kernel": "dense_gemm2_kernel + dense_fused12_kernel + dense_gemm_kernel (every op of the dense plan)", "launches_per_step": top_launches // max(args.steps, 1), "peak_source": peak_src,
                          "note": "achieved = algorithmic FLOPs of the per-site network / summed device time of the kernel family; the dense plan "
                                  "shares conv work between overlapping windows, so executed FLOPs are lower (DESIGN.md)"},
             "clocks": clocks,

@@ -339,3 +339,51 @@ def test_sub_batches_and_compact_groups_do_not_change_results(lib_built, monkeyp
     assert (la.view(np.uint32) == lb.view(np.uint32)).all()
     assert (a.ml == b.ml).all()
     assert launches > 300  # really many sub-batches
+
+
+def test_full_size_config1_batch(lib_built, models):
+    """BASELINE.json configs[1] at full size (1 000 reads x 15 kb, all contexts, ~5.86 M sites, 15 sub-batches, several compact
+    groups per context): site lists, call order and contexts bit-exact against the oracle for EVERY read; per-read offsets
+    consistent; probabilities within 1e-3 and ML within +-1 on a random sample of 1 500 sites per context; the MM text of a sample
+    of reads equal to the oracle's; ML histograms summing to the calls."""
+    O = hmoracle.oracle()
+    batch, _ = synth.make_reads(1000, 15000, seed=20261)
+    eng = hme.Engine(n_slots=1, max_reads=1000, max_bases=batch.n_bases + 1024, keep_debug=True)
+    try:
+        got = eng.call(batch, flags=hme.HM_SUBMIT_MM_TEXT | hme.HM_SUBMIT_ML_HIST)
+        ctx = eng.dump_ctx(0, got.n_calls)
+        logits = eng.dump_logits(0, got.n_calls)
+        launches = eng.timing(0).kernel_launches
+    finally:
+        eng.close()
+    want = O.batch_sites(batch, 7)
+    assert got.n_calls == sum(len(w["qoff"]) for w in want) > 5_800_000
+    assert launches > 500
+    off = 0
+    for r, w in enumerate(want):
+        n = len(w["qoff"])
+        assert int(got.call_off[r]) == off and int(got.n_fwd[r]) == w["n_fwd"], r
+        assert (got.qoff[off:off + n] == w["qoff"]).all() and (ctx[off:off + n] == w["ctx"]).all(), r
+        off += n
+    assert got.n_sites == tuple(int((ctx == c).sum()) for c in range(3))
+    assert int(got.ml_hist.sum()) == got.n_calls
+    for c in range(3):
+        assert (got.ml_hist[c] == np.bincount(got.ml[ctx == c], minlength=256)).all()
+    # MM text of a few reads against the oracle's build_mm (C+m,...;G-m,...;)
+    for r in (0, 499, 999):
+        a, nf = int(got.call_off[r]), int(got.n_fwd[r])
+        b = int(got.call_off[r + 1])
+        fwd_txt, rev_txt = got.read_mm(r)
+        mm = O.build_mm(want[r]["fwd"], got.qoff[a:a + nf], got.qoff[a + nf:b])
+        assert mm == b"C+m" + fwd_txt.tobytes() + b";G-m" + rev_txt.tobytes() + b";", r
+    # CNN on a random sample per context
+    rng = np.random.default_rng(11)
+    p_gpu, _ = cnn_oracle.logits_to_prob_ml(logits)
+    for c in range(3):
+        idx = np.sort(rng.choice(np.nonzero(ctx == c)[0], size=1500, replace=False))
+        read_of = np.searchsorted(got.call_off, idx, side="right") - 1
+        feats = np.concatenate([O.batch_features(batch, want, int(r), np.array([int(k - got.call_off[r])])) for k, r in zip(idx, read_of)])
+        lg = cnn_oracle.forward_logits(models[c], feats)
+        p_cpu, ml_cpu = cnn_oracle.logits_to_prob_ml(lg)
+        assert np.abs(p_gpu[idx] - p_cpu).max() <= PROB_TOL, (c, float(np.abs(p_gpu[idx] - p_cpu).max()))
+        assert np.abs(got.ml[idx].astype(np.int32) - ml_cpu.astype(np.int32)).max() <= ML_TOL, c
