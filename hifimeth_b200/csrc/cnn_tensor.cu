@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -34,7 +35,7 @@
 namespace hm {
 namespace {
 
-std::string g_err = "";
+thread_local std::string g_err = "";  // engines of different devices run on different host threads
 int tfail(const std::string& s) { g_err = s; return -1; }
 #define TCUDA(stage, call)                                                                   \
     do {                                                                                     \
@@ -421,15 +422,21 @@ bool two_cta_enabled()
     return v;
 }
 
-bool g_attr_set = false;
 float g_debug_op_ms = 0.f;
+// The dynamic shared memory limit of a kernel is a per-DEVICE attribute: one process may drive several GPUs (the `call` driver's
+// --devices), so it is set once per device, under a lock (engines are created from one thread per device).
 int ensure_kernel_attr()
 {
-    if (g_attr_set) return 0;
+    static std::mutex m;
+    static bool done[64] = {};
+    int dev = 0;
+    TCUDA("dense kernel attribute", cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(m);
+    if (dev >= 0 && dev < 64 && done[dev]) return 0;
     TCUDA("dense kernel attribute", cudaFuncSetAttribute(dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     TCUDA("dense kernel attribute", cudaFuncSetAttribute(dense_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     TCUDA("dense kernel attribute", cudaFuncSetAttribute(dense_fused12_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-    g_attr_set = true;
+    if (dev >= 0 && dev < 64) done[dev] = true;
     return 0;
 }
 
