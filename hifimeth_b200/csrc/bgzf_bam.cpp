@@ -5,6 +5,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -15,7 +18,7 @@ namespace hm {
 
 namespace {
 constexpr size_t kBlockPayload = 0xff00;      // uncompressed bytes per BGZF block (htslib's BGZF_BLOCK_SIZE)
-constexpr size_t kReadSlab = 8u << 20;        // compressed bytes read per slab (~130 blocks: enough to spread over the threads)
+constexpr size_t kReadSlab = 16u << 20;       // compressed bytes read per slab (~260 blocks: enough to spread over the threads)
 constexpr size_t kReadAhead = 3;              // inflated slabs queued ahead of the consumer
 constexpr size_t kWriteBatch = 1024;          // blocks deflated per parallel batch (~64 MB)
 
@@ -43,21 +46,86 @@ size_t bgzf_block_size(const uint8_t* p, size_t n, bool& bad)
 }
 }  // namespace
 
+namespace {
+// One process-wide pool of worker threads shared by every parallel_for (reader inflate, record packing and assembly, writer
+// deflate): spawning threads per call cost ~1 ms per 8 MB slab.  Callers are never pool threads themselves, so a caller may
+// block on its own job while the pool serves several jobs at once.
+class Pool {
+public:
+    static Pool& get()
+    {
+        static Pool p;
+        return p;
+    }
+    void run(size_t n, size_t workers, const std::function<void(size_t)>& fn)
+    {
+        struct Job {
+            std::atomic<size_t> next{0}, left{0};
+            std::mutex m;
+            std::condition_variable cv;
+        } job;
+        job.left = workers;
+        auto body = [&job, &fn, n] {
+            for (size_t i = job.next.fetch_add(1); i < n; i = job.next.fetch_add(1)) fn(i);
+            std::lock_guard<std::mutex> lk(job.m);
+            if (--job.left == 0) job.cv.notify_all();
+        };
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            for (size_t k = 0; k + 1 < workers; ++k) q_.push_back(body);
+            cv_.notify_all();
+        }
+        body();  // the caller works too
+        std::unique_lock<std::mutex> lk(job.m);
+        job.cv.wait(lk, [&] { return job.left == 0; });
+    }
+    size_t size() const { return threads_.size() + 1; }
+
+private:
+    Pool()
+    {
+        const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+        for (unsigned k = 0; k + 1 < hw; ++k)
+            threads_.emplace_back([this] {
+                for (;;) {
+                    std::function<void()> task;
+                    {
+                        std::unique_lock<std::mutex> lk(m_);
+                        cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+                        if (q_.empty()) return;
+                        task = std::move(q_.front());
+                        q_.pop_front();
+                    }
+                    task();
+                }
+            });
+    }
+    ~Pool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+            cv_.notify_all();
+        }
+        for (auto& t : threads_) t.join();
+    }
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<std::function<void()>> q_;
+    std::vector<std::thread> threads_;
+    bool stop_ = false;
+};
+}  // namespace
+
 void parallel_for(size_t n, int threads, const std::function<void(size_t)>& fn)
 {
     if (n == 0) return;
-    const size_t t = std::min<size_t>(std::max(threads, 1), n);
+    const size_t t = std::min<size_t>(std::min<size_t>(std::max(threads, 1), n), Pool::get().size());
     if (t == 1) {
         for (size_t i = 0; i < n; ++i) fn(i);
         return;
     }
-    std::atomic<size_t> next{0};
-    std::vector<std::thread> pool;
-    for (size_t k = 0; k < t; ++k)
-        pool.emplace_back([&] {
-            for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
-        });
-    for (auto& th : pool) th.join();
+    Pool::get().run(n, t, fn);
 }
 
 // ---- BgzfReader ----------------------------------------------------------------------------------------------------------
