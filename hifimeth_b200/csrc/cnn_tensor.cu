@@ -876,7 +876,7 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
     const bool compact = compact_mode();
     const uint32_t first[4] = {0, b.class_count[0], b.class_count[0] + b.class_count[1], b.class_count[0] + b.class_count[1] + b.class_count[2]};
     auto stamp = [&](int key) {
-        if (!prof) return;
+        if (!prof || np >= pe.size()) return;
         cudaEventCreate(&pe[np]);
         cudaEventRecord(pe[np], stream);
         pk[np++] = key;
