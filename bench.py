@@ -279,7 +279,7 @@ def main():
                                  "shares conv work between overlapping windows, so executed FLOPs are lower (DESIGN.md)"},
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is a rank-0, N = 1 measurement
             threads = physical_cores()
             nr = int(os.environ.get("HM_CPU_SAMPLE_READS", "32"))
             s, r, dt, kind = cpu_pipeline(nr, threads)
