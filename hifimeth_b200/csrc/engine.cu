@@ -72,6 +72,8 @@ struct Slot {
     bool mm_valid = false;
     uint32_t *d_ml_hist = nullptr, *h_ml_hist = nullptr;  // [3][256]
     bool hist_valid = false;
+    hm::ReadKinStats *d_read_stats = nullptr, *h_read_stats = nullptr;  // [max_reads]
+    bool stats_valid = false;
     // fp32 CNN workspace (site chunk)
     float* d_feat = nullptr;
     float* d_act[8] = {};
@@ -200,6 +202,7 @@ void free_slot(Slot& s)
     cudaFreeHost(s.h_read_pref); cudaFree(s.d_read_pref);
     cudaFree(s.d_mm_delta); cudaFree(s.d_mm_bsum); cudaFree(s.d_mm_boff); cudaFree(s.d_mm_toff); cudaFree(s.d_mm_off); cudaFree(s.d_mm_fwd_len);
     cudaFree(s.d_ml_hist); cudaFreeHost(s.h_ml_hist);
+    cudaFree(s.d_read_stats); cudaFreeHost(s.h_read_stats);
     cudaFree(s.d_mm_text); cudaFreeHost(s.h_mm_off); cudaFreeHost(s.h_mm_fwd_len); cudaFreeHost(s.h_mm_total); cudaFreeHost(s.h_mm_text);
     cudaFreeHost(s.h_call_off); cudaFreeHost(s.h_n_fwd); cudaFreeHost(s.h_totals); cudaFreeHost(s.h_qoff); cudaFreeHost(s.h_ml);
     void* dev[] = {s.d_seq4, s.d_fi, s.d_fp, s.d_ri, s.d_rp, s.d_valid, s.d_base_off, s.d_seq_off, s.d_flag, s.d_chunk_read,
@@ -281,6 +284,8 @@ int alloc_slot(hm_engine* e, Slot& s)
     HM_CUDA(e, st, hmalloc(&s.h_mm_off, R + 1));
     HM_CUDA(e, st, hmalloc(&s.h_mm_fwd_len, R));
     HM_CUDA(e, st, hmalloc(&s.h_mm_total, 1));
+    HM_CUDA(e, st, dmalloc(&s.d_read_stats, R));
+    HM_CUDA(e, st, hmalloc(&s.h_read_stats, R));
     HM_CUDA(e, st, dmalloc(&s.d_ml_hist, 3 * 256));
     HM_CUDA(e, st, hmalloc(&s.h_ml_hist, 3 * 256));
     HM_CUDA(e, st, hmalloc(&s.h_mm_text, s.mm_text_cap));
@@ -580,6 +585,17 @@ int hm_batch_submit(hm_engine* e, int slot, uint32_t n_reads, uint32_t flags)
         }
         HM_CUDA(e, "MM text", cudaEventRecord(s.ev[6], st));
     }
+    s.stats_valid = false;
+    const bool want_stats = (flags & HM_SUBMIT_READ_STATS) != 0;
+    if (want_stats && s.n_reads) {
+        // row A9 (diagnostics): sum / max of the decoded frames per read
+        HM_CUDA(e, "read stats", cudaMemsetAsync(s.d_read_stats, 0, s.n_reads * sizeof(hm::ReadKinStats), st));
+        if (s.n_chunks) {
+            hm::read_stats_kernel<<<s.n_chunks, hm::kFrontThreads, 0, st>>>(s.d_kinf, s.d_base_off, s.d_chunk_read, s.d_chunk_pos, s.d_read_stats);
+            ++launches;
+        }
+        HM_CUDA(e, "read stats", cudaGetLastError());
+    }
     if ((rc = stage_cnn(e, s, launches))) return rc;
     s.hist_valid = false;
     const bool want_hist = (flags & HM_SUBMIT_ML_HIST) != 0;
@@ -613,6 +629,10 @@ int hm_batch_submit(hm_engine* e, int slot, uint32_t n_reads, uint32_t flags)
         if (want_hist) {
             HM_CUDA(e, stg, cp(s.h_ml_hist, s.d_ml_hist, 3 * 256 * sizeof(uint32_t)));
             s.hist_valid = true;
+        }
+        if (want_stats) {
+            HM_CUDA(e, stg, cp(s.h_read_stats, s.d_read_stats, s.n_reads * sizeof(hm::ReadKinStats)));
+            s.stats_valid = true;
         }
         s.timing.d2h_bytes = bytes + 5 * sizeof(uint32_t);
     }
@@ -652,6 +672,8 @@ int hm_batch_collect(hm_engine* e, int slot, hm_call_batch* out)
     out->mm_off = s.mm_valid ? s.h_mm_off : nullptr;
     out->mm_fwd_len = s.mm_valid ? s.h_mm_fwd_len : nullptr;
     out->ml_hist = s.hist_valid ? s.h_ml_hist : nullptr;
+    static_assert(sizeof(hm::ReadKinStats) == sizeof(hm_read_stats), "hm_read_stats layout");
+    out->read_stats = s.stats_valid ? reinterpret_cast<const hm_read_stats*>(s.h_read_stats) : nullptr;
     s.collected = true;
     return HM_OK;
 }
@@ -789,6 +811,9 @@ int hm_microbench(hm_engine* e, int slot, const char* name, uint32_t n_sites, in
                 hm::scan_write_kernel<<<s.n_chunks, hm::kFrontThreads, 0, st>>>(s.d_cls, s.d_chunk_read, s.d_chunk_pos, s.d_read_first_chunk, s.d_pref,
                                                                              s.n_chunks, s.d_qoff, s.d_call_ctx, s.d_site_read, s.d_site_pos, s.d_site_out);
             bytes = 0.5 * s.n_bases + 5.0 * s.n_calls;  // SURVEY s8d; the lists the engine really writes are 17 B/site
+        } else if (k == "stats") {
+            if (s.n_chunks) hm::read_stats_kernel<<<s.n_chunks, hm::kFrontThreads, 0, st>>>(s.d_kinf, s.d_base_off, s.d_chunk_read, s.d_chunk_pos, s.d_read_stats);
+            bytes = 8.0 * s.n_bases;  // the four decoded frames of every base read once
         } else if (k == "gather") {
             if (ns) hm::gather_features_kernel<<<ns, 128, 0, st>>>(s.d_bcode, s.d_kinf, s.d_base_off, s.d_site_read, s.d_site_pos, 0, ns, d_tmp);
             bytes = 12832.0 * ns;

@@ -474,6 +474,51 @@ scan_write_kernel(const uint64_t* __restrict__ cls_in, const uint32_t* __restric
     }
 }
 
+// A9 (north_star "per-read normalisation"; DIAGNOSTICS ONLY -- the reference normalises by the fixed 952, src/corelib/
+// bam_info.hpp:108, and nothing computed here is fed to the model): per read the sum and maximum of the decoded frames of each
+// kinetics plane (fi, fp, ri, rp), from which the caller gets per-read means.  One block per chunk (the decode kernel's chunk
+// table): coalesced 8-byte loads, warp-shuffle reduction, one set of atomics per block into the read's record (zeroed by the
+// caller).  HBM bound: 8 B/base in.
+struct __align__(8) ReadKinStats {
+    unsigned long long sum[4];
+    uint32_t max[4];
+};
+
+__global__ void __launch_bounds__(kFrontThreads)
+read_stats_kernel(const ushort4* __restrict__ kinf, const uint32_t* __restrict__ base_off, const uint32_t* __restrict__ chunk_read,
+                  const uint32_t* __restrict__ chunk_pos, ReadKinStats* __restrict__ out)
+{
+    __shared__ unsigned long long s_sum[kFrontThreads / 32][4];
+    __shared__ uint32_t s_max[kFrontThreads / 32][4];
+    const uint32_t r = chunk_read[blockIdx.x], p0 = chunk_pos[blockIdx.x];
+    const uint32_t B = base_off[r], L = base_off[r + 1] - B;
+    const uint32_t n = min((uint32_t)kChunk, L - p0);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t s[4] = {0, 0, 0, 0}, m[4] = {0, 0, 0, 0};  // <= 16 values of <= 952 per thread: 32-bit partial sums
+    for (uint32_t i = threadIdx.x; i < n; i += kFrontThreads) {
+        const ushort4 k = kinf[B + p0 + i];
+        s[0] += k.x; s[1] += k.y; s[2] += k.z; s[3] += k.w;
+        m[0] = max(m[0], (uint32_t)k.x); m[1] = max(m[1], (uint32_t)k.y); m[2] = max(m[2], (uint32_t)k.z); m[3] = max(m[3], (uint32_t)k.w);
+    }
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+            m[k] = max(m[k], __shfl_xor_sync(0xffffffffu, m[k], o));
+        }
+        if (lane == 0) { s_sum[warp][k] = s[k]; s_max[warp][k] = m[k]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        unsigned long long ts = 0;
+        uint32_t tm = 0;
+        for (int w = 0; w < kFrontThreads / 32; ++w) { ts += s_sum[w][threadIdx.x]; tm = max(tm, s_max[w][threadIdx.x]); }
+        atomicAdd(&out[r].sum[threadIdx.x], ts);
+        atomicMax(&out[r].max[threadIdx.x], tm);
+    }
+}
+
 // A4: one block per site, 128 threads; thread w writes window row w (8 floats, 32 B).
 // Row for strand position i:  onehot(seq[i]), lut[own ipd]/952, lut[own pw]/952, lut[opp ipd]/952,
 // lut[opp pw]/952 with IEEE fp32 division, zero-filled outside the read (eval_kmer_features.cpp:36-64).

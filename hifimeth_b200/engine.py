@@ -19,7 +19,7 @@ DEFAULT_MODEL_DIR = PKG.parent / "models"
 
 HM_CTX_CPG, HM_CTX_CHG, HM_CTX_CHH = 1, 2, 4
 HM_CNN_TENSOR, HM_CNN_FP32_SIMT = 0, 1
-HM_SUBMIT_SKIP_H2D, HM_SUBMIT_SKIP_D2H, HM_SUBMIT_MM_TEXT, HM_SUBMIT_ML_HIST = 1, 2, 4, 8
+HM_SUBMIT_SKIP_H2D, HM_SUBMIT_SKIP_D2H, HM_SUBMIT_MM_TEXT, HM_SUBMIT_ML_HIST, HM_SUBMIT_READ_STATS = 1, 2, 4, 8, 16
 
 _u8p = C.POINTER(C.c_uint8)
 _u16p = C.POINTER(C.c_uint16)
@@ -43,9 +43,14 @@ class hm_read_batch(C.Structure):
                 ("flag", _u16p), ("valid", _u8p), ("fi", _u8p), ("fp", _u8p), ("ri", _u8p), ("rp", _u8p)]
 
 
+class hm_read_stats(C.Structure):
+    _fields_ = [("sum", C.c_uint64 * 4), ("max", C.c_uint32 * 4)]
+
+
 class hm_call_batch(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_calls", C.c_uint32), ("call_off", _u32p), ("n_fwd", _u32p), ("qoff", _i32p),
-                ("ml", _u8p), ("n_sites", C.c_uint64 * 3), ("mm_text", _u8p), ("mm_off", _u32p), ("mm_fwd_len", _u32p), ("ml_hist", _u32p)]
+                ("ml", _u8p), ("n_sites", C.c_uint64 * 3), ("mm_text", _u8p), ("mm_off", _u32p), ("mm_fwd_len", _u32p), ("ml_hist", _u32p),
+                ("read_stats", C.POINTER(hm_read_stats))]
 
 
 class hm_timing(C.Structure):
@@ -130,6 +135,8 @@ class CallBatch:
     mm_off: np.ndarray = None
     mm_fwd_len: np.ndarray = None
     ml_hist: np.ndarray = None     # HM_SUBMIT_ML_HIST: [3, 256] ML histograms per context (CpG, CHG, CHH)
+    stats_sum: np.ndarray = None   # HM_SUBMIT_READ_STATS: [n_reads, 4] u64 sums of the decoded frames (fi, fp, ri, rp)
+    stats_max: np.ndarray = None   # [n_reads, 4] u32 maxima
 
     def read_mm(self, r: int):
         """(fwd text, rev text) of read r: the ",d,d,..." runs that follow "C+m" and "G-m" in its MM tag."""
@@ -220,6 +227,10 @@ class Engine:
             out.mm_text = f(_view(c.mm_text, int(out.mm_off[-1]), np.uint8))
         if c.ml_hist:
             out.ml_hist = f(_view(c.ml_hist, 3 * 256, np.uint32)).reshape(3, 256)
+        if c.read_stats:
+            raw = np.ctypeslib.as_array(C.cast(c.read_stats, _u8p), shape=(max(c.n_reads, 1) * C.sizeof(hm_read_stats),))[:c.n_reads * C.sizeof(hm_read_stats)]
+            rec = raw.view(np.dtype([("sum", "<u8", 4), ("max", "<u4", 4)]))
+            out.stats_sum, out.stats_max = rec["sum"].copy(), rec["max"].copy()
         return out
 
     def timing(self, slot: int) -> hm_timing:

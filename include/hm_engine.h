@@ -86,6 +86,13 @@ typedef struct hm_read_batch {
     uint8_t* rp;         /* [n_bases] reverse PW */
 } hm_read_batch;
 
+/* HM_SUBMIT_READ_STATS: per-read sum and maximum of the decoded kinetics frames, planes in the order fi, fp, ri, rp.  Diagnostics
+ * only: the model is fed frames / 952 exactly as the reference does (src/corelib/bam_info.hpp:108); SURVEY.md s8a row A9. */
+typedef struct hm_read_stats {
+    uint64_t sum[4];
+    uint32_t max[4];
+} hm_read_stats;
+
 /* Result of one batch, in engine-owned pinned memory.  For read r the calls are
  * [call_off[r], call_off[r+1]): first n_fwd[r] forward-strand calls (C on the read) with ascending qoff,
  * then the reverse-strand calls (G on the read) with ascending qoff -- exactly the two arrays
@@ -107,6 +114,8 @@ typedef struct hm_call_batch {
     /* HM_SUBMIT_ML_HIST only (else NULL): [3][256] histogram of this batch's ML bytes per context (CpG, CHG, CHH) over reads
      * without flag 0x900 -- what `hifimeth pileup` accumulates to infer its thresholds (src/app/hifimeth/pileup.cpp:237-272). */
     const uint32_t* ml_hist;
+    /* HM_SUBMIT_READ_STATS only (else NULL): [n_reads] */
+    const hm_read_stats* read_stats;
 } hm_call_batch;
 
 /* Device-side timing of the last submit of a slot (CUDA events on the slot's stream). */
@@ -121,6 +130,7 @@ typedef struct hm_timing {
 #define HM_SUBMIT_SKIP_H2D 1u   /* inputs of this slot are already resident in HBM (re-run) */
 #define HM_SUBMIT_SKIP_D2H 2u   /* leave results on the device (kernel-only timing) */
 #define HM_SUBMIT_MM_TEXT 4u    /* also build the MM skip-count text on the device (hm_call_batch.mm_*) */
+#define HM_SUBMIT_READ_STATS 16u /* also reduce every read's decoded kinetics to sum / max per plane (hm_call_batch.read_stats) */
 #define HM_SUBMIT_ML_HIST 8u    /* also histogram the ML bytes per context on the device (hm_call_batch.ml_hist) */
 
 typedef struct hm_engine hm_engine;
@@ -224,7 +234,7 @@ float hm_debug_last_op_ms(void);
 /* ---- kernel microbenchmarks (BASELINE.json config 5) --------------------------------------------------- */
 /* Runs one named kernel family `iters` times on the slot's resident inputs and returns the mean device
  * time per launch (CUDA events) and the algorithmic bytes / flops one launch processes.
- * name: "decode", "scan", "gather", "cnn", "mm" (row N1: MM skip counts + text). */
+ * name: "decode", "scan", "gather", "cnn", "mm" (row N1: MM skip counts + text), "stats" (row A9 diagnostics). */
 int hm_microbench(hm_engine* e, int slot, const char* name, uint32_t n_sites, int iters, float* ms_per_launch,
                   double* algo_bytes, double* algo_flops);
 

@@ -409,3 +409,22 @@ def test_call_cli_two_devices(lib_built, tmp_path):
         r = subprocess.run([str(exe), "call", "-b", "3", "--devices", devs, str(src), str(dst)], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr
     assert synth.read_bam(one)[2] == synth.read_bam(two)[2]
+
+
+def test_read_stats_diagnostics(eng):
+    """Row A9 (diagnostics only): per-read sum / max of the decoded frames of fi, fp, ri, rp from the warp-reduction kernel equal
+    the oracle's decode table applied on the host; asking for them changes nothing else; without the flag the pointer is NULL."""
+    O = hmoracle.oracle()
+    batch, _ = synth.make_reads(9, (300, 7000), seed=4242, flag_rev_every=2, uniform_codes=True)
+    plain = eng.call(batch, slot=1)
+    got = eng.call(batch, flags=hme.HM_SUBMIT_READ_STATS)
+    assert plain.stats_sum is None and got.stats_sum.shape == (batch.n_reads, 4)
+    assert (got.qoff == plain.qoff).all() and (got.ml == plain.ml).all()
+    frames = [O.decode_plane(getattr(batch, k)).astype(np.uint64) for k in ("fi", "fp", "ri", "rp")]
+    for r in range(batch.n_reads):
+        a, b = int(batch.base_off[r]), int(batch.base_off[r + 1])
+        for k in range(4):
+            assert int(got.stats_sum[r, k]) == int(frames[k][a:b].sum()), (r, k)
+            assert int(got.stats_max[r, k]) == int(frames[k][a:b].max()), (r, k)
+    ms, by, _ = eng.microbench(0, "stats", 0, 3)
+    assert ms > 0 and by == 8.0 * batch.n_bases

@@ -12,7 +12,7 @@ peak = json.loads((Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json
 batch, _ = synth.make_reads(1000, 15000, 20261)
 eng = hme.Engine(n_slots=1, max_reads=1000, max_bases=batch.n_bases + 1024)
 eng.call(batch)
-for name, n_sites in (("decode", 0), ("scan", 0), ("mm", 0), ("gather", 1 << 14), ("gather", 1 << 18)):
+for name, n_sites in (("decode", 0), ("scan", 0), ("mm", 0), ("stats", 0), ("gather", 1 << 14), ("gather", 1 << 18)):
     for _ in range(2):
         ms, by, fl = eng.microbench(0, name, n_sites, 20)
     print(json.dumps({"kernel": name, "n_sites": n_sites, "ms_per_launch": ms, "algorithmic_bytes": by, "GB_per_s": by / ms / 1e6,
