@@ -26,16 +26,25 @@ mm_delta_kernel(const uint8_t* __restrict__ bcode, const uint32_t* __restrict__ 
                 uint32_t* __restrict__ delta, uint32_t* __restrict__ block_sum)
 {
     __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_r0;
     const uint32_t k = blockIdx.x * kMmBlock + threadIdx.x;
     uint32_t len = 0;
-    if (k < n_calls) {
-        // read of call k: last r with call_off[r] <= k
+    if (threadIdx.x == 0) {
+        // read of the block's first call: last r with call_off[r] <= k (one binary search per block; calls are ordered by
+        // read, so every other thread walks forward from there -- a read has thousands of calls, a block 1 024)
         uint32_t lo = 0, hi = n_reads;
+        const uint32_t k0 = min(k, n_calls ? n_calls - 1 : 0u);
         while (hi - lo > 1) {
             const uint32_t mid = (lo + hi) >> 1;
-            if (call_off[mid] <= k) lo = mid; else hi = mid;
+            if (call_off[mid] <= k0) lo = mid; else hi = mid;
         }
-        const uint32_t r = lo, a = call_off[r], nf = n_fwd[r], idx = k - a;
+        s_r0 = lo;
+    }
+    __syncthreads();
+    if (k < n_calls) {
+        uint32_t r = s_r0;
+        while (r + 1 < n_reads && call_off[r + 1] <= k) ++r;
+        const uint32_t a = call_off[r], nf = n_fwd[r], idx = k - a;
         const bool rev = idx >= nf;
         const uint8_t target = rev ? 2 : 1;  // G : C in forward-strand codes
         const int32_t q = qoff[k];
@@ -63,25 +72,38 @@ mm_delta_kernel(const uint8_t* __restrict__ bcode, const uint32_t* __restrict__ 
 __global__ void __launch_bounds__(1024)
 mm_scan_blocks_kernel(const uint32_t* __restrict__ block_sum, uint32_t n_blocks, uint32_t* __restrict__ block_off)
 {
-    __shared__ uint32_t s_part[1024];
+    __shared__ uint32_t s_warp[32];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t per = (n_blocks + 1023u) / 1024u;
-    const uint32_t lo = threadIdx.x * per, hi = min(lo + per, n_blocks);
+    const uint32_t lo = min(threadIdx.x * per, n_blocks), hi = min(lo + per, n_blocks);
     uint32_t sum = 0;
     for (uint32_t i = lo; i < hi; ++i) sum += block_sum[i];
-    s_part[threadIdx.x] = sum;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-        uint32_t add = (int)threadIdx.x >= off ? s_part[threadIdx.x - off] : 0u;
-        __syncthreads();
-        s_part[threadIdx.x] += add;
-        __syncthreads();
+    // inclusive scan of the 1 024 partials: shuffles inside a warp, one shared round over the 32 warp totals
+    uint32_t inc = sum;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((int)lane >= o) inc += t;
     }
-    uint32_t run = threadIdx.x ? s_part[threadIdx.x - 1] : 0u;
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = s_warp[lane];
+        uint32_t wi = w;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if ((int)lane >= o) wi += t;
+        }
+        s_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    uint32_t run = s_warp[warp] + inc - sum;
     for (uint32_t i = lo; i < hi; ++i) {
         block_off[i] = run;
         run += block_sum[i];
     }
-    if (threadIdx.x == 1023) block_off[n_blocks] = s_part[1023];
+    if (threadIdx.x == 1023) block_off[n_blocks] = run;
 }
 
 // Pass 3: text offset of every call (text_off[n_calls] = total) and the characters ",<delta>".
