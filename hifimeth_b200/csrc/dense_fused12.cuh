@@ -200,7 +200,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
                             umma::mma2_bf16_w(d_addr, a_hi[k] + sa, bq + b_step, desc_hi, idesc, 1);
                             bq += 2 * b_step;
                         }
-                        umma::mma2_commit_mc(&empty[st]);
+                        // epilogue-1 refills the ring one 32-channel chunk (two stages) at a time: one release per chunk
+                        if (st & 1) umma::mma2_commit_mc(&empty[st]);
                     }
                     b_cur += 2 * b_step * 3u;
                     __syncwarp();
@@ -273,8 +274,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
                 for (int k = 0; k < kMaxScatter; ++k) msc[k] = -1;
             }
             for (int c = (int)half; c < 4; c += 2) {  // 32 channels = stages 2c, 2c + 1
-                umma::mbar_wait(&empty[2 * c], (it & 1u) ^ 1u);
-                umma::mbar_wait(&empty[2 * c + 1], (it & 1u) ^ 1u);
+                umma::mbar_wait(&empty[2 * c + 1], (it & 1u) ^ 1u);  // committed after the second stage of the chunk
                 uint32_t v[32];
                 umma::tmem_ld32(t_addr + 32u * (uint32_t)c, v);
                 umma::tmem_ld_wait();
