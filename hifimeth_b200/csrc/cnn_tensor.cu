@@ -758,10 +758,19 @@ DenseOp patch_op(const DevOp& d, const TensorWorkspaceImpl& s, uint32_t n_tiles,
     return p;
 }
 
+long long* g_f12_dbg = nullptr;
+
 // conv1 + conv2 of `rows` dense rows in one launch (dense_fused12_kernel): tiles of 124 output rows, CTA pairs.
 int launch_fused12(const DevOp& d1, const DevOp& d2, const TensorWorkspaceImpl& s, uint32_t rows, int sm_count, cudaStream_t stream)
 {
     Fused12Op f{};
+    // HM_F12_STAMPS=1: CTA 0 of every launch stamps its first tiles; the last launch's stamps are printed after the batch
+    static const bool stamps = getenv("HM_F12_STAMPS") != nullptr;
+    if (stamps) {
+        if (!g_f12_dbg) cudaMalloc((void**)&g_f12_dbg, 48 * 16 * sizeof(long long));
+        cudaMemsetAsync(g_f12_dbg, 0, 48 * 16 * sizeof(long long), stream);
+        f.dbg = g_f12_dbg;
+    }
     f.n_tiles = (rows + kF12OutRows - 1) / kF12OutRows;
     f.c1 = patch_op(d1, s, f.n_tiles, nullptr);
     f.c2 = patch_op(d2, s, f.n_tiles, nullptr);
@@ -1013,6 +1022,18 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
         ++*launches;
     }
     TCUDA("site lookup", cudaGetLastError());
+    if (g_f12_dbg) {  // HM_F12_STAMPS: where the fused kernel's CTA 0 spent its first tiles (cycles relative to the first stamp)
+        cudaStreamSynchronize(stream);
+        std::vector<long long> h(48 * 16);
+        cudaMemcpy(h.data(), g_f12_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        const long long t0 = h[0];
+        fprintf(stderr, "fused12 stamps (cycles since tile 0): tile: mma1-issue-start mma1-issued t_empty | full[0..7] seen | mma2-issued || epi1: a1_full chunk-a chunk-b | epi2: t_full\n");
+        for (int t = 8; t < 24; ++t) {
+            fprintf(stderr, "%2d:", t);
+            for (int k = 0; k < 16; ++k) fprintf(stderr, " %7lld%s", h[16 * t + k] ? h[16 * t + k] - t0 : -1, (k == 2 || k == 10 || k == 11 || k == 14) ? " |" : "");
+            fprintf(stderr, "\n");
+        }
+    }
     if (timing) timing->top_kernel_launches = dense_launches;
     return 0;
 }

@@ -33,7 +33,10 @@ struct Fused12Op {
     DenseOp c1;        // conv1 form, pair lowering (w_img = [rank 0 half][rank 1 half]); scatter fields = Y1's scatter copies
     DenseOp c2;        // conv2, pair lowering; out / scatter fields = Y2's; seg[] unused (its operand is produced on chip)
     uint32_t n_tiles;  // 124-row tiles
+    long long* dbg;    // HM_F12_STAMPS: CTA 0 writes clock64 stamps of its first 48 tiles, 16 per tile (see kStamp* below)
 };
+// stamp slots per tile: 0 MMA warp reaches issue of MMA1(t+1), 1 MMA1(t+1) issued, 2 t_empty seen, 3..10 full[0..7] seen,
+// 11 MMA2(t) issued; 12 epilogue-1 sees a1_full, 13 / 14 its first / second chunk written; 15 epilogue-2 sees t_full
 
 inline size_t fused12_smem_bytes(const Fused12Op& f)
 {
@@ -97,6 +100,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
     umma::tc_fence_after();
     const uint32_t tmem_base = *s_tmem;  // columns [0,256): A1 x 2, [256,512): A2 x 2
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    long long* const dbg = (blockIdx.x == 0) ? f.dbg : nullptr;
+    auto stamp = [&](uint32_t it, int slot) {
+        if (dbg && it < 48u) dbg[16u * it + (uint32_t)slot] = clock64();
+    };
     uint32_t n_my = 0;  // tiles of this pair
     for (uint32_t t2 = pair; 2 * t2 < f.n_tiles; t2 += n_pairs) ++n_my;
 
@@ -181,15 +188,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
             };
             if (n_my) issue_mma1(0);
             for (uint32_t it = 0; it < n_my; ++it) {
+                if (lane == 0) stamp(it, 0);
                 if (it + 1 < n_my) issue_mma1(it + 1);
+                if (lane == 0) stamp(it, 1);
                 const uint32_t buf = it & 1u, use = it >> 1;
                 umma::mbar_wait(&t_empty[buf], (use & 1u) ^ 1u);
                 umma::tc_fence_after();
+                if (lane == 0) stamp(it, 2);
                 const uint32_t d_addr = tmem_base + 256u + buf * 128u;
                 uint32_t b_cur = b2_base;
                 for (int st = 0; st < kStages; ++st) {
                     umma::mbar_wait(&full[st], it & 1u);
                     umma::tc_fence_after();
+                    if (lane == 0) stamp(it, 3 + st);
                     if (umma::elect_one()) {
                         const uint32_t sa = ring16 + (uint32_t)st * stage16;
                         uint32_t bq = b_cur;
@@ -208,6 +219,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
                 }
                 if (umma::elect_one()) umma::mma2_commit_mc(&t_full[buf]);
                 __syncwarp();
+                if (lane == 0) stamp(it, 11);
             }
         } else {
             umma::mbar_wait(w_full, 0);
@@ -223,6 +235,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
             const uint32_t buf = it & 1u, use = it >> 1;
             umma::mbar_wait(&t_full[buf], use & 1u);
             umma::tc_fence_after();
+            if (threadIdx.x == 32u * (kProducerWarps + 1)) stamp(it, 15);
             const uint32_t t_addr = tmem_base + (lane_grp << 16) + 256u + buf * 128u;
             const unsigned long long row = (unsigned long long)(2 * t2 + rank) * kF12OutRows + m;
             const bool keep = m < (uint32_t)kF12OutRows;
@@ -263,9 +276,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
         uint32_t it = 0;
         for (uint32_t t2 = pair; 2 * t2 < f.n_tiles; t2 += n_pairs, ++it) {
             const uint32_t buf = it & 1u, use = it >> 1;
-            umma::mbar_wait(&a1_full[buf], use & 1u);
-            umma::tc_fence_after();
-            const uint32_t t_addr = tmem_base + (lane_grp << 16) + buf * 128u;
+            // the site-row lookups do not depend on the accumulator: issue them before waiting for it
             const unsigned long long row = (unsigned long long)(2 * t2 + rank) * kF12OutRows + m;
             int msc[kMaxScatter];
             scatter_rows(c1, row, msc);
@@ -273,6 +284,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
                 #pragma unroll
                 for (int k = 0; k < kMaxScatter; ++k) msc[k] = -1;
             }
+            umma::mbar_wait(&a1_full[buf], use & 1u);
+            umma::tc_fence_after();
+            const bool stamper = threadIdx.x == 32u * (kProducerWarps + 1 + kEpilogueWarps);
+            if (stamper) stamp(it, 12);
+            const uint32_t t_addr = tmem_base + (lane_grp << 16) + buf * 128u;
             for (int c = (int)half; c < 4; c += 2) {  // 32 channels = stages 2c, 2c + 1
                 umma::mbar_wait(&empty[2 * c + 1], (it & 1u) ^ 1u);  // committed after the second stage of the chunk
                 uint32_t v[32];
@@ -310,19 +326,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
                     *reinterpret_cast<uint4*>(st + (uint32_t)(g & 1) * pl_bytes) = vh[g];
                     *reinterpret_cast<uint4*>(st + (uint32_t)(2 + (g & 1)) * pl_bytes) = vl[g];
                 }
-                // Y1's scatter copies (compact rows are consecutive, so these fill whole lines)
-                #pragma unroll
-                for (int k = 0; k < kMaxScatter; ++k) {
-                    if (msc[k] >= 0) {
-                        uint8_t* q_hi = c1.sc_out[k] + (unsigned long long)(4 * c) * c1.sc_plane_stride + (unsigned long long)msc[k] * 16ull;
-                        uint8_t* q_lo = q_hi + (unsigned long long)c1.out_groups * c1.sc_plane_stride;
-                        #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            *reinterpret_cast<uint4*>(q_hi + g * c1.sc_plane_stride) = vh[g];
-                            *reinterpret_cast<uint4*>(q_lo + g * c1.sc_plane_stride) = vl[g];
-                        }
-                    }
-                }
                 umma::fence_proxy_async();  // the tensor core (async proxy) reads what these threads just wrote
                 umma::tc_fence_before();
                 __syncwarp();
@@ -337,6 +340,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
                         umma::mbar_arrive_cluster(umma::mapa(umma::smem_u32(&full[2 * c + 1]), 0));
                     }
                 }
+                // Y1's scatter copies (compact rows are consecutive, so these fill whole lines).  AFTER the hand-over: the proxy fence
+                // above is a memory barrier for this thread, and in front of it these global stores made every chunk wait for their
+                // acknowledgement (HM_F12_STAMPS: ~4 000 cycles per chunk; 3 300 with the stores behind the arrive).  Giving them to
+                // four dedicated warps instead was slower still: one warp needs ~2 200 cycles per 32-column chunk.
+                #pragma unroll
+                for (int k = 0; k < kMaxScatter; ++k) {
+                    if (msc[k] >= 0) {
+                        uint8_t* q_hi = c1.sc_out[k] + (unsigned long long)(4 * c) * c1.sc_plane_stride + (unsigned long long)msc[k] * 16ull;
+                        uint8_t* q_lo = q_hi + (unsigned long long)c1.out_groups * c1.sc_plane_stride;
+                        #pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            *reinterpret_cast<uint4*>(q_hi + g * c1.sc_plane_stride) = vh[g];
+                            *reinterpret_cast<uint4*>(q_lo + g * c1.sc_plane_stride) = vl[g];
+                        }
+                    }
+                }
+                if (stamper) stamp(it, c < 2 ? 13 : 14);
             }
         }
     }
