@@ -34,7 +34,7 @@ constexpr int kMaxTerms = 3;
 constexpr int kMaxSegs = 3;
 constexpr int kMaxScatter = 5;
 constexpr int kProducerWarps = 8;
-constexpr int kEpilogueWarps = 8;  // two per TMEM lane group; 32-column chunks alternate between the two
+constexpr int kEpilogueWarps = 8;  // two per TMEM lane group; each takes half of the accumulator columns
 constexpr int kDenseThreads = 32 * (kProducerWarps + 1 + kEpilogueWarps);
 
 struct DenseSeg {
@@ -97,14 +97,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
-// Epilogue of one 32-column chunk of one row: ReLU'd values -> hi/lo bf16 -> the op's own map (plane layout) and the
-// compact scatter copies.  msc[k] = compact row for scatter k, or -1.
-__device__ __forceinline__ void epilogue_store_chunk(const DenseOp& op, unsigned long long row, int c0, const float (&f)[32],
-                                                     const int (&msc)[kMaxScatter], bool skip_store)
+// Epilogue of one chunk of NG 8-column groups (32 or 16 columns) of one row: ReLU'd values -> hi/lo bf16 -> the op's own map
+// (plane layout) and the compact scatter copies.  msc[k] = compact row for scatter k, or -1.
+template <int NG>
+__device__ __forceinline__ void epilogue_store_groups(const DenseOp& op, unsigned long long row, int c0, const float (&f)[8 * NG],
+                                                      const int (&msc)[kMaxScatter], bool skip_store)
 {
-    uint4 vh[4], vl[4];
+    uint4 vh[NG], vl[NG];
     #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < NG; ++g) {
         uint32_t hi[4], lo[4];
         #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -125,7 +126,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const DenseOp& op, unsigned
         uint8_t* p_hi = op.out + (unsigned long long)g0 * op.out_plane_stride + row * 16ull;
         uint8_t* p_lo = p_hi + (unsigned long long)op.out_groups * op.out_plane_stride;
         #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < NG; ++g) {
             *reinterpret_cast<uint4*>(p_hi + g * op.out_plane_stride) = vh[g];
             *reinterpret_cast<uint4*>(p_lo + g * op.out_plane_stride) = vl[g];
         }
@@ -137,10 +138,61 @@ __device__ __forceinline__ void epilogue_store_chunk(const DenseOp& op, unsigned
             uint8_t* q_hi = op.sc_out[k] + (unsigned long long)g0 * op.sc_plane_stride + (unsigned long long)msc[k] * 16ull;
             uint8_t* q_lo = q_hi + (unsigned long long)op.out_groups * op.sc_plane_stride;
             #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < NG; ++g) {
                 *reinterpret_cast<uint4*>(q_hi + g * op.sc_plane_stride) = vh[g];
                 *reinterpret_cast<uint4*>(q_lo + g * op.sc_plane_stride) = vl[g];
             }
+        }
+    }
+}
+
+__device__ __forceinline__ void epilogue_store_chunk(const DenseOp& op, unsigned long long row, int c0, const float (&f)[32],
+                                                     const int (&msc)[kMaxScatter], bool skip_store)
+{
+    epilogue_store_groups<4>(op, row, c0, f, msc, skip_store);
+}
+
+// Map-form epilogue of one tile row: the N accumulator columns are split evenly between the two warps of a TMEM lane group at
+// 16-column granularity (N = 96 -> 48 + 48: with 32-column chunks one warp had two chunks and the other one, and a chunk costs
+// one warp ~2 200 cycles -- the N = 96 layers were epilogue-bound at 4 400 cycles per tile against 3 456 cycles of MMAs).
+__device__ __forceinline__ void epilogue_map_row(const DenseOp& op, uint32_t t_addr, unsigned long long row, uint32_t half, const float* s_bias,
+                                                 const int (&msc)[kMaxScatter], bool skip_store)
+{
+    const int n = op.n;
+    const int mid = ((n >> 1) + 15) & ~15;
+    int c0 = half ? mid : 0;
+    const int c1 = half ? n : mid;
+    while (c0 < c1) {
+        if (c1 - c0 >= 32) {
+            uint32_t v[32];
+            umma::tmem_ld32(t_addr + (uint32_t)c0, v);
+            umma::tmem_ld_wait();
+            float f[32];
+            #pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 bv = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+                f[j] = fmaxf(__uint_as_float(v[j]) + bv.x, 0.f);
+                f[j + 1] = fmaxf(__uint_as_float(v[j + 1]) + bv.y, 0.f);
+                f[j + 2] = fmaxf(__uint_as_float(v[j + 2]) + bv.z, 0.f);
+                f[j + 3] = fmaxf(__uint_as_float(v[j + 3]) + bv.w, 0.f);
+            }
+            epilogue_store_groups<4>(op, row, c0, f, msc, skip_store);
+            c0 += 32;
+        } else {
+            uint32_t v[16];
+            umma::tmem_ld16(t_addr + (uint32_t)c0, v);
+            umma::tmem_ld_wait();
+            float f[16];
+            #pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const float4 bv = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+                f[j] = fmaxf(__uint_as_float(v[j]) + bv.x, 0.f);
+                f[j + 1] = fmaxf(__uint_as_float(v[j + 1]) + bv.y, 0.f);
+                f[j + 2] = fmaxf(__uint_as_float(v[j + 2]) + bv.z, 0.f);
+                f[j + 3] = fmaxf(__uint_as_float(v[j + 3]) + bv.w, 0.f);
+            }
+            epilogue_store_groups<2>(op, row, c0, f, msc, skip_store);
+            c0 += 16;
         }
     }
 }
@@ -364,10 +416,10 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel_t(const __
             float l0 = 0.f, l1 = 0.f;
             int msc[kMaxScatter];
             scatter_rows(op, row, msc);
-            // map form: chunks alternate between the two warps of a lane group; head form: the first warp does all
-            const int c_first = op.mode == 0 ? (int)half * 32 : 0, c_step = op.mode == 0 ? 64 : 32;
-            const int c_end = (op.mode == 0 || half == 0) && !(variant & 8u) ? n : 0;
-            for (int c0 = c_first; c0 < c_end; c0 += c_step) {
+            // map form: the columns are split between the two warps of a lane group; head form: the first warp does all
+            if (op.mode == 0 && !(variant & 8u)) epilogue_map_row(op, t_addr, row, half, s_bias, msc, (variant & 4u) != 0);
+            const int c_end = (op.mode == 1 && half == 0 && !(variant & 8u)) ? n : 0;
+            for (int c0 = 0; c0 < c_end; c0 += 32) {
                 uint32_t v[32];
                 umma::tmem_ld32(t_addr + (uint32_t)c0, v);
                 umma::tmem_ld_wait();
@@ -380,14 +432,10 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel_t(const __
                     f[j + 2] = fmaxf(__uint_as_float(v[j + 2]) + bv.z, 0.f);
                     f[j + 3] = fmaxf(__uint_as_float(v[j + 3]) + bv.w, 0.f);
                 }
-                if (op.mode == 0) {
-                    epilogue_store_chunk(op, row, c0, f, msc, (variant & 4u) != 0);
-                } else {
-                    #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        l0 = fmaf(f[j], s_bias[256 + c0 + j], l0);
-                        l1 = fmaf(f[j], s_bias[512 + c0 + j], l1);
-                    }
+                #pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    l0 = fmaf(f[j], s_bias[256 + c0 + j], l0);
+                    l1 = fmaf(f[j], s_bias[512 + c0 + j], l1);
                 }
             }
             umma::tc_fence_before();

@@ -167,21 +167,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) de
             const unsigned long long row = (unsigned long long)(2 * t2 + rank) * kTileRows + m;
             int msc[kMaxScatter];
             scatter_rows(op, row, msc);
-            for (int c0 = (int)half * 32; c0 < n; c0 += 64) {
-                uint32_t v[32];
-                umma::tmem_ld32(t_addr + (uint32_t)c0, v);
-                umma::tmem_ld_wait();
-                float f[32];
-                #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 bv = *reinterpret_cast<const float4*>(s_bias + c0 + j);
-                    f[j] = fmaxf(__uint_as_float(v[j]) + bv.x, 0.f);
-                    f[j + 1] = fmaxf(__uint_as_float(v[j + 1]) + bv.y, 0.f);
-                    f[j + 2] = fmaxf(__uint_as_float(v[j + 2]) + bv.z, 0.f);
-                    f[j + 3] = fmaxf(__uint_as_float(v[j + 3]) + bv.w, 0.f);
-                }
-                epilogue_store_chunk(op, row, c0, f, msc, false);
-            }
+            epilogue_map_row(op, t_addr, row, half, s_bias, msc, false);
             umma::tc_fence_before();
             __syncwarp();
             if (lane == 0) {
