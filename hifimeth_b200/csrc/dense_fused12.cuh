@@ -233,10 +233,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
         uint32_t it = 0;
         for (uint32_t t2 = pair; 2 * t2 < f.n_tiles; t2 += n_pairs, ++it) {
             const uint32_t buf = it & 1u, use = it >> 1;
-            umma::mbar_wait(&t_full[buf], use & 1u);
-            umma::tc_fence_after();
-            if (threadIdx.x == 32u * (kProducerWarps + 1)) stamp(it, 15);
-            const uint32_t t_addr = tmem_base + (lane_grp << 16) + 256u + buf * 128u;
+            // the site-row lookups do not depend on the accumulator: issue them before waiting for it
             const unsigned long long row = (unsigned long long)(2 * t2 + rank) * kF12OutRows + m;
             const bool keep = m < (uint32_t)kF12OutRows;
             int msc[kMaxScatter];
@@ -245,6 +242,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
                 #pragma unroll
                 for (int k = 0; k < kMaxScatter; ++k) msc[k] = -1;
             }
+            umma::mbar_wait(&t_full[buf], use & 1u);
+            umma::tc_fence_after();
+            if (threadIdx.x == 32u * (kProducerWarps + 1)) stamp(it, 15);
+            const uint32_t t_addr = tmem_base + (lane_grp << 16) + 256u + buf * 128u;
             for (int c0 = (int)half * 32; c0 < 128; c0 += 64) {
                 uint32_t v[32];
                 umma::tmem_ld32(t_addr + (uint32_t)c0, v);

@@ -409,13 +409,14 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel_t(const __
         uint32_t it = 0;
         for (uint32_t tile = blockIdx.x; tile < op.n_tiles; tile += gridDim.x, ++it) {
             const uint32_t buf = it & 1u, use = it >> 1;
-            umma::mbar_wait(&t_full[buf], use & 1u);
-            umma::tc_fence_after();
-            const uint32_t t_addr = tmem_base + (lane_grp << 16) + buf * acc_stride;
+            // the site-row lookups do not depend on the accumulator: issue them before waiting for it
             const unsigned long long row = (unsigned long long)tile * kTileRows + m;
             float l0 = 0.f, l1 = 0.f;
             int msc[kMaxScatter];
             scatter_rows(op, row, msc);
+            umma::mbar_wait(&t_full[buf], use & 1u);
+            umma::tc_fence_after();
+            const uint32_t t_addr = tmem_base + (lane_grp << 16) + buf * acc_stride;
             // map form: the columns are split between the two warps of a lane group; head form: the first warp does all
             if (op.mode == 0 && !(variant & 8u)) epilogue_map_row(op, t_addr, row, half, s_bias, msc, (variant & 4u) != 0);
             const int c_end = (op.mode == 1 && half == 0 && !(variant & 8u)) ? n : 0;

@@ -161,12 +161,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) de
         uint32_t it = 0;
         for (uint32_t t2 = pair; 2 * t2 < op.n_tiles; t2 += n_pairs, ++it) {
             const uint32_t buf = it & 1u, use = it >> 1;
-            umma::mbar_wait(&t_full[buf], use & 1u);
-            umma::tc_fence_after();
-            const uint32_t t_addr = tmem_base + (lane_grp << 16) + buf * acc_stride;
+            // the site-row lookups do not depend on the accumulator: issue them before waiting for it
             const unsigned long long row = (unsigned long long)(2 * t2 + rank) * kTileRows + m;
             int msc[kMaxScatter];
             scatter_rows(op, row, msc);
+            umma::mbar_wait(&t_full[buf], use & 1u);
+            umma::tc_fence_after();
+            const uint32_t t_addr = tmem_base + (lane_grp << 16) + buf * acc_stride;
             epilogue_map_row(op, t_addr, row, half, s_bias, msc, false);
             umma::tc_fence_before();
             __syncwarp();

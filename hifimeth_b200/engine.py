@@ -8,13 +8,14 @@ B200 raises HmError.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from pathlib import Path
 
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libhm_engine.so"
+LIB_PATH = Path(os.environ["HM_ENGINE_LIB"]) if os.environ.get("HM_ENGINE_LIB") else PKG / "libhm_engine.so"  # override: A/B runs of two builds
 DEFAULT_MODEL_DIR = PKG.parent / "models"
 
 HM_CTX_CPG, HM_CTX_CHG, HM_CTX_CHH = 1, 2, 4
