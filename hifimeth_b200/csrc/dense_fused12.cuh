@@ -27,7 +27,8 @@ namespace hm {
 constexpr int kF12OutRows = 124;  // conv2 rows per CTA tile (128 - the reach of conv2's taps)
 constexpr int kF12XRing = 4;
 constexpr int kF12Epi1Warps = 8;  // two per TMEM lane group; 32-channel chunks alternate between the two
-constexpr int kF12Threads = 32 * (kProducerWarps + 1 + kEpilogueWarps + kF12Epi1Warps);
+constexpr int kF12ProducerWarps = kF12XRing;  // one per X ring slot; fewer threads than the other kernels: 96 registers for the epilogues
+constexpr int kF12Threads = 32 * (kF12ProducerWarps + 1 + kEpilogueWarps + kF12Epi1Warps);
 
 struct Fused12Op {
     DenseOp c1;        // conv1 form, pair lowering (w_img = [rank 0 half][rank 1 half]); scatter fields = Y1's scatter copies
@@ -107,7 +108,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
     uint32_t n_my = 0;  // tiles of this pair
     for (uint32_t t2 = pair; 2 * t2 < f.n_tiles; t2 += n_pairs) ++n_my;
 
-    if (warp < (uint32_t)kProducerWarps) {
+    if (warp < (uint32_t)kF12ProducerWarps) {
         // ===================================== producers: weights once, then the X ring =====================================
         if (warp == 0) {
             if (lane == 0) umma::mbar_arrive_expect_tx(w_full, c1.w_bytes + c2.w_bytes);
@@ -146,7 +147,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
                 }
             }
         }
-    } else if (warp == (uint32_t)kProducerWarps) {
+    } else if (warp == (uint32_t)kF12ProducerWarps) {
         if (rank == 0) {
             // ===================================== MMA issuer (leader) =====================================================
             const uint32_t idesc = umma::make_idesc_bf16_m256(128u);
@@ -225,10 +226,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
             umma::mbar_wait(w_full, 0);
             if (lane == 0) umma::mbar_arrive_cluster(umma::mapa(umma::smem_u32(w_full), 0));
         }
-    } else if (warp < (uint32_t)(kProducerWarps + 1 + kEpilogueWarps)) {
+    } else if (warp < (uint32_t)(kF12ProducerWarps + 1 + kEpilogueWarps)) {
         // ===================================== epilogue-2: A2 -> Y2 in HBM (own CTA's 124 rows) ===============================
         const uint32_t lane_grp = (warp & 3u) * 32u;
-        const uint32_t half = (warp - (uint32_t)(kProducerWarps + 1)) >> 2;
+        const uint32_t half = (warp - (uint32_t)(kF12ProducerWarps + 1)) >> 2;
         const uint32_t m = lane_grp + lane;
         uint32_t it = 0;
         for (uint32_t t2 = pair; 2 * t2 < f.n_tiles; t2 += n_pairs, ++it) {
@@ -244,7 +245,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
             }
             umma::mbar_wait(&t_full[buf], use & 1u);
             umma::tc_fence_after();
-            if (threadIdx.x == 32u * (kProducerWarps + 1)) stamp(it, 15);
+            if (threadIdx.x == 32u * (kF12ProducerWarps + 1)) stamp(it, 15);
             const uint32_t t_addr = tmem_base + (lane_grp << 16) + 256u + buf * 128u;
             for (int c0 = (int)half * 32; c0 < 128; c0 += 64) {
                 uint32_t v[32];
@@ -271,7 +272,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
     } else {
         // ===================================== epilogue-1: A1 -> the A ring (+ Y1's scatter copies) ==========================
         const uint32_t lane_grp = (warp & 3u) * 32u;
-        const uint32_t half = (warp - (uint32_t)(kProducerWarps + 1 + kEpilogueWarps)) >> 2;  // chunks half, half + 2
+        const uint32_t half = (warp - (uint32_t)(kF12ProducerWarps + 1 + kEpilogueWarps)) >> 2;  // chunks half, half + 2
         const uint32_t m = lane_grp + lane;
         const uint32_t pl_bytes = c2.seg[0].nrows * 16u;  // one plane of a stage: 132 rows x 16 B
         uint32_t it = 0;
@@ -287,7 +288,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
             }
             umma::mbar_wait(&a1_full[buf], use & 1u);
             umma::tc_fence_after();
-            const bool stamper = threadIdx.x == 32u * (kProducerWarps + 1 + kEpilogueWarps);
+            const bool stamper = threadIdx.x == 32u * (kF12ProducerWarps + 1 + kEpilogueWarps);
             if (stamper) stamp(it, 12);
             const uint32_t t_addr = tmem_base + (lane_grp << 16) + buf * 128u;
             for (int c = (int)half; c < 4; c += 2) {  // 32 channels = stages 2c, 2c + 1
