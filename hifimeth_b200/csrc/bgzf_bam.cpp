@@ -19,6 +19,7 @@ namespace hm {
 namespace {
 constexpr size_t kBlockPayload = 0xff00;      // uncompressed bytes per BGZF block (htslib's BGZF_BLOCK_SIZE)
 constexpr size_t kReadSlab = 16u << 20;       // compressed bytes read per slab (~260 blocks: enough to spread over the threads)
+constexpr uint32_t kMaxRecord = 1u << 29;    // a block_size above 512 MiB is corruption, not a record
 constexpr size_t kReadAhead = 3;              // inflated slabs queued ahead of the consumer
 constexpr size_t kWriteBatch = 1024;          // blocks deflated per parallel batch (~64 MB)
 
@@ -209,6 +210,7 @@ bool BgzfReader::inflate_more(std::vector<uint8_t>& out, std::string& err)
             if (!bs || off + bs > raw_.size()) break;
             if (bs < 26) { err = "corrupt BGZF block"; return false; }
             const size_t isize = rd32(raw_.data() + off + bs - 4);
+            if (isize > 65536) { err = "corrupt BGZF block (ISIZE above 64 KiB)"; return false; }  // BGZF payloads are <= 64 KiB
             blks.push_back({off, bs, isize, total});
             total += isize;
             off += bs;
@@ -360,6 +362,7 @@ bool BamReader::open(const char* path, int threads, BamHeader& hdr, std::string&
     if (!read_bytes(h, 8, err)) { if (err.empty()) err = "empty BAM file"; return false; }
     if (memcmp(h, "BAM\1", 4) != 0) { err = "bad BAM magic"; return false; }
     const uint32_t l_text = rd32(h + 4);
+    if (l_text > kMaxRecord) { err = "corrupt BAM header"; return false; }
     hdr.text.assign(l_text, '\0');
     uint8_t nr[4];
     if (!read_bytes(reinterpret_cast<uint8_t*>(&hdr.text[0]), l_text, err) || !read_bytes(nr, 4, err)) { if (err.empty()) err = "truncated BAM header"; return false; }
@@ -370,6 +373,7 @@ bool BamReader::open(const char* path, int threads, BamHeader& hdr, std::string&
         uint8_t ln[4];
         if (!read_bytes(ln, 4, err)) { if (err.empty()) err = "truncated BAM references"; return false; }
         const uint32_t l_name = rd32(ln);
+        if (l_name > 65536 || hdr.refs.size() > kMaxRecord) { err = "corrupt BAM references"; return false; }
         const size_t at = hdr.refs.size();
         hdr.refs.resize(at + 4 + (size_t)l_name + 4);
         memcpy(hdr.refs.data() + at, ln, 4);
@@ -389,7 +393,7 @@ bool BamReader::next(const uint8_t*& body, size_t& len, std::string& err)
         const size_t avail = cur_->data.size() - pos_;
         if (avail >= 4) {
             const uint32_t bs = rd32(cur_->data.data() + pos_);
-            if (bs < 32) { err = "corrupt BAM record"; return false; }
+            if (bs < 32 || bs > kMaxRecord) { err = "corrupt BAM record"; return false; }
             if (avail >= 4 + (size_t)bs) {  // fast path: the record lies inside the current slab
                 body = cur_->data.data() + pos_ + 4;
                 len = bs;
@@ -403,7 +407,7 @@ bool BamReader::next(const uint8_t*& body, size_t& len, std::string& err)
     uint8_t lw[4];
     if (!read_bytes(lw, 4, err)) { if (err.empty()) err = "truncated BAM record"; return false; }
     const uint32_t bs = rd32(lw);
-    if (bs < 32) { err = "corrupt BAM record"; return false; }
+    if (bs < 32 || bs > kMaxRecord) { err = "corrupt BAM record"; return false; }
     std::vector<uint8_t> tmp(bs);
     if (!read_bytes(tmp.data(), bs, err)) { if (err.empty()) err = "truncated BAM record"; return false; }
     cur_->extra.push_back(std::move(tmp));

@@ -19,6 +19,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <exception>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -469,7 +470,22 @@ void writer_thread(Shared& S, hm::BamWriter& out)
 
 }  // namespace
 
+static int call_main_impl(int argc, char** argv);
+
+// Nothing throws across the C boundary: an allocation failure or any other exception ends the run with EXIT_FAILURE.
 extern "C" int hm_call_main(int argc, char** argv)
+{
+    try {
+        return call_main_impl(argc, argv);
+    } catch (const std::exception& e) {
+        fprintf(stderr, "[hifimeth-b200] fatal: %s\n", e.what());
+    } catch (...) {
+        fprintf(stderr, "[hifimeth-b200] fatal: unknown exception\n");
+    }
+    return EXIT_FAILURE;
+}
+
+static int call_main_impl(int argc, char** argv)
 {
     if (argc < 2) { fprintf(stderr, "usage: %s call [OPTIONS] BAM MOD-BAM\n", argc ? argv[0] : "hifimeth-b200"); return EXIT_FAILURE; }
     Options opt;
@@ -546,6 +562,7 @@ extern "C" int hm_call_main(int argc, char** argv)
 // Round trip of the BAM codec alone (tests): read every record of `in_path`, write it unchanged to `out_path`.
 extern "C" int hm_bam_copy(const char* in_path, const char* out_path, int threads, int level)
 {
+    try {
     std::string err;
     hm::BamReader in;
     hm::BamHeader hdr;
@@ -562,4 +579,7 @@ extern "C" int hm_bam_copy(const char* in_path, const char* out_path, int thread
     if (!err.empty()) return HM_ERR_FORMAT;
     if (!out.close(err)) return HM_ERR_ARG;
     return (int)std::min<long long>(n, 0x7fffffff);
+    } catch (...) {
+        return HM_ERR_FORMAT;
+    }
 }

@@ -64,3 +64,60 @@ def test_call_cli_usage_errors(lib_built):
     assert r.returncode != 0
     r = subprocess.run([str(exe), "call", "only-one-path.bam"], capture_output=True, text=True)
     assert r.returncode != 0
+
+
+def test_bam_reader_survives_corruption(lib_built, tmp_path):
+    """Fuzz of the BGZF/BAM reader: truncations and random byte damage of a valid file (headers, BSIZE / ISIZE / CRC fields,
+    deflate streams, record lengths after re-compression) must end in an error code or a clean copy -- never in a crash, a hang
+    or an unbounded allocation.  Runs in a child process so that a crash is a test failure, not the end of the session."""
+    import subprocess
+    import sys
+    import zlib
+
+    _, reads = synth.make_reads(12, (300, 4000), seed=99)
+    bodies = [synth.record_body(r) for r in reads]
+    good = tmp_path / "good.bam"
+    synth.write_bam(good, bodies, level=1, block=20000)
+    raw = bytearray(good.read_bytes())
+    rng = np.random.default_rng(7)
+    cases = []
+    for cut in (0, 10, 17, 28, 100, len(raw) // 3, len(raw) - 29, len(raw) - 1):
+        cases.append(bytes(raw[:cut]))
+    for _ in range(60):
+        b = bytearray(raw)
+        for _ in range(int(rng.integers(1, 4))):
+            b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        cases.append(bytes(b))
+    # damage INSIDE the BAM stream (valid BGZF around it): record lengths, header lengths
+    text, refs, _ = synth.read_bam(good)
+    import gzip
+    stream = bytearray(gzip.decompress(bytes(raw)))
+    for pos, val in ((4, 0xffffffff), (4, 0x7fffffff), (8 + len(text), 0x10000000), (8 + len(text) + 4, 0xfffffff0),
+                     (8 + len(text) + 4, 5), (8 + len(text) + 4 + 16, 0x7fffffff)):
+        s2 = bytearray(stream)
+        s2[pos:pos + 4] = int(val).to_bytes(4, "little")
+        out = bytearray()
+        for off in range(0, len(s2), 0xff00):
+            chunk = bytes(s2[off:off + 0xff00])
+            co = zlib.compressobj(1, zlib.DEFLATED, -15)
+            comp = co.compress(chunk) + co.flush()
+            out += bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0]) + (len(comp) + 25).to_bytes(2, "little")
+            out += comp + (zlib.crc32(chunk) & 0xffffffff).to_bytes(4, "little") + len(chunk).to_bytes(4, "little")
+        cases.append(bytes(out))
+    for i, c in enumerate(cases):
+        (tmp_path / f"case{i}.bam").write_bytes(c)
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from hifimeth_b200 import engine as hme\n"
+        "lib = hme.load_library()\n"
+        "res = []\n"
+        "for i in range(%d):\n"
+        "    res.append(lib.hm_bam_copy((%r + '/case%%d.bam' %% i).encode(), (%r + '/out.bam').encode(), 3, 1))\n"
+        "print(' '.join(map(str, res)))\n" % (str(hme.PKG.parent), len(cases), str(tmp_path), str(tmp_path)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
+    res = [int(x) for x in r.stdout.split()]
+    assert len(res) == len(cases)
+    assert all(x < 0 for x in res[:8])             # every truncation is an error
+    assert all(x < 0 or x <= len(bodies) + 2 for x in res)
+    assert sum(x < 0 for x in res) > len(res) // 2  # most random damage is caught (CRC / structure)
