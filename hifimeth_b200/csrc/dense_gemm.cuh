@@ -13,7 +13,7 @@
 // (8 rows x 16 B, SWIZZLE_NONE, K-major), so a convolution tap is a descriptor whose start address is advanced by
 // shift * 16 bytes -- no im2col, no re-load per tap.
 //
-// CTA = 13 warps, persistent over tiles (grid = #SMs):
+// CTA = 17 warps, persistent over tiles (grid = #SMs):
 //   warps 0-7 producers: weights once (resident for the whole launch), then the activation ring; ring slot s is always
 //             filled by warp s (a warp has one bulk-copy instruction in flight at a time, tools/bulk_copy_probe.cu, so
 //             the number of stages in flight is the number of producer warps)
