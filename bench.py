@@ -271,7 +271,7 @@ def main():
             "e2e": {"value": sites_all * args.steps / e2e_s, "unit": "sites/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         # DRAM read+write of the kernel family per step: ncu, profiles/r1_launches_v8_fused12_grouped.csv (51.3 GB
+                         # DRAM read+write of the kernel family per step: ncu, profiles/r1_launches_v9_final.csv (51.3 GB
                          # for a 128-read step, scaled by reads; 58.2 GB before conv1 + conv2 were fused)
                          "traffic": 51.3e9 * args.reads / 128.0, "traffic_unit": "bytes per step",
                          "kernel": "dense_gemm2_kernel + dense_fused12_kernel + dense_gemm_kernel (every op of the dense plan)", "launches_per_step": top_launches // max(args.steps, 1), "peak_source": peak_src,
