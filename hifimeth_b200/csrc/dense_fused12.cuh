@@ -68,7 +68,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
     uint64_t* t_full = a1_full + 2;                 // [2]  multicast commit: MMA2 of a tile has completed
     uint64_t* t_empty = t_full + 2;                 // [2]  leader only: one arrive per epilogue-2 warp of both CTAs
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(t_empty + 2);
-    float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(t_empty + 3) + 15) & ~(uintptr_t)15);  // [0,128) conv1, [128,256) conv2
+    // as an offset from the shared-memory array, so that the compiler keeps the accesses in the shared state space (through a
+    // uintptr_t round trip they became generic LD / ST: long-scoreboard latency and a queue shared with the global stores)
+    float* s_bias = reinterpret_cast<float*>(smem + (((uint32_t)(reinterpret_cast<uint8_t*>(t_empty + 3) - smem) + 15u) & ~15u));  // [0,128) conv1, [128,256) conv2
 
     if (warp == 0) {
         if (lane == 0) {

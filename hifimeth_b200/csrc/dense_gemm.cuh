@@ -222,7 +222,9 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel_t(const __
     uint64_t* t_full = w_full + 1;          // [2]
     uint64_t* t_empty = t_full + 2;         // [2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(t_empty + 2);
-    float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(t_empty + 3) + 15) & ~(uintptr_t)15);  // [768]: bias | fc2 row 0 | fc2 row 1
+    // as an offset from the shared-memory array, so that the compiler keeps the accesses in the shared state space (through a
+    // uintptr_t round trip they became generic LD / ST: long-scoreboard latency and a queue shared with the global stores)
+    float* s_bias = reinterpret_cast<float*>(smem + (((uint32_t)(reinterpret_cast<uint8_t*>(t_empty + 3) - smem) + 15u) & ~15u));  // [768]: bias | fc2 row 0 | fc2 row 1
 
     bool any_gather = false, any_bulk = false;
     for (int s = 0; s < op.n_segs; ++s) {

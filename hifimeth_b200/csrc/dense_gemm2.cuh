@@ -29,7 +29,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) de
     uint64_t* t_full = w_full + 1;          // [2]     multicast commit from the leader
     uint64_t* t_empty = t_full + 2;         // [2]     leader only: one arrive per epilogue warp of both CTAs
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(t_empty + 2);
-    float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(t_empty + 3) + 15) & ~(uintptr_t)15);
+    // as an offset from the shared-memory array, so that the compiler keeps the accesses in the shared state space (through a
+    // uintptr_t round trip they became generic LD / ST: long-scoreboard latency and a queue shared with the global stores)
+    float* s_bias = reinterpret_cast<float*>(smem + (((uint32_t)(reinterpret_cast<uint8_t*>(t_empty + 3) - smem) + 15u) & ~15u));
 
     if (warp == 0) {
         if (lane == 0) {
