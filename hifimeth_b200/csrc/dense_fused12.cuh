@@ -234,17 +234,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
         const uint32_t half = (warp - (uint32_t)(kF12ProducerWarps + 1)) >> 2;
         const uint32_t m = lane_grp + lane;
         uint32_t it = 0;
+        // site-row lookups one tile ahead: this warp never waits long at t_full, so loads issued in the same tile had their whole
+        // latency exposed at first use
+        const bool keep = m < (uint32_t)kF12OutRows;
+        int msc_next[kMaxScatter];
+        scatter_rows(c2, (unsigned long long)(2 * pair + rank) * kF12OutRows + m, msc_next);
         for (uint32_t t2 = pair; 2 * t2 < f.n_tiles; t2 += n_pairs, ++it) {
             const uint32_t buf = it & 1u, use = it >> 1;
-            // the site-row lookups do not depend on the accumulator: issue them before waiting for it
             const unsigned long long row = (unsigned long long)(2 * t2 + rank) * kF12OutRows + m;
-            const bool keep = m < (uint32_t)kF12OutRows;
             int msc[kMaxScatter];
-            scatter_rows(c2, row, msc);
-            if (!keep) {
-                #pragma unroll
-                for (int k = 0; k < kMaxScatter; ++k) msc[k] = -1;
-            }
+            #pragma unroll
+            for (int k = 0; k < kMaxScatter; ++k) msc[k] = keep ? msc_next[k] : -1;
+            if (2 * (t2 + n_pairs) < f.n_tiles) scatter_rows(c2, (unsigned long long)(2 * (t2 + n_pairs) + rank) * kF12OutRows + m, msc_next);
             umma::mbar_wait(&t_full[buf], use & 1u);
             umma::tc_fence_after();
             if (threadIdx.x == 32u * (kF12ProducerWarps + 1)) stamp(it, 15);
@@ -278,16 +279,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
         const uint32_t m = lane_grp + lane;
         const uint32_t pl_bytes = c2.seg[0].nrows * 16u;  // one plane of a stage: 132 rows x 16 B
         uint32_t it = 0;
+        // site-row lookups one tile ahead (as in epilogue-2); rows 124 .. 127 are rows 0 .. 3 of the next tile, which scatters them
+        const bool keep1 = m < (uint32_t)kF12OutRows;
+        int msc_next[kMaxScatter];
+        scatter_rows(c1, (unsigned long long)(2 * pair + rank) * kF12OutRows + m, msc_next);
         for (uint32_t t2 = pair; 2 * t2 < f.n_tiles; t2 += n_pairs, ++it) {
             const uint32_t buf = it & 1u, use = it >> 1;
-            // the site-row lookups do not depend on the accumulator: issue them before waiting for it
-            const unsigned long long row = (unsigned long long)(2 * t2 + rank) * kF12OutRows + m;
             int msc[kMaxScatter];
-            scatter_rows(c1, row, msc);
-            if (m >= (uint32_t)kF12OutRows) {  // rows 124 .. 127 are rows 0 .. 3 of the next tile, which scatters them
-                #pragma unroll
-                for (int k = 0; k < kMaxScatter; ++k) msc[k] = -1;
-            }
+            #pragma unroll
+            for (int k = 0; k < kMaxScatter; ++k) msc[k] = keep1 ? msc_next[k] : -1;
+            if (2 * (t2 + n_pairs) < f.n_tiles) scatter_rows(c1, (unsigned long long)(2 * (t2 + n_pairs) + rank) * kF12OutRows + m, msc_next);
             umma::mbar_wait(&a1_full[buf], use & 1u);
             umma::tc_fence_after();
             const bool stamper = threadIdx.x == 32u * (kF12ProducerWarps + 1 + kEpilogueWarps);

@@ -409,13 +409,17 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel_t(const __
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpilogueWarps) : "memory");
         uint32_t it = 0;
+        // site-row lookups one tile ahead (see dense_gemm2.cuh)
+        int msc_next[kMaxScatter];
+        scatter_rows(op, (unsigned long long)blockIdx.x * kTileRows + m, msc_next);
         for (uint32_t tile = blockIdx.x; tile < op.n_tiles; tile += gridDim.x, ++it) {
             const uint32_t buf = it & 1u, use = it >> 1;
-            // the site-row lookups do not depend on the accumulator: issue them before waiting for it
             const unsigned long long row = (unsigned long long)tile * kTileRows + m;
             float l0 = 0.f, l1 = 0.f;
             int msc[kMaxScatter];
-            scatter_rows(op, row, msc);
+            #pragma unroll
+            for (int k = 0; k < kMaxScatter; ++k) msc[k] = msc_next[k];
+            if (tile + gridDim.x < op.n_tiles) scatter_rows(op, (unsigned long long)(tile + gridDim.x) * kTileRows + m, msc_next);
             umma::mbar_wait(&t_full[buf], use & 1u);
             umma::tc_fence_after();
             const uint32_t t_addr = tmem_base + (lane_grp << 16) + buf * acc_stride;

@@ -161,12 +161,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) de
         for (int i = (int)threadIdx.x - 32 * (kProducerWarps + 1); i < n; i += 32 * kEpilogueWarps) s_bias[i] = __ldg(op.bias + i);
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpilogueWarps) : "memory");
         uint32_t it = 0;
+        // The site-row lookups (global loads) are issued one tile AHEAD: an epilogue-bound kernel never waits at t_full, so loads
+        // issued at the top of the same tile had their whole latency exposed at first use (ncu: long-scoreboard stalls there).
+        int msc_next[kMaxScatter];
+        scatter_rows(op, (unsigned long long)(2 * pair + rank) * kTileRows + m, msc_next);
         for (uint32_t t2 = pair; 2 * t2 < op.n_tiles; t2 += n_pairs, ++it) {
             const uint32_t buf = it & 1u, use = it >> 1;
-            // the site-row lookups do not depend on the accumulator: issue them before waiting for it
             const unsigned long long row = (unsigned long long)(2 * t2 + rank) * kTileRows + m;
             int msc[kMaxScatter];
-            scatter_rows(op, row, msc);
+            #pragma unroll
+            for (int k = 0; k < kMaxScatter; ++k) msc[k] = msc_next[k];
+            if (2 * (t2 + n_pairs) < op.n_tiles) scatter_rows(op, (unsigned long long)(2 * (t2 + n_pairs) + rank) * kTileRows + m, msc_next);
             umma::mbar_wait(&t_full[buf], use & 1u);
             umma::tc_fence_after();
             const uint32_t t_addr = tmem_base + (lane_grp << 16) + buf * acc_stride;
