@@ -7,6 +7,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <deque>
+#include <exception>
 #include <mutex>
 #include <cstdlib>
 #include <cstring>
@@ -64,10 +65,17 @@ public:
             std::atomic<size_t> next{0}, left{0};
             std::mutex m;
             std::condition_variable cv;
+            std::exception_ptr error;  // first exception of any task: rethrown in the caller, never left to std::terminate a pool thread
         } job;
         job.left = workers;
         auto body = [&job, &fn, n] {
-            for (size_t i = job.next.fetch_add(1); i < n; i = job.next.fetch_add(1)) fn(i);
+            try {
+                for (size_t i = job.next.fetch_add(1); i < n; i = job.next.fetch_add(1)) fn(i);
+            } catch (...) {
+                job.next = n;  // the other workers stop taking tasks
+                std::lock_guard<std::mutex> lk(job.m);
+                if (!job.error) job.error = std::current_exception();
+            }
             std::lock_guard<std::mutex> lk(job.m);
             if (--job.left == 0) job.cv.notify_all();
         };
@@ -79,6 +87,7 @@ public:
         body();  // the caller works too
         std::unique_lock<std::mutex> lk(job.m);
         job.cv.wait(lk, [&] { return job.left == 0; });
+        if (job.error) std::rethrow_exception(job.error);
     }
     size_t size() const { return threads_.size() + 1; }
 
@@ -164,9 +173,17 @@ bool BgzfReader::open(const char* path, int threads, std::string& err)
 void BgzfReader::run()
 {
     for (;;) {
-        auto slab = std::make_shared<Slab>();
+        std::shared_ptr<Slab> slab;
         std::string err;
-        const bool more = inflate_more(slab->data, err);
+        bool more = false;
+        try {  // an allocation failure ends the stream with an error instead of terminating the process
+            slab = std::make_shared<Slab>();
+            more = inflate_more(slab->data, err);
+        } catch (const std::exception& e) {
+            err = std::string("BGZF reader: ") + e.what();
+        } catch (...) {
+            err = "BGZF reader: unknown exception";
+        }
         std::unique_lock<std::mutex> lk(m_);
         if (!more) {
             worker_err_ = err;
@@ -208,7 +225,9 @@ bool BgzfReader::inflate_more(std::vector<uint8_t>& out, std::string& err)
             const size_t bs = bgzf_block_size(raw_.data() + off, raw_.size() - off, bad);
             if (bad) { err = "not a BGZF block (is the input a BAM file?)"; return false; }
             if (!bs || off + bs > raw_.size()) break;
-            if (bs < 26) { err = "corrupt BGZF block"; return false; }
+            // header (12) + extra field + at least the empty deflate stream (2) + CRC32 / ISIZE (8): XLEN comes from the file, and a
+            // block shorter than that would make the inflate length below wrap around
+            if (bs < 12 + (size_t)rd16(raw_.data() + off + 10) + 2 + 8) { err = "corrupt BGZF block (BSIZE smaller than its own header and trailer)"; return false; }
             const size_t isize = rd32(raw_.data() + off + bs - 4);
             if (isize > 65536) { err = "corrupt BGZF block (ISIZE above 64 KiB)"; return false; }  // BGZF payloads are <= 64 KiB
             blks.push_back({off, bs, isize, total});

@@ -218,25 +218,38 @@ private:
     bool closed_ = false;
 };
 
-// Finished batches arrive in any order (one producer per GPU); the writer takes them in input order.
+// Finished batches arrive in any order (one producer per GPU); the writer takes them in input order.  The box is BOUNDED: a
+// producer blocks in put() once `cap` batches are waiting, so that GPU workers cannot run ahead of a slow writer (zlib deflate is
+// the limiter on many GPUs) and pile assembled batches up in memory.  The batch the writer waits for is always admitted -- every
+// other batch in the box is younger than it, so the cap cannot deadlock.
 class OrderedOutbox {
 public:
-    void put(OutBatch&& b)
+    explicit OrderedOutbox(size_t cap) : cap_(std::max<size_t>(cap, 1)) {}
+    // false once finish() was called (the run failed): the batch is dropped.
+    bool put(OutBatch&& b)
     {
         std::unique_lock<std::mutex> lk(m_);
         const uint64_t k = b.seq;
+        space_.wait(lk, [&] { return done_ || k == next_ || ready_.size() < cap_; });
+        if (done_) return false;
         ready_.emplace(k, std::move(b));
+        peak_ = std::max(peak_, ready_.size());
         cv_.notify_all();
+        return true;
     }
     // Blocks until batch `seq` is there; false once finish() was called and it never will be.
     bool take(uint64_t seq, OutBatch& b)
     {
         std::unique_lock<std::mutex> lk(m_);
+        next_ = seq;
+        space_.notify_all();  // a producer holding exactly this batch may now enter even when the box is full
         cv_.wait(lk, [&] { return ready_.count(seq) || done_; });
         auto it = ready_.find(seq);
         if (it == ready_.end()) return false;
         b = std::move(it->second);
         ready_.erase(it);
+        next_ = seq + 1;
+        space_.notify_all();
         return true;
     }
     void finish()
@@ -244,12 +257,16 @@ public:
         std::lock_guard<std::mutex> lk(m_);
         done_ = true;
         cv_.notify_all();
+        space_.notify_all();
     }
+    size_t peak() { std::lock_guard<std::mutex> lk(m_); return peak_; }
 
 private:
     std::mutex m_;
-    std::condition_variable cv_;
+    std::condition_variable cv_, space_;
     std::map<uint64_t, OutBatch> ready_;
+    uint64_t next_ = 0;  // the batch the writer takes next
+    size_t cap_, peak_ = 0;
     bool done_ = false;
 };
 
@@ -270,7 +287,7 @@ struct Shared {
     std::chrono::steady_clock::time_point t_start = std::chrono::steady_clock::now();
     std::atomic<uint64_t> at_ready{0}, at_input_done{0}, at_last_collect{0}, at_destroyed{0};
     uint64_t since_start() const { return (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_start).count(); }
-    explicit Shared(const Options& o, size_t depth) : opt(o), raw(depth) { for (auto& v : n_sites) v = 0; }
+    explicit Shared(const Options& o, size_t depth) : opt(o), raw(depth), outbox(depth) { for (auto& v : n_sites) v = 0; }
     void fail(const std::string& msg)
     {
         {
@@ -295,7 +312,7 @@ struct Stopwatch {
 };
 
 // Reader: inflates the input (block-parallel) and cuts it into batches by read count and by bases.
-void reader_thread(Shared& S, hm::BamReader& in)
+void reader_body(Shared& S, hm::BamReader& in)
 {
     std::string err;
     RawBatch cur;
@@ -336,7 +353,7 @@ void reader_thread(Shared& S, hm::BamReader& in)
 
 // One worker per entry of --devices: owns an engine with two staging slots.  While the GPU works on batch k the worker
 // assembles the records of batch k-1 and packs batch k+1.
-void gpu_worker(Shared& S, int device, int threads)
+void gpu_worker_body(Shared& S, int device, int threads)
 {
     const Options& opt = S.opt;
     Stopwatch sw;
@@ -351,6 +368,10 @@ void gpu_worker(Shared& S, int device, int threads)
     cfg.cnn_mode = HM_CNN_TENSOR;
     hm_engine* eng = nullptr;
     if (hm_engine_create(&cfg, &eng) != HM_OK) { S.fail(std::string("device ") + std::to_string(device) + ": " + hm_last_error(nullptr)); return; }
+    struct EngineGuard {  // also destroys the engine when an exception unwinds this thread
+        hm_engine*& e;
+        ~EngineGuard() { if (e) hm_engine_destroy(e); e = nullptr; }
+    } guard{eng};
     S.us_create += sw.lap_us();
     S.at_ready = S.since_start();
 
@@ -414,8 +435,7 @@ void gpu_worker(Shared& S, int device, int threads)
         f.raw = RawBatch{};
         f.live = false;
         S.us_assemble += w.lap_us();
-        S.outbox.put(std::move(ob));
-        return true;
+        return S.outbox.put(std::move(ob));
     };
 
     int cur = 0;
@@ -451,10 +471,11 @@ void gpu_worker(Shared& S, int device, int threads)
     for (int k = 0; k < 2 && ok && !S.failed; ++k)
         if (fl[cur ^ k].live) ok = finish(cur ^ k);
     hm_engine_destroy(eng);
+    eng = nullptr;
     S.at_destroyed = S.since_start();
 }
 
-void writer_thread(Shared& S, hm::BamWriter& out)
+void writer_body(Shared& S, hm::BamWriter& out)
 {
     std::string err;
     Stopwatch sw;
@@ -468,11 +489,39 @@ void writer_thread(Shared& S, hm::BamWriter& out)
     }
 }
 
+// Thread entry points: an exception in any thread (bad_alloc from a buffer resize, a task of parallel_for) fails the run through
+// Shared::fail -- which also wakes every other thread -- instead of reaching std::terminate.
+template <class F>
+void guarded(Shared& S, const char* role, F&& body)
+{
+    try {
+        body();
+    } catch (const std::exception& e) {
+        S.fail(std::string(role) + ": " + e.what());
+    } catch (...) {
+        S.fail(std::string(role) + ": unknown exception");
+    }
+}
+void reader_thread(Shared& S, hm::BamReader& in)
+{
+    guarded(S, "reader", [&] { reader_body(S, in); });
+    S.raw.close();  // workers drain what is queued and stop, also when the reader ended early
+}
+void gpu_worker(Shared& S, int device, int threads)
+{
+    guarded(S, "GPU worker", [&] { gpu_worker_body(S, device, threads); });
+}
+void writer_thread(Shared& S, hm::BamWriter& out)
+{
+    guarded(S, "writer", [&] { writer_body(S, out); });
+}
+
 }  // namespace
 
 static int call_main_impl(int argc, char** argv);
 
-// Nothing throws across the C boundary: an allocation failure or any other exception ends the run with EXIT_FAILURE.
+// Nothing throws across the C boundary: an allocation failure or any other exception ends the run with EXIT_FAILURE (the calling
+// thread is guarded here, the reader / worker / writer threads by guarded() above, pool tasks by parallel_for itself).
 extern "C" int hm_call_main(int argc, char** argv)
 {
     try {

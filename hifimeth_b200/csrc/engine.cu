@@ -422,8 +422,12 @@ const char* hm_version(void) { return "hifimeth-b200 0.1.0 (sm_100a)"; }
 const char* hm_last_error(const hm_engine* e)
 {
     if (e) return e->err.c_str();
+    // a copy private to the calling thread: several device workers may fail in hm_engine_create at once, and a pointer into the
+    // shared string could dangle as soon as the lock is dropped
+    thread_local std::string copy;
     std::lock_guard<std::mutex> g(g_err_mu);
-    return g_create_error.c_str();
+    copy = g_create_error;
+    return copy.c_str();
 }
 
 void hm_engine_destroy(hm_engine* e)
@@ -526,12 +530,17 @@ int hm_batch_submit(hm_engine* e, int slot, uint32_t n_reads, uint32_t flags)
     HM_CUDA(e, "submit", cudaEventRecord(s.ev[0], st));
     if (!skip_h2d) {
         if (n_reads && s.host.base_off[0] != 0) return fail(e, HM_ERR_ARG, "hm_batch_submit: base_off[0] must be 0");
+        if (n_reads && s.host.seq_off[0] != 0) return fail(e, HM_ERR_ARG, "hm_batch_submit: seq_off[0] must be 0");
         const uint32_t nb = n_reads ? s.host.base_off[n_reads] : 0;
         const uint32_t nsb = n_reads ? s.host.seq_off[n_reads] : 0;
         if (nb > e->cfg.max_bases) return fail(e, HM_ERR_ARG, "hm_batch_submit: %u bases exceed capacity %u", nb, e->cfg.max_bases);
+        // the staging and device SEQ buffers hold max_bases / 2 + max_reads + 16 bytes (alloc_slot); callers may fill the SoA directly
+        const size_t seq_cap = (size_t)e->cfg.max_bases / 2 + e->cfg.max_reads + 16;
+        if (nsb > seq_cap) return fail(e, HM_ERR_ARG, "hm_batch_submit: %u packed SEQ bytes exceed capacity %zu", nsb, seq_cap);
         for (uint32_t r = 0; r < n_reads; ++r) {
             uint32_t L = s.host.base_off[r + 1] - s.host.base_off[r];
-            if (s.host.base_off[r + 1] < s.host.base_off[r] || s.host.seq_off[r + 1] - s.host.seq_off[r] < (L + 1) / 2)
+            if (s.host.base_off[r + 1] < s.host.base_off[r] || s.host.seq_off[r + 1] < s.host.seq_off[r] ||
+                s.host.seq_off[r + 1] - s.host.seq_off[r] < (L + 1) / 2)
                 return fail(e, HM_ERR_ARG, "hm_batch_submit: inconsistent offsets at read %u", r);
             if ((int32_t)L < e->cfg.min_read_len) s.host.valid[r] = 0;  // -l, mod_main.cpp:189-192
         }
@@ -693,6 +702,7 @@ int hm_debug_dump_decode(hm_engine* e, int slot, uint16_t* fi, uint16_t* fp, uin
     if (!e || slot < 0 || slot >= e->n_slots) return fail(e, HM_ERR_ARG, "hm_debug_dump_decode: bad slot");
     Slot& s = e->slots[slot];
     if (!s.collected) return fail(e, HM_ERR_STATE, "hm_debug_dump_decode: collect slot %d first", slot);
+    if (!e->cfg.keep_debug) return fail(e, HM_ERR_STATE, "hm_debug_dump_decode: the engine was created without hm_config.keep_debug");
     cudaSetDevice(e->cfg.device);
     const size_t nb = s.n_bases;
     uint16_t* d16 = nullptr;
@@ -719,6 +729,7 @@ int hm_debug_dump_ctx(hm_engine* e, int slot, uint8_t* ctx)
     if (!e || !ctx || slot < 0 || slot >= e->n_slots) return fail(e, HM_ERR_ARG, "hm_debug_dump_ctx: bad argument");
     Slot& s = e->slots[slot];
     if (!s.collected) return fail(e, HM_ERR_STATE, "hm_debug_dump_ctx: collect slot %d first", slot);
+    if (!e->cfg.keep_debug) return fail(e, HM_ERR_STATE, "hm_debug_dump_ctx: the engine was created without hm_config.keep_debug");
     cudaSetDevice(e->cfg.device);
     HM_CUDA(e, "debug ctx", cudaMemcpy(ctx, s.d_call_ctx, s.n_calls, cudaMemcpyDeviceToHost));
     return HM_OK;
@@ -729,6 +740,7 @@ int hm_debug_dump_features(hm_engine* e, int slot, uint32_t first, uint32_t coun
     if (!e || !out || slot < 0 || slot >= e->n_slots) return fail(e, HM_ERR_ARG, "hm_debug_dump_features: bad argument");
     Slot& s = e->slots[slot];
     if (!s.collected) return fail(e, HM_ERR_STATE, "hm_debug_dump_features: collect slot %d first", slot);
+    if (!e->cfg.keep_debug) return fail(e, HM_ERR_STATE, "hm_debug_dump_features: the engine was created without hm_config.keep_debug");
     if ((uint64_t)first + count > s.n_calls) return fail(e, HM_ERR_ARG, "hm_debug_dump_features: range beyond %u calls", s.n_calls);
     if (!count) return HM_OK;
     cudaSetDevice(e->cfg.device);
@@ -761,6 +773,7 @@ int hm_debug_dump_logits(hm_engine* e, int slot, float* out)
     if (!e || !out || slot < 0 || slot >= e->n_slots) return fail(e, HM_ERR_ARG, "hm_debug_dump_logits: bad argument");
     Slot& s = e->slots[slot];
     if (!s.collected) return fail(e, HM_ERR_STATE, "hm_debug_dump_logits: collect slot %d first", slot);
+    if (!e->cfg.keep_debug) return fail(e, HM_ERR_STATE, "hm_debug_dump_logits: the engine was created without hm_config.keep_debug");
     cudaSetDevice(e->cfg.device);
     HM_CUDA(e, "debug logits", cudaMemcpy(out, s.d_logits, (size_t)s.n_calls * 2 * sizeof(float), cudaMemcpyDeviceToHost));
     return HM_OK;

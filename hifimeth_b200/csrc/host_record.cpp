@@ -83,13 +83,20 @@ size_t put_decimal(uint8_t* dst, uint32_t v)
     return n;
 }
 
-size_t put_mn(uint8_t* dst, int32_t l_seq)
+// bam_aux_update_int (contract: src/htslib/sam.h:1844-1866; htslib 1.19.1 sam.c, not vendored): a new tag gets the smallest
+// unsigned type that holds the value -- htslib compares with `<`, so 255 is stored as 'S' and 65535 as 'I' -- and an EXISTING
+// integer tag keeps its width when the value fits in it (the field is reused in place), growing only when it does not.
+// old_type = 0: no existing field.
+size_t put_mn(uint8_t* dst, int32_t l_seq, char old_type = 0)
 {
-    // bam_aux_update_int stores the smallest integer type that fits (src/htslib/sam.h:1844-1866)
+    int sz = l_seq < 0xff ? 1 : (l_seq < 0xffff ? 2 : 4);
+    const int old_sz = (old_type == 'c' || old_type == 'C') ? 1 : (old_type == 's' || old_type == 'S') ? 2 : (old_type == 'i' || old_type == 'I') ? 4 : 0;
+    if (old_sz > sz) sz = old_sz;
     dst[0] = 'M'; dst[1] = 'N';
-    if (l_seq <= 0xff) { dst[2] = 'C'; dst[3] = (uint8_t)l_seq; return 4; }
-    if (l_seq <= 0xffff) { dst[2] = 'S'; uint16_t v = (uint16_t)l_seq; memcpy(dst + 3, &v, 2); return 5; }
-    dst[2] = 'I'; uint32_t v = (uint32_t)l_seq; memcpy(dst + 3, &v, 4); return 7;
+    const uint32_t v = (uint32_t)l_seq;
+    dst[2] = sz == 1 ? 'C' : (sz == 2 ? 'S' : 'I');
+    memcpy(dst + 3, &v, (size_t)sz);  // little endian
+    return 3 + (size_t)sz;
 }
 
 }  // namespace
@@ -232,9 +239,13 @@ static size_t strip_tags(const uint8_t* body, size_t len, const RecLayout& r, in
             dropped[k] = true;
             drop = true;
         }
-        if (!drop && have_calls && !mn_written && body[p] == 'M' && body[p + 1] == 'N' && strchr("cCsSiI", body[p + 2])) {
-            o += put_mn(out + o, r.l_seq);
-            mn_written = true;
+        if (!drop && have_calls && !mn_written && body[p] == 'M' && body[p + 1] == 'N') {
+            // an integer MN is updated where it stands, keeping its width when l_seq fits; the reference aborts on an MN of any other
+            // type (bam_aux_update_int fails, build_mod_bam.cpp:240-247) -- here that field is dropped and a fresh MN is appended
+            if (strchr("cCsSiI", body[p + 2])) {
+                o += put_mn(out + o, r.l_seq, (char)body[p + 2]);
+                mn_written = true;
+            }
             drop = true;
         }
         if (!drop) {

@@ -181,6 +181,18 @@ class _Ref:
         L.ref_build_mod_bam.argtypes = [_u8p, C.c_size_t, C.c_int, _i32p, _u8p, C.c_int, _i32p, _u8p, C.c_int,
                                         _u8p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.ref_parse_mods.argtypes = [_u8p, C.c_size_t, _i32p, _u8p, _u8p, C.c_int]
+        self.has_pileup = hasattr(L, "hmref_pileup_thresholds")
+        if self.has_pileup:
+            L.hmref_pileup_thresholds.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+            L.hmref_pileup_thresholds.restype = None
+
+    def pileup_thresholds(self, cpg, chg, chh):
+        """The reference's own s_resolve_scaled_prob_threshold (src/app/hifimeth/pileup.cpp:355-436, compiled through
+        oracle/ref_pileup.cpp) on three 256-bin histograms -> (cpg, chg, chh) thresholds."""
+        a, b, c = (np.ascontiguousarray(x, np.uint64) for x in (cpg, chg, chh))
+        out = np.zeros(3, np.uint8)
+        self.lib.hmref_pileup_thresholds(a.ctypes.data, b.ctypes.data, c.ctypes.data, out.ctypes.data)
+        return tuple(int(x) for x in out)
 
     def query_decode(self, body: bytes, l: int):
         src = np.frombuffer(body, np.uint8)

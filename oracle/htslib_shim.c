@@ -186,24 +186,37 @@ int bam_aux_update_str(bam1_t *b, const char tag[2], int len, const char *data)
 
 int bam_aux_update_int(bam1_t *b, const char tag[2], int64_t val)
 {
-    /* smallest integer type that holds val (sam.h:1844-1866 names the types c,C,s,S,i,I) */
+    /* htslib 1.19.1 sam.c (not vendored; contract in sam.h:1844-1866): the smallest type that holds val, compared with `<`
+     * (255 -> 'S', 65535 -> 'I'); an existing integer field keeps its width when val fits in it. */
     uint8_t payload[5];
     size_t plen;
+    int sz, neg = val < 0;
     if (val < INT32_MIN || val > UINT32_MAX) { errno = EOVERFLOW; return -1; }
-    if (val < 0) {
-        if (val >= INT8_MIN) { payload[0] = 'c'; int8_t v = (int8_t)val; memcpy(payload + 1, &v, 1); plen = 2; }
-        else if (val >= INT16_MIN) { payload[0] = 's'; int16_t v = (int16_t)val; memcpy(payload + 1, &v, 2); plen = 3; }
-        else { payload[0] = 'i'; int32_t v = (int32_t)val; memcpy(payload + 1, &v, 4); plen = 5; }
-    } else {
-        if (val <= UINT8_MAX) { payload[0] = 'C'; uint8_t v = (uint8_t)val; memcpy(payload + 1, &v, 1); plen = 2; }
-        else if (val <= UINT16_MAX) { payload[0] = 'S'; uint16_t v = (uint16_t)val; memcpy(payload + 1, &v, 2); plen = 3; }
-        else { payload[0] = 'I'; uint32_t v = (uint32_t)val; memcpy(payload + 1, &v, 4); plen = 5; }
-    }
+    if (val < INT16_MIN) sz = 4;
+    else if (val < INT8_MIN) sz = 2;
+    else if (val < 0) sz = 1;
+    else if (val < UINT8_MAX) sz = 1;
+    else if (val < UINT16_MAX) sz = 2;
+    else sz = 4;
     uint8_t *s = bam_aux_get(b, tag);
     if (s) {
-        if (!strchr("cCsSiI", s[0])) { errno = EINVAL; return -1; }
-        return replace_field(b, s, payload, plen);
+        int old_sz;
+        switch (s[0]) {
+        case 'c': case 'C': old_sz = 1; break;
+        case 's': case 'S': old_sz = 2; break;
+        case 'i': case 'I': old_sz = 4; break;
+        default: errno = EINVAL; return -1;
+        }
+        if (old_sz > sz) sz = old_sz;
     }
+    payload[0] = (uint8_t)(neg ? (sz == 1 ? 'c' : sz == 2 ? 's' : 'i') : (sz == 1 ? 'C' : sz == 2 ? 'S' : 'I'));
+    {
+        uint32_t v = (uint32_t)(int32_t)val;
+        if (!neg) v = (uint32_t)val;
+        memcpy(payload + 1, &v, (size_t)sz);
+    }
+    plen = 1 + (size_t)sz;
+    if (s) return replace_field(b, s, payload, plen);
     if (errno != ENOENT) return -1;
     return append_field(b, tag, payload, plen);
 }

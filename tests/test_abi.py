@@ -252,3 +252,85 @@ def test_ml_threshold_rule_matches_oracle(lib_built):
         seen.add(got[0])
     assert 128 in seen and len(seen) > 5
     assert hme.ml_threshold(bimodal)[0] == int(np.argmin(bimodal[20:236])) + 20
+
+
+def _threshold_cases():
+    rng = np.random.default_rng(5)
+    x = np.arange(256)
+    bimodal = (40000 * np.exp(-x / 12.0) + 30000 * np.exp(-(255 - x) / 9.0) + 15).astype(np.uint64)
+    cases = [bimodal, np.full(256, 100, np.uint64), np.zeros(256, np.uint64)]
+    sparse = np.zeros(256, np.uint64); sparse[100:140] = 5000
+    few = np.zeros(256, np.uint64); few[30:200] = 12
+    edge = bimodal.copy(); edge[:60] = 3; edge[200:] = 9
+    exact50 = np.zeros(256, np.uint64); exact50[60:110] = 300       # en - st == 50 exactly: the rule applies
+    exact49 = np.zeros(256, np.uint64); exact49[60:109] = 300       # 49 bins: it does not
+    sum9999 = np.zeros(256, np.uint64); sum9999[40:140] = 100; sum9999[40] = 99   # 9 999 samples -> 128
+    sum10000 = np.zeros(256, np.uint64); sum10000[40:140] = 100                   # 10 000 samples -> first minimum
+    outer = np.zeros(256, np.uint64); outer[:] = 50; outer[:20] = 10**7; outer[236:] = 10**7; outer[130] = 11
+    ties = np.full(256, 77, np.uint64); ties[90] = 76; ties[150] = 76              # equal minima: the first wins
+    huge = np.full(256, 2**40, np.uint64); huge[77] = 2**40 - 1
+    cases += [sparse, few, edge, exact50, exact49, sum9999, sum10000, outer, ties, huge]
+    for _ in range(60):
+        cases.append(rng.integers(0, 400, 256).astype(np.uint64) * rng.integers(0, 2, 256).astype(np.uint64))
+        cases.append((rng.integers(0, 3000, 256) + 10).astype(np.uint64))
+        b = np.zeros(256, np.uint64)
+        lo, hi = sorted(int(v) for v in rng.integers(0, 257, 2))
+        b[lo:hi] = rng.integers(0, 25, hi - lo)
+        b[lo:hi] *= np.uint64(rng.integers(1, 40))
+        cases.append(b)
+    return cases
+
+
+def test_ml_threshold_pinned_to_reference_pileup(lib_built, capfd):
+    """Row N3, pinned: hm_ml_threshold (and the oracle's restatement) against the REFERENCE'S OWN compiled
+    s_resolve_scaled_prob_threshold (src/app/hifimeth/pileup.cpp:355-436; oracle/ref_pileup.cpp includes pileup.cpp into
+    oracle/_ref) on degenerate, boundary and random histograms, in every context slot of the reference's signature."""
+    R = hmoracle.ref()
+    if not R.available or not R.has_pileup:
+        pytest.skip("oracle/_ref was built without the pileup translation unit")
+    O = hmoracle.oracle()
+    cases = _threshold_cases()
+    seen = set()
+    for i in range(0, len(cases) - 2, 1):
+        a, b, c = cases[i], cases[i + 1], cases[i + 2]
+        want = R.pileup_thresholds(a, b, c)
+        got = tuple(hme.ml_threshold(x)[0] for x in (a, b, c))
+        assert got == want, (i, got, want)
+        assert tuple(O.ml_threshold(x)[0] for x in (a, b, c)) == want
+        seen.update(want)
+    assert 128 in seen and len(seen) > 10
+    capfd.readouterr()  # the reference prints its decision to stderr
+
+
+def test_existing_mn_tag_keeps_its_width_like_bam_aux_update_int(lib_built):
+    """A re-called BAM already carries MN (and MM / ML): build_one_mod_bam updates MN through bam_aux_update_int
+    (src/corelib/build_mod_bam.cpp:240-247), which reuses the field in place and keeps its width when the value fits.  Checked
+    against the reference's build_mod_bam.cpp compiled in oracle/_ref, for every integer type the old field may have."""
+    import struct
+
+    R = hmoracle.ref()
+    if not R.available:
+        pytest.skip("oracle/_ref not built")
+    _, reads = synth.make_reads(1, 1200, seed=3)
+    base = synth.record_body(reads[0])
+    seq = np.asarray(reads[0]["seq"])  # the reference asserts that forward calls sit on a C and reverse calls on a G
+    fq = np.nonzero(seq == 1)[0][[2, 40, 200]].astype(np.int32); fml = np.array([1, 128, 255], np.uint8)
+    rq = np.nonzero(seq == 2)[0][[5, 250]].astype(np.int32); rml = np.array([7, 9], np.uint8)
+    olds = [b"MNC" + struct.pack("<B", 7), b"MNc" + struct.pack("<b", 7), b"MNS" + struct.pack("<H", 99), b"MNs" + struct.pack("<h", 99),
+            b"MNI" + struct.pack("<I", 123456), b"MNi" + struct.pack("<i", 123456)]
+    for old in olds:
+        for where in ("end", "middle"):
+            body = base + old if where == "end" else base + old + b"zzZtail\0"
+            want = R.build_mod_bam(body, False, fq, fml, rq, rml)
+            got = hme.build_mod_record(body, False, fq, fml, rq, rml)
+            assert got == want, (old, where)
+            # the record still parses and MN holds l_seq
+            assert b"MN" in got
+    # width as a function of the value for a NEW tag: htslib compares with `<`
+    for L, typ in ((254, b"C"), (255, b"S"), (65534, b"S"), (65535, b"I")):
+        _, rd = synth.make_reads(1, L, seed=4)
+        body = synth.record_body(rd[0])
+        q = np.nonzero(np.asarray(rd[0]["seq"]) == 1)[0][:1].astype(np.int32); m = np.array([200], np.uint8)
+        want = R.build_mod_bam(body, False, q, m, [], [])
+        got = hme.build_mod_record(body, False, q, m, [], [])
+        assert got == want and got[-(3 + {b"C": 1, b"S": 2, b"I": 4}[typ]):][:3] == b"MN" + typ, (L, typ)

@@ -121,3 +121,41 @@ def test_bam_reader_survives_corruption(lib_built, tmp_path):
     assert all(x < 0 for x in res[:8])             # every truncation is an error
     assert all(x < 0 or x <= len(bodies) + 2 for x in res)
     assert sum(x < 0 for x in res) > len(res) // 2  # most random damage is caught (CRC / structure)
+
+
+def test_bgzf_block_with_oversized_xlen_is_rejected(lib_built, tmp_path):
+    """A crafted block whose XLEN is larger than BSIZE allows (the inflate length would wrap around and zlib would read far past the
+    buffer) must be refused as corrupt -- ADVICE r1."""
+    import zlib
+
+    def block(payload: bytes, xlen_extra: int, bsize_delta: int = 0) -> bytes:
+        co = zlib.compressobj(1, zlib.DEFLATED, -15)
+        comp = co.compress(payload) + co.flush()
+        extra = b"BC" + (2).to_bytes(2, "little") + b"\0\0" + b"\0" * xlen_extra
+        total = 12 + len(extra) + len(comp) + 8
+        extra = b"BC" + (2).to_bytes(2, "little") + (total - 1 + bsize_delta).to_bytes(2, "little") + b"\0" * xlen_extra
+        return bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255]) + len(extra).to_bytes(2, "little") + extra + comp + \
+            (zlib.crc32(payload) & 0xffffffff).to_bytes(4, "little") + len(payload).to_bytes(4, "little")
+
+    lib = hme.load_library()
+    out = str(tmp_path / "o.bam").encode()
+    # XLEN = 200 claimed, but BSIZE says the whole block is 40 bytes
+    evil = bytearray(block(b"BAM\x01" + bytes(8), 0))
+    evil[10:12] = (200).to_bytes(2, "little")
+    evil += bytes(400)
+    bad = tmp_path / "xlen.bam"
+    for bs in (27, 40, 100, 219):
+        e2 = bytearray(evil)
+        e2[16:18] = (bs - 1).to_bytes(2, "little")
+        bad.write_bytes(bytes(e2))
+        assert lib.hm_bam_copy(str(bad).encode(), out, 2, 1) < 0
+    # sanity: padding inside a consistent extra field is legal BGZF and still reads
+    _, reads = synth.make_reads(2, 400, seed=1)
+    bodies = [synth.record_body(r) for r in reads]
+    good = tmp_path / "g.bam"
+    synth.write_bam(good, bodies, level=1)
+    import gzip
+    stream = gzip.decompress(good.read_bytes())
+    padded = tmp_path / "padded.bam"
+    padded.write_bytes(block(stream, 6) + block(b"", 0))
+    assert lib.hm_bam_copy(str(padded).encode(), out, 2, 1) == len(bodies)
