@@ -563,6 +563,7 @@ struct TensorModel {
     int i_y1 = -1, i_y2 = -1;
     uint8_t* d_blob = nullptr;
     double macs_per_row = 0;  // executed, one precision pass, all ops
+    int lens[9] = {};         // per-site output length of every layer (lens[0] = 401)
 };
 
 const char* tensor_last_error() { return g_err.c_str(); }
@@ -573,6 +574,8 @@ int tensor_model_build(TensorModelHandle& m, const CnnModel& host)
     std::string err;
     if (!build_plan(host, compact_mode(), plan, err)) return tfail("dense plan: " + err);
     TensorModel* t = new TensorModel();
+    t->lens[0] = host.kmer;
+    for (int l = 0; l < 8; ++l) t->lens[l + 1] = (t->lens[l] + 2 - host.convs[l].k) / 2 + 1;
     std::vector<uint8_t> blob;
     for (const HostOp& h : plan) {
         // an op whose resident weights leave no room for the activation ring is split over output channels
@@ -657,6 +660,8 @@ struct TensorWorkspaceImpl {
     uint32_t* d_site_rows = nullptr;  // [compact_cap] compact row -> X row (global)
     float* d_clogit = nullptr;        // [rows_cap][2] logits of the compact rows
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // shape of the last tensor_batch_run (debug hooks): sub-batches, compact groups per context, rows of the X map
+    uint32_t last_subs = 0, last_groups[3] = {0, 0, 0}, last_x_rows = 0;
 };
 
 int tensor_workspace_alloc(TensorWorkspace& w, uint32_t max_bases, uint32_t max_reads, uint32_t max_rows)
@@ -868,6 +873,9 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
         }
         r = r1;
     }
+    s->last_subs = (uint32_t)subs.size();
+    s->last_x_rows = gtile * kTileRows;
+    for (uint32_t& g : s->last_groups) g = 0;
     if (gtile) {
         TCUDA("track tables", cudaMemcpyAsync(s->d_tile_read, s->h_tile_read, (size_t)gtile * 4, cudaMemcpyHostToDevice, stream));
         TCUDA("track tables", cudaMemcpyAsync(s->d_tile_first, s->h_tile_first, (size_t)gtile * 4, cudaMemcpyHostToDevice, stream));
@@ -984,6 +992,7 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
                     }
                 }
                 TCUDA("dense plan", cudaGetLastError());
+                ++s->last_groups[c];
                 g0 = g1 > g0 ? g1 : g0 + 1;
             }
         }
@@ -1047,6 +1056,132 @@ float tensor_last_dense_ms(TensorWorkspace& w)
 }
 
 float tensor_debug_last_op_ms() { return g_debug_op_ms; }
+
+// ---- debug readback of the maps the PRODUCT path works on (hm_debug_dump_xmap / hm_debug_dump_acts) ------------------------------
+namespace {
+
+// out[r][g*8 .. g*8+8) = hi + lo of row rows[r] of a plane-layout map; a negative row gives NaN ("the product path never
+// materialises this value").
+__global__ void __launch_bounds__(256)
+debug_rows_kernel(const uint8_t* __restrict__ map, unsigned long long plane_stride, uint32_t groups, const long long* __restrict__ rows,
+                  uint32_t n, float* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * groups) return;
+    const uint32_t r = i / groups, g = i % groups;
+    const long long row = rows[r];
+    float* o = out + ((size_t)r * groups + g) * 8;
+    if (row < 0) {
+        for (int e = 0; e < 8; ++e) o[e] = __int_as_float(0x7fc00000);
+        return;
+    }
+    const uint4 hi = *reinterpret_cast<const uint4*>(map + (unsigned long long)g * plane_stride + (unsigned long long)row * 16ull);
+    const uint4 lo = *reinterpret_cast<const uint4*>(map + (unsigned long long)(groups + g) * plane_stride + (unsigned long long)row * 16ull);
+    const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
+    for (int j = 0; j < 4; ++j) {
+        o[2 * j] = __uint_as_float(h[j] << 16) + __uint_as_float(l[j] << 16);
+        o[2 * j + 1] = __uint_as_float(h[j] & 0xffff0000u) + __uint_as_float(l[j] & 0xffff0000u);
+    }
+}
+
+int debug_read_rows(const uint8_t* map, unsigned long long plane_stride, uint32_t groups, const std::vector<long long>& rows, float* out,
+                    cudaStream_t stream)
+{
+    if (rows.empty()) return 0;
+    long long* d_rows = nullptr;
+    float* d_out = nullptr;
+    const size_t n = rows.size();
+    TCUDA("debug rows", cudaMalloc((void**)&d_rows, n * sizeof(long long)));
+    TCUDA("debug rows", cudaMalloc((void**)&d_out, n * groups * 8 * sizeof(float)));
+    TCUDA("debug rows", cudaMemcpyAsync(d_rows, rows.data(), n * sizeof(long long), cudaMemcpyHostToDevice, stream));
+    debug_rows_kernel<<<(uint32_t)((n * groups + 255) / 256), 256, 0, stream>>>(map, plane_stride, groups, d_rows, (uint32_t)n, d_out);
+    TCUDA("debug rows", cudaGetLastError());
+    TCUDA("debug rows", cudaMemcpyAsync(out, d_out, n * groups * 8 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    TCUDA("debug rows", cudaStreamSynchronize(stream));
+    cudaFree(d_rows);
+    cudaFree(d_out);
+    return 0;
+}
+
+// X-map row of the s-row (strand offset o - 201) of a site; the site's window is rows s + 1 .. s + 401.
+long long site_s_row(const TensorWorkspaceImpl& s, uint32_t read, bool rev, int o)
+{
+    const uint32_t trk = (rev ? s.h_track_row + s.reads_cap : s.h_track_row)[read];
+    return (long long)trk + kHaloL + o - 201;
+}
+
+}  // namespace
+
+int tensor_debug_xwindow(TensorWorkspace& w, uint32_t n, const uint32_t* read, const uint8_t* rev, const int32_t* o, float* out, cudaStream_t stream)
+{
+    TensorWorkspaceImpl* s = w.impl;
+    if (!s || !s->d_xg || !s->last_x_rows) return tfail("debug X window: no X map is resident (tensor path, compact mode, after a batch)");
+    std::vector<long long> rows((size_t)n * 401);
+    for (uint32_t i = 0; i < n; ++i) {
+        if (read[i] >= s->reads_cap) return tfail("debug X window: read index out of range");
+        const long long sr = site_s_row(*s, read[i], rev[i] != 0, o[i]);
+        for (int j = 0; j < 401; ++j) {
+            const long long r = sr + 1 + j;
+            if (r < 0 || r >= (long long)s->last_x_rows + kSlackRows) return tfail("debug X window: row outside the X map");
+            rows[(size_t)i * 401 + j] = r;
+        }
+    }
+    return debug_read_rows(s->d_xg, s->xg_stride, 1, rows, out, stream);
+}
+
+int tensor_debug_site_acts(const TensorModelHandle& model, int ctx, TensorWorkspace& w, uint32_t n, const uint32_t* read, const uint8_t* rev,
+                           const int32_t* o, const uint32_t* compact_row, int layer, float* out, int* n_out, int* channels, cudaStream_t stream)
+{
+    TensorWorkspaceImpl* s = w.impl;
+    const TensorModel* tm = model.p;
+    if (!s || !tm) return tfail("debug activations: no tensor model / workspace");
+    if (!compact_mode()) return tfail("debug activations: not available under HM_DENSE_ALL");
+    if (layer < 1 || layer > 8) return tfail("debug activations: layer must be 1..8");
+    const int nl = tm->lens[layer];
+    const int C = layer <= 6 ? kLayerCout[layer - 1] : 64;
+    *n_out = nl;
+    *channels = C;
+    if (!n) return 0;
+    if (s->last_subs != 1 || s->last_groups[ctx] != 1)
+        return tfail("debug activations: the batch must fit one sub-batch and one compact group (use a smaller batch)");
+    const uint32_t groups = (uint32_t)C / 8;
+    // Y1 exists in HBM only as the compact copies the fused kernel scatters for F2 / G2
+    const DevOp* y1_prod = nullptr;
+    if (layer == 1 && tm->fused12) y1_prod = &tm->f12_c1;
+    for (int v = 0; v < nl; ++v) {
+        const uint8_t* map = nullptr;
+        unsigned long long stride = 0;
+        std::vector<long long> rows(n);
+        bool compact = false;
+        int shift = 0;
+        if (layer >= 7) { map = s->map[(layer == 7 ? MAP_T7 : MAP_T8) + v]; compact = true; }
+        else if (v == 0) { map = s->map[MAP_F + layer - 1]; compact = true; }
+        else if (v == nl - 1) { map = s->map[MAP_G + layer - 1]; compact = true; }
+        else {
+            shift = -((1 << layer) - 2) + v * (1 << layer);
+            if (y1_prod) {
+                for (int k = 0; k < y1_prod->p.n_scatter; ++k)
+                    if (y1_prod->p.sc_shift[k] == shift) { map = s->map[y1_prod->sc_map[k]]; compact = true; }
+            } else {
+                map = s->map[MAP_Y + layer - 1];
+            }
+        }
+        stride = compact ? s->cplane_stride : s->plane_stride;
+        for (uint32_t i = 0; i < n; ++i) {
+            if (!map) { rows[i] = -1; continue; }
+            if (compact) { rows[i] = compact_row[i]; continue; }
+            const long long r = site_s_row(*s, read[i], rev[i] != 0, o[i]) + shift;
+            if (r < 0 || r >= (long long)s->rows_cap + kSlackRows) return tfail("debug activations: row outside the dense map");
+            rows[i] = r;
+        }
+        std::vector<float> tmp((size_t)n * C);
+        if (!map) {
+            for (float& x : tmp) x = NAN;
+        } else if (debug_read_rows(map, stride, groups, rows, tmp.data(), stream)) return -1;
+        for (uint32_t i = 0; i < n; ++i) memcpy(out + ((size_t)i * nl + v) * C, tmp.data() + (size_t)i * C, (size_t)C * sizeof(float));
+    }
+    return 0;
+}
 
 // ---- unit-test hook: one op on caller-provided fp32 maps ------------------------------------------------------------------------
 int tensor_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int cin, int cout, int n_src, const float* const* src, int n_terms,

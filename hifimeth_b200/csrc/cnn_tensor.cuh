@@ -56,6 +56,17 @@ int tensor_batch_run(const TensorModelHandle* models /*[3]*/, uint32_t ctx_mask,
 // Device time (ms) of the dense plan of the last batch run on this workspace; call after the stream is synchronised.
 float tensor_last_dense_ms(TensorWorkspace& w);
 
+// Debug readback of what the PRODUCT path computes on (hm_debug_dump_xmap / hm_debug_dump_acts; valid after tensor_batch_run,
+// stream synchronised).  A site is (read, rev, o = strand offset); compact_row = its row in the compact maps of its context.
+//   xwindow:   out [n][401][8] f32 = hi + lo of the X-map rows the site's window covers (raw features, before bn0).
+//   site_acts: out [n][n_l][C_l] f32 = the per-site output of conv layer `layer` (1..8) as assembled from the maps the plan left
+//              behind: Y_l (dense) for interior positions, F_l / G_l (compact) for the first / last, T7 / T8 for layers 7, 8;
+//              NaN where the product path never holds the value in HBM (interior of layer 1 when conv1 + conv2 are fused,
+//              except the rows scattered for F2 / G2).  The last run must have been this context alone, in one sub-batch.
+int tensor_debug_xwindow(TensorWorkspace& w, uint32_t n, const uint32_t* read, const uint8_t* rev, const int32_t* o, float* out, cudaStream_t stream);
+int tensor_debug_site_acts(const TensorModelHandle& model, int ctx, TensorWorkspace& w, uint32_t n, const uint32_t* read, const uint8_t* rev,
+                           const int32_t* o, const uint32_t* compact_row, int layer, float* out, int* n_out, int* channels, cudaStream_t stream);
+
 // Unit-test hook behind hm_debug_dense_op (include/hm_engine.h).
 int tensor_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int cin, int cout, int n_src, const float* const* src,
                           int n_terms, const int32_t* term_src, const int32_t* term_shift, const float* weights, const float* bias,

@@ -779,6 +779,102 @@ int hm_debug_dump_logits(hm_engine* e, int slot, float* out)
     return HM_OK;
 }
 
+namespace {
+// Site-list view of calls [first, first + count) of a collected batch (hm_call_batch order): read, strand, strand offset o,
+// context and the row the site owns in the compact maps of its context (one sub-batch, one group).
+struct DebugSites {
+    std::vector<uint32_t> read, compact_row;
+    std::vector<uint8_t> rev, ctx;
+    std::vector<int32_t> o;
+};
+int debug_sites(hm_engine* e, Slot& s, uint32_t first, uint32_t count, DebugSites& d)
+{
+    std::vector<uint32_t> site_out(s.n_calls), inv(s.n_calls), h_read(s.n_calls), h_pos(s.n_calls);
+    HM_CUDA(e, "debug sites", cudaMemcpy(site_out.data(), s.d_site_out, (size_t)s.n_calls * 4, cudaMemcpyDeviceToHost));
+    HM_CUDA(e, "debug sites", cudaMemcpy(h_read.data(), s.d_site_read, (size_t)s.n_calls * 4, cudaMemcpyDeviceToHost));
+    HM_CUDA(e, "debug sites", cudaMemcpy(h_pos.data(), s.d_site_pos, (size_t)s.n_calls * 4, cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < s.n_calls; ++i) inv[site_out[i]] = i;
+    const uint32_t f1 = s.totals[0], f2 = f1 + s.totals[1], f3 = f2 + s.totals[2];
+    d.read.resize(count); d.compact_row.resize(count); d.rev.resize(count); d.ctx.resize(count); d.o.resize(count);
+    for (uint32_t i = 0; i < count; ++i) {
+        const uint32_t k = inv[first + i];
+        const uint32_t r = h_read[k], sp = h_pos[k];
+        const int L = (int)(s.host.base_off[r + 1] - s.host.base_off[r]), p = (int)(sp & 0x7fffffffu);
+        d.read[i] = r;
+        d.rev[i] = (uint8_t)(sp >> 31);
+        d.o[i] = d.rev[i] ? L - 1 - p : p;
+        d.ctx[i] = (uint8_t)(k < f1 ? 0 : k < f2 ? 1 : 2);
+        d.compact_row[i] = k < f1 ? k : k < f2 ? k - f1 : k < f3 ? k - f2 : s.totals[2] + (k - f3);
+    }
+    return HM_OK;
+}
+}  // namespace
+
+int hm_debug_dump_xmap(hm_engine* e, int slot, uint32_t first, uint32_t count, float* out)
+{
+    if (!e || !out || slot < 0 || slot >= e->n_slots) return fail(e, HM_ERR_ARG, "hm_debug_dump_xmap: bad argument");
+    Slot& s = e->slots[slot];
+    if (!s.collected) return fail(e, HM_ERR_STATE, "hm_debug_dump_xmap: collect slot %d first", slot);
+    if (!e->cfg.keep_debug) return fail(e, HM_ERR_STATE, "hm_debug_dump_xmap: the engine was created without hm_config.keep_debug");
+    if (e->cfg.cnn_mode != HM_CNN_TENSOR) return fail(e, HM_ERR_STATE, "hm_debug_dump_xmap: only the tensor path keeps an X map");
+    if ((uint64_t)first + count > s.n_calls) return fail(e, HM_ERR_ARG, "hm_debug_dump_xmap: range beyond %u calls", s.n_calls);
+    if (!count) return HM_OK;
+    cudaSetDevice(e->cfg.device);
+    DebugSites d;
+    int rc = debug_sites(e, s, first, count, d);
+    if (rc) return rc;
+    if (hm::tensor_debug_xwindow(s.tws, count, d.read.data(), d.rev.data(), d.o.data(), out, s.stream))
+        return fail(e, HM_ERR_CUDA, "%s", hm::tensor_last_error());
+    return HM_OK;
+}
+
+int hm_debug_dump_acts(hm_engine* e, int slot, int ctx, int layer, uint32_t first, uint32_t count, float* out, size_t out_floats,
+                       int32_t* n_pos, int32_t* channels)
+{
+    if (!e || !out || !n_pos || !channels || slot < 0 || slot >= e->n_slots || ctx < 0 || ctx > 2)
+        return fail(e, HM_ERR_ARG, "hm_debug_dump_acts: bad argument");
+    Slot& s = e->slots[slot];
+    if (!s.collected) return fail(e, HM_ERR_STATE, "hm_debug_dump_acts: collect slot %d first", slot);
+    if (!e->cfg.keep_debug) return fail(e, HM_ERR_STATE, "hm_debug_dump_acts: the engine was created without hm_config.keep_debug");
+    if (e->cfg.cnn_mode != HM_CNN_TENSOR || !e->have_model[ctx]) return fail(e, HM_ERR_STATE, "hm_debug_dump_acts: tensor path with context %d enabled only", ctx);
+    if ((uint64_t)first + count > s.n_calls || !count) return fail(e, HM_ERR_ARG, "hm_debug_dump_acts: bad range");
+    cudaSetDevice(e->cfg.device);
+    DebugSites d;
+    int rc = debug_sites(e, s, first, count, d);
+    if (rc) return rc;
+    // calls of other contexts in the range are reported as NaN rows
+    std::vector<uint32_t> pick;
+    for (uint32_t i = 0; i < count; ++i)
+        if (d.ctx[i] == ctx) pick.push_back(i);
+    DebugSites q;
+    for (uint32_t i : pick) { q.read.push_back(d.read[i]); q.rev.push_back(d.rev[i]); q.o.push_back(d.o[i]); q.compact_row.push_back(d.compact_row[i]); }
+    // re-run this context alone so that every map holds ITS values (a batch run leaves the last context's behind)
+    hm_timing keep = s.timing;
+    uint32_t launches = 0;
+    hm::TensorBatch tb{};
+    tb.d_bcode = s.d_bcode; tb.d_kinf = s.d_kinf; tb.d_base_off = s.d_base_off;
+    tb.d_site_read = s.d_site_read; tb.d_site_pos = s.d_site_pos; tb.d_site_out = s.d_site_out;
+    tb.h_base_off = s.host.base_off; tb.h_valid = s.host.valid; tb.h_read_pref = s.h_read_pref; tb.n_reads = s.n_reads;
+    for (int k = 0; k < 4; ++k) tb.class_count[k] = s.totals[k];
+    tb.d_logits = s.d_logits; tb.d_ml = s.d_ml;
+    const int run = hm::tensor_batch_run(e->tensor, 1u << ctx, s.tws, tb, s.stream, e->sm_count, &launches, &s.timing);
+    s.timing = keep;
+    if (run) return fail(e, HM_ERR_CUDA, "CUDA error in tensor CNN: %s", hm::tensor_last_error());
+    HM_CUDA(e, "debug activations", cudaStreamSynchronize(s.stream));
+    int nl = 0, C = 0;
+    std::vector<float> tmp((size_t)std::max<size_t>(pick.size(), 1) * 197 * 128);
+    if (hm::tensor_debug_site_acts(e->tensor[ctx], ctx, s.tws, (uint32_t)pick.size(), q.read.data(), q.rev.data(), q.o.data(), q.compact_row.data(),
+                                   layer, tmp.data(), &nl, &C, s.stream))
+        return fail(e, HM_ERR_STATE, "%s", hm::tensor_last_error());
+    *n_pos = nl;
+    *channels = C;
+    const size_t per = (size_t)nl * C;
+    if ((size_t)count * per > out_floats) return fail(e, HM_ERR_ARG, "hm_debug_dump_acts: output needs %zu floats", (size_t)count * per);
+    for (size_t i = 0; i < (size_t)count * per; ++i) out[i] = NAN;
+    for (size_t j = 0; j < pick.size(); ++j) memcpy(out + pick[j] * per, tmp.data() + j * per, per * sizeof(float));
+    return HM_OK;
+}
+
 int hm_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int cin, int cout, int n_src, const float* const* src, int n_terms,
                       const int32_t* term_src, const int32_t* term_shift, const float* weights, const float* bias, int conv1_taps,
                       const float* w2, const float* b2, const uint32_t* gather_rows, uint32_t gather_mask, float* out)

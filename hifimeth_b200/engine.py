@@ -63,7 +63,7 @@ class hm_timing(C.Structure):
 ABI_SYMBOLS = ["hm_engine_create", "hm_engine_destroy", "hm_last_error", "hm_version", "hm_batch_acquire", "hm_batch_submit",
                "hm_batch_collect", "hm_batch_timing", "hm_codev1_encode", "hm_codev1_decode", "hm_pack_record", "hm_pack_records",
                "hm_mod_record_bound", "hm_build_mod_record", "hm_build_mod_record_mm", "hm_parse_mod_record", "hm_ml_threshold", "hm_call_main", "hm_bam_copy", "hm_debug_dump_decode", "hm_debug_dump_ctx",
-               "hm_debug_dump_features", "hm_debug_dump_logits", "hm_debug_dense_op", "hm_debug_last_op_ms", "hm_microbench"]
+               "hm_debug_dump_features", "hm_debug_dump_logits", "hm_debug_dump_xmap", "hm_debug_dump_acts", "hm_debug_dense_op", "hm_debug_last_op_ms", "hm_microbench"]
 
 _lib = None
 
@@ -108,6 +108,9 @@ def load_library() -> C.CDLL:
     L.hm_debug_dump_ctx.argtypes = [C.c_void_p, C.c_int, _u8p]
     L.hm_debug_dump_features.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, _f32p]
     L.hm_debug_dump_logits.argtypes = [C.c_void_p, C.c_int, _f32p]
+    L.hm_debug_dump_xmap.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, _f32p]
+    L.hm_debug_dump_acts.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, _f32p, C.c_size_t, C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_int32)]
     L.hm_debug_dense_op.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(_f32p), C.c_int, _i32p, _i32p,
                                     _f32p, _f32p, C.c_int, _f32p, _f32p, _u32p, C.c_uint32, _f32p]
     L.hm_debug_last_op_ms.restype = C.c_float
@@ -263,6 +266,20 @@ class Engine:
         out = np.empty((count, 401, 8), np.float32)
         self._check(self.lib.hm_debug_dump_features(self.h, slot, first, count, out.ctypes.data_as(_f32p)), "hm_debug_dump_features")
         return out
+
+    def dump_xmap(self, slot: int, first: int, count: int) -> np.ndarray:
+        """[count,401,8] windows as the product CNN path holds them (X map, bf16 hi + lo re-summed)."""
+        out = np.empty((count, 401, 8), np.float32)
+        self._check(self.lib.hm_debug_dump_xmap(self.h, slot, C.c_uint32(first), C.c_uint32(count), out.ctypes.data_as(_f32p)), "hm_debug_dump_xmap")
+        return out
+
+    def dump_acts(self, slot: int, ctx: int, layer: int, first: int, count: int) -> np.ndarray:
+        """[count, n_l, C_l] per-site output of conv layer 1..8 as assembled from the product path's maps (NaN = never stored)."""
+        out = np.empty(count * 197 * 128, np.float32)
+        npos, ch = C.c_int32(), C.c_int32()
+        self._check(self.lib.hm_debug_dump_acts(self.h, slot, ctx, layer, C.c_uint32(first), C.c_uint32(count), out.ctypes.data_as(_f32p),
+                                                C.c_size_t(out.size), C.byref(npos), C.byref(ch)), "hm_debug_dump_acts")
+        return out[:count * npos.value * ch.value].reshape(count, npos.value, ch.value).copy()
 
     def dump_logits(self, slot: int, n_calls: int) -> np.ndarray:
         out = np.empty((max(n_calls, 1), 2), np.float32)

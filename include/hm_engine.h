@@ -217,6 +217,19 @@ int hm_debug_dump_features(hm_engine* e, int slot, uint32_t first, uint32_t coun
 /* Logits [n_calls][2] f32 in hm_call_batch order. */
 int hm_debug_dump_logits(hm_engine* e, int slot, float* out);
 
+/* What the PRODUCT CNN path actually eats: the [count][401][8] window of each call as held in the engine's X map (bf16 hi + lo,
+ * re-summed to f32), i.e. the features after track_features_kernel rather than the fp32 re-gather of hm_debug_dump_features.
+ * Same values as s_extract_kmer_features (src/app/hifimeth/eval_kmer_features.cpp:9-65) up to the 16-bit mantissa of hi + lo:
+ * one-hot columns and out-of-read rows exact, kinetics within 2^-16 relative.  Tensor path only. */
+int hm_debug_dump_xmap(hm_engine* e, int slot, uint32_t first, uint32_t count, float* out);
+/* Per-site activations of conv layer `layer` (1..8) of context ctx (0 CpG, 1 CHG, 2 CHH) for calls [first, first + count), all of
+ * which must be sites of that context: out [count][*n_pos][*channels] f32, position-major (the transpose of the reference's
+ * [C][L] layout, training/model_cnn.py:76-85), assembled from the maps the dense plan leaves in HBM.  NaN marks values the
+ * product path never stores (interior positions of layer 1: conv1 and conv2 are fused on chip).  Re-runs the context on the
+ * resident batch, which must fit one sub-batch.  Tensor path only. */
+int hm_debug_dump_acts(hm_engine* e, int slot, int ctx, int layer, uint32_t first, uint32_t count, float* out, size_t out_floats,
+                       int32_t* n_pos, int32_t* channels);
+
 /* One op of the tensor-core dense plan on caller-provided fp32 data (unit test of dense_gemm_kernel; no engine needed):
  *   out[r][:] = relu(bias + sum_k src[term_src[k]][r + term_shift[k]][:] . W_k),  r < rows (multiple of 128)
  * src maps are [rows_alloc][cin] f32, W_k = weights + k*cin*cout as [cin][cout].  conv1_taps > 0 selects the conv1 form:

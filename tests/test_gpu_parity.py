@@ -391,23 +391,24 @@ def test_full_size_config1_batch(lib_built, models):
 
 def test_call_cli_two_devices(lib_built, tmp_path):
     """`--devices 0,1`: one engine per GPU inside one process (per-device kernel attributes, per-thread current device), batches
-    dealt by the host work queue; the output equals the single-device run record for record.  Skipped on a one-GPU box."""
+    dealt by the host work queue; the output equals the single-device run record for record.  On a one-GPU box the second worker
+    runs on device 0 as well (`--devices 0,0`): the same queue, two engines, batches finishing out of order."""
     import subprocess
 
     try:
         n_gpu = len([l for l in subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout.splitlines() if l.startswith("GPU ")])
     except OSError:
         n_gpu = 0
-    if n_gpu < 2:
-        pytest.skip("needs two GPUs")
+    two_devs = "0,1" if n_gpu >= 2 else "0,0"
     _, reads = synth.make_reads(24, (1000, 4000), seed=77, flag_rev_every=5)
     bodies = [synth.record_body(r) for r in reads]
     src, one, two = tmp_path / "in.bam", tmp_path / "one.bam", tmp_path / "two.bam"
     synth.write_bam(src, bodies)
     exe = hme.PKG / "bin" / "hifimeth-b200"
-    for devs, dst in (("0", one), ("0,1", two)):
+    for devs, dst in (("0", one), (two_devs, two)):
         r = subprocess.run([str(exe), "call", "-b", "3", "--devices", devs, str(src), str(dst)], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr
+        assert ("on 2 worker(s)" in r.stderr) == (devs != "0")
     assert synth.read_bam(one)[2] == synth.read_bam(two)[2]
 
 
@@ -428,3 +429,73 @@ def test_read_stats_diagnostics(eng):
             assert int(got.stats_max[r, k]) == int(frames[k][a:b].max()), (r, k)
     ms, by, _ = eng.microbench(0, "stats", 0, 3)
     assert ms > 0 and by == 8.0 * batch.n_bases
+
+
+def test_product_feature_map_and_layer_activations_direct(lib_built, models):
+    """the maps the PRODUCT path computes on, compared with the oracle directly instead of through |dp| <= 1e-3.
+
+    X map (track_features_kernel, bf16 hi + lo): one-hot columns and out-of-read rows exact, kinetics within 2^-16 relative of the
+    oracle's fp32 features; both strands, flag 0x10, reads of length exactly -l and -l + 1.
+    Layers 1..8 (Y_l dense maps, F_l / G_l / T7 / T8 compact maps, the scatter copies of Y1): against
+    cnn_oracle.forward_logits(return_acts=True) within 1e-3 of the layer's scale -- a wrong halo row, tap or strand flip is O(1)."""
+    O = hmoracle.oracle()
+    _, reads = synth.make_reads(5, (1000, 2600), seed=4242, flag_rev_every=2)
+    _, r1000 = synth.make_reads(1, 1000, seed=4243)
+    _, r1001 = synth.make_reads(1, 1001, seed=4244)
+    batch = hme.pack_records_host([synth.record_body(r) for r in reads + r1000 + r1001], min_read_len=1000)
+    assert list(batch.valid) == [1] * 7
+    eng = hme.Engine(max_reads=16, max_bases=1 << 16, keep_debug=True)
+    try:
+        got = eng.call(batch)
+        want = O.batch_call(batch, models)
+        ctx = eng.dump_ctx(0, got.n_calls)
+        n_calls = got.n_calls
+        rng = np.random.default_rng(9)
+        # every read contributes its first, last and a few random calls (first / last sites have clipped windows)
+        picks = []
+        for r in range(batch.n_reads):
+            a, b = int(got.call_off[r]), int(got.call_off[r + 1])
+            picks += [a, a + 1, b - 1, b - 2] + [int(x) for x in rng.integers(a, b, 6)]
+        picks = sorted(set(picks))
+        read_of = np.searchsorted(got.call_off, picks, side="right") - 1
+        feats = {}
+        for k, r in zip(picks, read_of):
+            f_cpu = O.batch_features(batch, want, int(r), np.array([int(k - got.call_off[r])]))[0]
+            feats[k] = f_cpu
+            x = eng.dump_xmap(0, int(k), 1)[0]
+            assert (x[:, :4] == f_cpu[:, :4]).all(), (k, "one-hot")
+            outside = ~(f_cpu[:, :4].any(axis=1))  # rows beyond the read carry no base
+            assert (x[outside] == 0).all() and (f_cpu[outside] == 0).all(), (k, "rows outside the read")
+            assert (x[200, :4] == np.array([0, 1, 0, 0], np.float32)).all()  # centre row is the called C on its own strand
+            err = np.abs(x[:, 4:].astype(np.float64) - f_cpu[:, 4:]) 
+            assert (err <= np.abs(f_cpu[:, 4:]) * 2.0 ** -16).all(), (k, float(err.max()))
+        # ---- per-layer activations --------------------------------------------------------------------------------------
+        worst = {}
+        for c in range(3):
+            ks = [k for k in picks if ctx[k] == c]
+            assert len(ks) >= 6, c
+            f = np.stack([feats[k] for k in ks])
+            _, acts = cnn_oracle.forward_logits(models[c], f, return_acts=True)
+            for layer in range(1, 9):
+                ref = np.transpose(acts[layer], (0, 2, 1))  # [B, C, n] -> [B, n, C]
+                scale = max(1.0, float(np.abs(ref).max()))
+                seen = 0
+                for j, k in enumerate(ks):
+                    a = eng.dump_acts(0, c, layer, int(k), 1)[0]
+                    assert a.shape == ref[j].shape, (c, layer, a.shape, ref[j].shape)
+                    have = ~np.isnan(a)
+                    if layer >= 2:
+                        assert have.all(), (c, layer)
+                    else:
+                        assert have[0].all() and have[-1].all() and have.any(axis=1).sum() >= 4  # F1, G1, the rows scattered for F2 / G2
+                    d = np.abs(a[have] - ref[j][have]).max()
+                    worst[(c, layer)] = max(worst.get((c, layer), 0.0), float(d) / scale)
+                    seen += int(have.sum())
+                assert seen > 0
+        print("max |d act| / layer scale:", {k: f"{v:.1e}" for k, v in worst.items()})
+        assert max(worst.values()) <= 1e-3, worst
+        # the dump leaves the engine usable and the results unchanged
+        again = eng.call(batch)
+        assert (again.ml == got.ml).all() and (again.qoff == got.qoff).all()
+    finally:
+        eng.close()
