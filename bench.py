@@ -9,12 +9,23 @@ path over that batch through the C ABI: kinetics decode -> site scan -> feature 
           events the library records on the stream it launches on, max over ranks.
   e2e     the same through hm_batch_submit / hm_batch_collect with HOST buffers: pinned staging -> H2D -> kernels -> D2H of
           call_off / n_fwd / qoff / ML, wall clock between device synchronisations.
-  roofline   the CNN's tensor-core kernel family (dense_gemm_kernel): algorithmic FLOPs of the step (22 297 600 per
-          CpG/CHG site, 22 881 280 per CHH site) / summed device time of its launches in the step.
+  roofline   the CNN's tensor-core kernel family: `achieved` / `frac` = ALGORITHMIC FLOPs of the step (22 297 600 per
+          CpG/CHG site, 22 881 280 per CHH site) / device time of the dense plan; next to it what the silicon
+          did: `executed_tflops` (FLOPs the launches issued, counted by the engine) and `executed_frac` of the sustained bf16
+          peak, `traffic` (DRAM bytes of the family per step from the committed ncu launch list named in `traffic_source`) and
+          `hbm_frac` = traffic / time / measured HBM peak, `algorithmic_bytes` (what has to cross HBM: the H2D + D2H bytes).
   cpu_baseline / --impl reference   the reference-faithful CPU pipeline on this host's cores: the reference's own feature
-          code (oracle/_ref, compiled from /root/reference) or its C restatement + fp32 torch forward of the ONNX weights.
+          code (oracle/_ref, compiled from /root/reference) or its C restatement + fp32 torch forward of the ONNX weights;
+          site batch 512 (its best case) as the headline, the reference's default 32 and configs[0] (CpG only) as variants.
+  gpu_library_baseline / --impl torchscript-gpu   the reference's app-gpu design re-hosted on this GPU: torch.jit.load of
+          models/*.pt on cuda at batch 4096 (src/app-gpu/hifimeth-gpu/5mc_call_gpu.cpp:194-218,309-334), CNN forward only,
+          fp32 and TF32 -- the library kernels the hand-written path has to beat.
+  queue   the PRODUCT's multi-GPU path: ONE process, `hifimeth-b200 call --devices 0..N-1` on a synthetic BAM of
+          configs[2] shape (20 kb reads), wall clock from process start to output closed, with the CLI's phase timers.
 
-Reads are independent, so N GPUs = N engines on N batches with no collective ("scaling": "weak").
+Reads are independent, so N GPUs = N engines with no collective ("scaling": "weak").  Under torchrun every rank times its
+own batch (`value`, device time, max over ranks = `kernel_scaling`); then rank 0 alone runs the one-process host work queue
+over all N devices and reports it as `queue` -- and, for N > 1, as `e2e` (BAM in -> mod BAM out is the call a user makes).
 """
 from __future__ import annotations
 
@@ -101,7 +112,162 @@ def physical_cores() -> int:
     return max(1, n)
 
 
-def cpu_pipeline(n_reads: int, threads: int, site_batch: int = 512):
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def traffic_record():
+    """profiles/traffic.json: DRAM bytes per step of the CNN kernel family, condensed from a committed ncu launch list by
+    tools/traffic_from_ncu.py.  None when absent."""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        d = json.loads(p.read_text())
+        return float(d["cnn_dram_bytes_per_step"]), int(d["reads"]), str(d["source"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
+def gpu_library_baseline(device: int, feats_by_ctx, iters: int = 8):
+    """torch.jit.load(models/*.pt).cuda() forward at batch 4096 on real feature windows: what the reference's app-gpu binary
+    runs per batch (5mc_call_gpu.cpp:194-218), minus its CPU feature extraction and PCIe copies.  Sites/s, fp32 and TF32."""
+    import torch
+
+    out = {"kind": "torch.jit.load(models/{CpG,CHG,CHH}.pt).cuda(), batch 4096, CNN forward only (features resident in HBM, "
+                   "no feature extraction, no H2D); cuDNN/cuBLAS kernels of torch " + torch.__version__,
+           "batch": 4096, "unit": "sites/s"}
+    dev = torch.device("cuda", device)
+    for mode in ("fp32", "tf32"):
+        torch.backends.cudnn.allow_tf32 = mode == "tf32"
+        torch.backends.cuda.matmul.allow_tf32 = mode == "tf32"
+        tot_sites, tot_s, per_ctx = 0, 0.0, {}
+        for name, f in feats_by_ctx.items():
+            m = torch.jit.load(str(ROOT / "models" / f"{name}.pt"), map_location=dev).eval()
+            x = torch.from_numpy(f).to(dev)
+            with torch.no_grad():
+                for _ in range(3):
+                    m(x)
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(iters):
+                    m(x)
+                e1.record()
+                torch.cuda.synchronize(dev)
+            dt = e0.elapsed_time(e1) / 1e3
+            per_ctx[name] = len(f) * iters / dt
+            tot_sites += len(f) * iters
+            tot_s += dt
+        out[mode] = {"value": tot_sites / tot_s, "by_context": per_ctx}
+    torch.backends.cudnn.allow_tf32 = True
+    out["value"] = out["tf32"]["value"]
+    out["note"] = "value = TF32 (torch's default for cuDNN convolutions); the site mix is 1:1:1 here, CHH-heavy in the workload"
+    return out
+
+
+def write_queue_bam(path, n_reads: int, read_len: int, seed: int) -> dict:
+    """Synthetic BAM of configs[2] shape for the queue bench.  500 distinct reads are generated and BGZF-compressed once; that
+    run of blocks is written n_reads / 500 times (BGZF members are independent, and the BAM stream is the concatenation of
+    their payloads), so a multi-GB input costs seconds to make.  Says so in the returned description."""
+    import struct
+    import zlib
+
+    from hifimeth_b200 import synth
+
+    def bgzf(data: bytes, level: int = 1) -> bytes:
+        out = bytearray()
+        for off in range(0, len(data), 0xff00):
+            chunk = data[off:off + 0xff00]
+            co = zlib.compressobj(level, zlib.DEFLATED, -15)
+            comp = co.compress(chunk) + co.flush()
+            out += struct.pack("<BBBBIBBH", 31, 139, 8, 4, 0, 0, 255, 6) + b"BC" + struct.pack("<HH", 2, len(comp) + 25)
+            out += comp + struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk))
+        return bytes(out)
+
+    distinct = min(500, n_reads)
+    _, reads = synth.make_reads(distinct, read_len, seed)
+    body = bytearray()
+    for r in reads:
+        b = synth.record_body(r)
+        body += struct.pack("<i", len(b)) + b
+    text = b"@HD\tVN:1.6\tSO:unknown\n@RG\tID:synth\tPL:PACBIO\n"
+    head = bgzf(b"BAM\1" + struct.pack("<i", len(text)) + text + struct.pack("<i", 0))
+    run = bgzf(bytes(body))
+    reps = max(1, n_reads // distinct)
+    with open(path, "wb") as f:
+        f.write(head)
+        for _ in range(reps):
+            f.write(run)
+        f.write(bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0]))
+    return {"reads": reps * distinct, "read_len": read_len, "bam_bytes": len(head) + reps * len(run) + 28, "raw_bytes": reps * len(body),
+            "note": f"{distinct} distinct reads x {reps} (the same BGZF blocks repeated), input level 1"}
+
+
+def queue_bench(n_gpus: int, reads_per_gpu: int, read_len: int = 20000, level: int = 6, repeat: int = 1) -> dict:
+    """The product's multi-GPU path: ONE process, one reader, one worker per device, one ordered writer
+    (hifimeth_b200/csrc/call_main.cpp; reference shape: src/app/hifimeth/mod_main.cpp:330-388).  Wall clock of the process."""
+    import re
+    import tempfile
+
+    from hifimeth_b200 import build as hmbuild
+
+    tmp = Path(tempfile.mkdtemp(prefix="hm_queue_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None))
+    src, dst = tmp / "in.bam", tmp / "mod.bam"
+    try:
+        t0 = time.perf_counter()
+        info = write_queue_bam(src, reads_per_gpu * n_gpus, read_len, SEED + 7)
+        gen_s = time.perf_counter() - t0
+        cmd = [str(hmbuild.EXE), "call", "--level", str(level), "--devices", ",".join(str(i) for i in range(n_gpus)), str(src), str(dst)]
+        best = None
+        for _ in range(repeat):
+            t0 = time.perf_counter()
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            wall = time.perf_counter() - t0
+            if r.returncode != 0:
+                return {"error": r.stderr.strip()[-400:]}
+            if best is None or wall < best[0]:
+                best = (wall, r.stderr)
+        wall, log = best
+        m = re.search(r"CpG (\d+), CHG (\d+), CHH (\d+)", log)
+        sites = sum(int(x) for x in m.groups())
+        ph = re.search(r"read\+inflate ([\d.]+), engine create ([\d.]+), pack ([\d.]+), submit ([\d.]+), collect\(wait\) ([\d.]+), "
+                       r"assemble ([\d.]+), write\+deflate ([\d.]+); (\d+) batches of <= (\d+) bases on (\d+) worker\(s\), (\d+) host threads", log)
+        tl = re.search(r"engines ready ([\d.]+), input inflated ([\d.]+), last batch collected ([\d.]+), engines destroyed ([\d.]+), output closed ([\d.]+)", log)
+        out = {"value": sites / wall, "unit": "sites/s", "reads_per_s": info["reads"] / wall, "wall_s": wall, "sites": sites, "n_gpus": n_gpus,
+               "workload": f"configs[2] shape: {info['reads']} reads x {read_len} b BAM -> mod BAM, one process, --devices 0..{n_gpus - 1}, output level {level}",
+               "input": info, "out_bam_bytes": dst.stat().st_size, "gen_s": gen_s, "host_threads": os.cpu_count(), "cmd": " ".join(cmd[1:-2])}
+        if ph:
+            keys = ("read_inflate", "engine_create", "pack", "submit", "collect_wait", "assemble", "write_deflate")
+            out["phase_s_summed_per_role"] = {k: float(v) for k, v in zip(keys, ph.groups()[:7])}
+            out["batches"], out["max_bases_per_batch"] = int(ph.group(8)), int(ph.group(9))
+            out["host_threads"] = int(ph.group(11))
+        if tl:
+            ready, inflated, collected, destroyed, closed = (float(x) for x in tl.groups())
+            out["timeline_s"] = {"engines_ready": ready, "input_inflated": inflated, "last_batch_collected": collected,
+                                 "engines_destroyed": destroyed, "output_closed": closed}
+            if collected > ready:
+                out["steady_sites_per_s"] = sites / (collected - ready)
+            # the phase that ends last names the limiter
+            lim = "reader (BGZF inflate + framing)" if inflated >= collected - 0.05 else \
+                  "writer (record assembly hand-over + BGZF deflate)" if closed - destroyed > 0.25 * wall else \
+                  "engine creation (CUDA context + pinned / device allocation)" if ready > 0.5 * wall else "GPU workers"
+            out["limiter"] = lim
+        return out
+    finally:
+        for p in (src, dst):
+            p.unlink(missing_ok=True)
+        try:
+            tmp.rmdir()
+        except OSError:
+            pass
+
+
+def cpu_pipeline(n_reads: int, threads: int, site_batch: int = 512, ctx_mask: int = 7):
     """The reference-faithful CPU path on a bounded sample of the workload.  Returns (sites, reads, seconds, kind)."""
     import torch
     from concurrent.futures import ThreadPoolExecutor
@@ -117,11 +283,14 @@ def cpu_pipeline(n_reads: int, threads: int, site_batch: int = 512):
     bodies = [synth.record_body(r) for r in reads] if R.available else None
     kind = "reference feature code (oracle/_ref) + fp32 torch forward of the ONNX weights" if R.available else "C restatement (oracle/) + fp32 torch forward"
     t0 = time.perf_counter()
-    sites = O.batch_sites(batch, 7)
+    sites = O.batch_sites(batch, ctx_mask)
 
     def feats(r):
         out = []
         for c in range(3):
+            if not ctx_mask & (1 << c):
+                out.append(np.zeros((0, 401, 8), np.float32))
+                continue
             if R.available:
                 n = int((sites[r]["ctx"] == c).sum())
                 f = R.extract_features(bodies[r], c, 0, n)[0] if n else np.zeros((0, 401, 8), np.float32)
@@ -160,7 +329,8 @@ def run_reference(args, rank: int, world: int):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"configs[1]: {N_READS} reads x {READ_LEN} b, CpG+CHG+CHH; each step a bounded sample of {n_reads} reads"},
             "reads_per_s": float(np.mean(reads_s)),
-            "cpu_baseline": {"value": v, "unit": "sites/s", "cores": threads, "kind": "port", "sample": f"{n_reads} reads x {READ_LEN} b per step; {kind}; site batch 512"},
+            "cpu_baseline": {"value": v, "unit": "sites/s", "cores": threads, "kind": "port", "cpu_model": cpu_model(),
+                             "sample": f"{n_reads} reads x {READ_LEN} b per step; {kind}; site batch 512"},
             "e2e": {"value": v, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -173,6 +343,10 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--reads", type=int, default=N_READS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch.jit GPU library baseline")
+    ap.add_argument("--no-queue", action="store_true", help="skip the one-process host-work-queue run (hifimeth-b200 call)")
+    ap.add_argument("--queue-reads", type=int, default=int(os.environ.get("HM_QUEUE_READS", "4000")), help="20 kb reads per GPU in the queue run")
+    ap.add_argument("--queue-level", type=int, default=6, help="BGZF level of the queue run's output (htslib's default is 6)")
     ap.add_argument("--cnn-mode", type=int, default=int(os.environ.get("HM_CNN_MODE", "0")))
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -180,6 +354,17 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.impl == "torchscript-gpu":
+        if rank == 0:
+            import torch
+
+            torch.cuda.set_device(local)
+            rng = np.random.default_rng(SEED)
+            feats = {n: rng.random((4096, 401, 8), dtype=np.float32) for n in ("CpG", "CHG", "CHH")}
+            line = gpu_library_baseline(local, feats)
+            line.update({"impl": "torchscript-gpu", "metric": "CpG+CHG+CHH sites/sec (CNN forward only)", "n_gpus": 1, "data": "synthetic (random feature windows)"})
+            print(json.dumps(line), flush=True)
         return
     args.warmup = max(args.warmup, 3)
 
@@ -201,25 +386,34 @@ def main():
         torch.cuda.synchronize()
 
     batch, _ = synth.make_reads(args.reads, READ_LEN, SEED + rank)
-    eng = hme.Engine(device=local, n_slots=1, max_reads=args.reads, max_bases=batch.n_bases + 1024, cnn_mode=args.cnn_mode)
-    n = eng.stage(0, batch)
+    eng = hme.Engine(device=local, n_slots=2, max_reads=args.reads, max_bases=batch.n_bases + 1024, cnn_mode=args.cnn_mode)
 
-    # ---- e2e: host buffers, H2D + kernels + D2H every step ---------------------------------------------------------------------
-    for _ in range(args.warmup):
-        eng.submit(0, n)
-        res = eng.collect(0, copy=False)
+    # ---- e2e: HOST buffers every step -- the batch is packed into the slot's pinned SoA staging (eng.stage), copied H2D, run, and
+    # its calls copied D2H into pinned memory.  Two staging slots, as the `call` driver uses them: step i + 1 is packed and submitted
+    # while step i is on the device.  Wall clock between device synchronisations.
+    def e2e_loop(steps):
+        res, h2d, d2h = None, 0, 0
+        for i in range(steps):
+            slot = i & 1
+            n_ = eng.stage(slot, batch)
+            eng.submit(slot, n_)
+            if i:
+                res = eng.collect(slot ^ 1, copy=False)
+        res = eng.collect((steps - 1) & 1, copy=False)
+        t = eng.timing((steps - 1) & 1)
+        return res, t.h2d_bytes, t.d2h_bytes
+
+    res, _, _ = e2e_loop(max(args.warmup, 2))
     sites_step = res.n_calls
     n_sites = res.n_sites
     barrier()
     t0 = time.perf_counter()
-    h2d = d2h = 0
-    for _ in range(args.steps):
-        eng.submit(0, n)
-        eng.collect(0, copy=False)
-        t = eng.timing(0)
-        h2d, d2h = t.h2d_bytes, t.d2h_bytes
+    _, h2d, d2h = e2e_loop(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
+    n = eng.stage(0, batch)
+    eng.submit(0, n)
+    eng.collect(0, copy=False)
 
     # ---- kernel-only: inputs resident in HBM -------------------------------------------------------------------------------------
     flags = hme.HM_SUBMIT_SKIP_H2D | hme.HM_SUBMIT_SKIP_D2H
@@ -229,7 +423,7 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
-    dev_ms = top_ms = 0.0
+    dev_ms = top_ms = exec_flops = 0.0
     launches = top_launches = 0
     stage_ms = np.zeros(4)
     t0 = time.perf_counter()
@@ -239,6 +433,7 @@ def main():
         t = eng.timing(0)
         dev_ms += t.total_ms
         top_ms += t.top_kernel_ms
+        exec_flops += t.executed_flops
         launches += t.kernel_launches
         top_launches += t.top_kernel_launches
         stage_ms += np.array([t.decode_ms, t.scan_ms, t.cnn_ms, t.d2h_ms])
@@ -246,18 +441,58 @@ def main():
     wall_s = time.perf_counter() - t0
     clocks = sampler.stop()
 
-    times = torch.tensor([dev_ms / 1e3, e2e_s, top_ms / 1e3, wall_s], dtype=torch.float64, device="cuda")
+    # real feature windows for the GPU library baseline (validation kernel; needs a keep_debug engine: a small second one)
+    lib_base = None
+    if rank == 0 and world == 1 and not args.no_gpu_baseline and args.cnn_mode == 0:
+        try:
+            small, _ = synth.make_reads(8, READ_LEN, SEED + 99)
+            e2 = hme.Engine(device=local, n_slots=1, max_reads=8, max_bases=small.n_bases + 1024, keep_debug=True)
+            r2 = e2.call(small)
+            ctx = e2.dump_ctx(0, r2.n_calls)
+            feats = {}
+            for c, name in enumerate(("CpG", "CHG", "CHH")):
+                idx = np.nonzero(ctx == c)[0][:4096]
+                f = np.concatenate([e2.dump_features(0, int(k), 1) for k in idx[:256]])
+                feats[name] = np.tile(f, (16, 1, 1))[:4096]  # 256 distinct real windows, tiled to the batch of 4096
+            e2.close()
+            lib_base = gpu_library_baseline(local, feats)
+        except Exception as ex:  # the baseline must never take the bench line down
+            lib_base = {"error": repr(ex)[:300]}
+
+    times = torch.tensor([dev_ms / 1e3, e2e_s, top_ms / 1e3, wall_s, exec_flops], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(sites_step), float(launches), float(args.reads)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    dev_s, e2e_s, top_s, wall_s = (float(x) for x in times.tolist())
+    dev_s, e2e_s, top_s, wall_s, _ = (float(x) for x in times.tolist())
     sites_all, launches_all, reads_all = (float(x) for x in tot.tolist())
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()  # every rank has released its GPU: rank 0 now drives all N devices from one process
 
     if rank == 0:
         peak_tf, peak_gbs, peak_src = peaks()
         flop_step = FLOP_K11 * (n_sites[0] + n_sites[1]) + FLOP_K13 * n_sites[2]
         achieved = flop_step * args.steps / max(top_s, 1e-9) / 1e12 if top_s > 0 else 0.0
+        # what the silicon did (rank 0's own counters; every rank runs the same plan on its own batch)
+        executed = exec_flops / max(top_ms / 1e3, 1e-9) / 1e12 if top_ms > 0 else 0.0
+        tr = traffic_record()
+        traffic = tr[0] * args.reads / tr[1] if tr else None
+        hbm_frac = traffic / (top_ms / 1e3 / args.steps) / (peak_gbs * 1e9) if tr and top_ms > 0 else None
+        executed_frac = executed / peak_tf
+        roof = {"bound": "hbm" if (hbm_frac or 0) > executed_frac else "tensor",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "frac_is": "ALGORITHMIC per-site FLOPs (SURVEY.md s8d) / plan time / sustained bf16 peak; the plan shares conv work between "
+                           "overlapping windows and pays 3 split-precision passes, so read it with executed_frac and hbm_frac",
+                "algorithmic_flops_per_step": flop_step,
+                "executed_tflops": executed, "executed_frac": executed_frac, "executed_flops_per_step": exec_flops / max(args.steps, 1),
+                "traffic": traffic, "traffic_unit": "DRAM bytes per step (read + write) of the kernel family", "hbm_frac": hbm_frac,
+                "hbm_peak_gbs": peak_gbs, "traffic_source": (tr[2] + f" ({tr[1]}-read step, scaled by reads; tools/traffic_from_ncu.py)") if tr else None,
+                "algorithmic_bytes": int(h2d + d2h),
+                "kernel": "dense_gemm2_kernel + dense_fused12_kernel + dense_gemm_kernel (every op of the dense plan)",
+                "plan_ms_per_step": top_ms / max(args.steps, 1), "plan_ms_is": "CUDA events around all launches of the family on their stream (includes "
+                "the ~1 % of small kernels between them)", "launches_per_step": top_launches // max(args.steps, 1), "peak_source": peak_src}
         line = {
             "metric": "CpG+CHG+CHH sites/sec", "value": sites_all * args.steps / dev_s, "unit": "sites/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -268,27 +503,39 @@ def main():
             "reads_per_s": reads_all * args.steps / dev_s,
             "wall_ms_per_step": 1e3 * wall_s / args.steps,
             "stage_ms_per_step": {k: float(v) / args.steps for k, v in zip(("decode", "scan", "cnn", "d2h"), stage_ms)},
-            "e2e": {"value": sites_all * args.steps / e2e_s, "unit": "sites/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": sites_all * args.steps / e2e_s, "unit": "sites/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "what": "hm_batch_acquire / fill the pinned SoA staging / hm_batch_submit / hm_batch_collect every step, two slots pipelined, wall clock"},
             "gpu_launches": int(launches_all),
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         # DRAM read+write of the kernel family per step: ncu, profiles/r1_launches_v9_final.csv (51.3 GB
-                         # for a 128-read step, scaled by reads; 58.2 GB before conv1 + conv2 were fused)
-                         "traffic": 51.3e9 * args.reads / 128.0, "traffic_unit": "bytes per step",
-                         "kernel": "dense_gemm2_kernel + dense_fused12_kernel + dense_gemm_kernel (every op of the dense plan)", "launches_per_step": top_launches // max(args.steps, 1), "peak_source": peak_src,
-                         "note": "achieved = algorithmic FLOPs of the per-site network / summed device time of the kernel family; the dense plan "
-                                 "shares conv work between overlapping windows, so executed FLOPs are lower (DESIGN.md)"},
+            "roofline": roof,
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:  # the CPU baseline is a rank-0, N = 1 measurement
             threads = physical_cores()
             nr = int(os.environ.get("HM_CPU_SAMPLE_READS", "32"))
             s, r, dt, kind = cpu_pipeline(nr, threads)
-            line["cpu_baseline"] = {"value": s / dt, "unit": "sites/s", "cores": threads, "kind": "port",
+            line["cpu_baseline"] = {"value": s / dt, "unit": "sites/s", "cores": threads, "kind": "port", "cpu_model": cpu_model(),
                                     "sample": f"{nr} reads x {READ_LEN} b ({s} sites, {dt:.1f} s); {kind}; site batch 512"}
+            # the reference's default site batch (-s 32, src/app/hifimeth/mod_options.cpp:11) and configs[0] (CpG only)
+            nv = max(2, nr // 4)
+            s32, _, dt32, _ = cpu_pipeline(nv, threads, site_batch=32)
+            sc, _, dtc, _ = cpu_pipeline(nr, threads, site_batch=32, ctx_mask=1)
+            line["cpu_baseline"]["variants"] = [
+                {"what": "all contexts, site batch 32 (the reference's default -s)", "value": s32 / dt32, "sample": f"{nv} reads ({s32} sites, {dt32:.1f} s)"},
+                {"what": "configs[0]: CpG only, site batch 32", "value": sc / dtc, "sample": f"{nr} reads ({sc} sites, {dtc:.1f} s)"}]
+            line["cpu_baseline"]["readme_derived"] = "README.md:31 implies 150-220 k sites/s on 48 threads with OpenVINO (3-4.6 k sites/s/thread); OpenVINO is not installable here"
+        if lib_base is not None:
+            line["gpu_library_baseline"] = lib_base
+        if not args.no_queue and args.cnn_mode == 0:
+            q = queue_bench(world, args.queue_reads, level=args.queue_level)
+            line["queue"] = q
+            line["kernel_scaling"] = {"value": line["value"], "unit": "sites/s", "what": "N ranks, N resident batches, device time, max over ranks"}
+            if world > 1 and "value" in q:
+                # for N > 1 the end-to-end number IS the product's one-process queue path (BAM in -> mod BAM out)
+                line["e2e_per_rank_abi"] = line["e2e"]
+                line["e2e"] = {"value": q["value"], "unit": "sites/s", "h2d_bytes_per_step": int(q["input"]["reads"] * (4.5 * q["input"]["read_len"] + 16)),
+                               "d2h_bytes_per_step": int(q["sites"] * 5 + q["input"]["reads"] * 8), "step": "the whole BAM",
+                               "what": "hifimeth-b200 call --devices 0..N-1: BAM inflate, packing, H2D, kernels, D2H, MM/ML records, deflate; process wall clock incl. engine creation"}
         print(json.dumps(line), flush=True)
-    eng.close()
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -662,6 +662,7 @@ struct TensorWorkspaceImpl {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // shape of the last tensor_batch_run (debug hooks): sub-batches, compact groups per context, rows of the X map
     uint32_t last_subs = 0, last_groups[3] = {0, 0, 0}, last_x_rows = 0;
+    double macs = 0;  // executed MACs of the running batch, one precision pass (launch_op / launch_fused12 add to it)
 };
 
 int tensor_workspace_alloc(TensorWorkspace& w, uint32_t max_bases, uint32_t max_reads, uint32_t max_rows)
@@ -766,7 +767,7 @@ DenseOp patch_op(const DevOp& d, const TensorWorkspaceImpl& s, uint32_t n_tiles,
 long long* g_f12_dbg = nullptr;
 
 // conv1 + conv2 of `rows` dense rows in one launch (dense_fused12_kernel): tiles of 124 output rows, CTA pairs.
-int launch_fused12(const DevOp& d1, const DevOp& d2, const TensorWorkspaceImpl& s, uint32_t rows, int sm_count, cudaStream_t stream)
+int launch_fused12(const DevOp& d1, const DevOp& d2, TensorWorkspaceImpl& s, uint32_t rows, int sm_count, cudaStream_t stream)
 {
     Fused12Op f{};
     // HM_F12_STAMPS=1: CTA 0 of every launch stamps its first tiles; the last launch's stamps are printed after the batch
@@ -777,6 +778,7 @@ int launch_fused12(const DevOp& d1, const DevOp& d2, const TensorWorkspaceImpl& 
         f.dbg = g_f12_dbg;
     }
     f.n_tiles = (rows + kF12OutRows - 1) / kF12OutRows;
+    s.macs += (double)((f.n_tiles + 1) / 2 * 2) * kTileRows * (d1.macs_per_row + d2.macs_per_row);  // 128 rows computed per 124 kept
     f.c1 = patch_op(d1, s, f.n_tiles, nullptr);
     f.c2 = patch_op(d2, s, f.n_tiles, nullptr);
     cudaLaunchConfig_t cfg{};
@@ -792,9 +794,10 @@ int launch_fused12(const DevOp& d1, const DevOp& d2, const TensorWorkspaceImpl& 
     return cudaLaunchKernelEx(&cfg, dense_fused12_kernel, f) == cudaSuccess ? 0 : -1;
 }
 
-int launch_op(const DevOp& d, const TensorWorkspaceImpl& s, uint32_t n_tiles, float* logit_out, int sm_count, cudaStream_t stream)
+int launch_op(const DevOp& d, TensorWorkspaceImpl& s, uint32_t n_tiles, float* logit_out, int sm_count, cudaStream_t stream)
 {
     DenseOp p = patch_op(d, s, n_tiles, logit_out);
+    s.macs += (double)(d.two_cta ? (n_tiles + 1) / 2 * 2 : n_tiles) * kTileRows * d.macs_per_row;
     uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)sm_count);
     if (d.two_cta) grid = std::min<uint32_t>(((n_tiles + 1) / 2) * 2, (uint32_t)sm_count & ~1u);
     cudaLaunchConfig_t cfg{};
@@ -884,6 +887,7 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
     // ---- the plan, sub-batch by sub-batch -------------------------------------------------------------------------------------
     TCUDA("dense plan", cudaEventRecord(s->ev0, stream));
     uint32_t dense_launches = 0;
+    s->macs = 0;
     // HM_OP_TIMES=1: per-op device time (events between launches; serialises nothing, but PDL overlap is attributed to the
     // earlier op), summed over the sub-batches of this batch and printed to stderr.  Analysis aid, off by default.
     static const bool prof = getenv("HM_OP_TIMES") != nullptr;
@@ -1043,7 +1047,10 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
             fprintf(stderr, "\n");
         }
     }
-    if (timing) timing->top_kernel_launches = dense_launches;
+    if (timing) {
+        timing->top_kernel_launches = dense_launches;
+        timing->executed_flops = s->macs * 2.0 * 3.0;
+    }
     return 0;
 }
 

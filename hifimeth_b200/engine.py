@@ -57,7 +57,8 @@ class hm_call_batch(C.Structure):
 class hm_timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("decode_ms", C.c_float), ("scan_ms", C.c_float), ("cnn_ms", C.c_float),
                 ("d2h_ms", C.c_float), ("total_ms", C.c_float), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("kernel_launches", C.c_uint32), ("top_kernel_ms", C.c_float), ("top_kernel_launches", C.c_uint32)]
+                ("kernel_launches", C.c_uint32), ("top_kernel_ms", C.c_float), ("top_kernel_launches", C.c_uint32),
+                ("executed_flops", C.c_double)]
 
 
 ABI_SYMBOLS = ["hm_engine_create", "hm_engine_destroy", "hm_last_error", "hm_version", "hm_batch_acquire", "hm_batch_submit",

@@ -123,8 +123,12 @@ typedef struct hm_timing {
     float h2d_ms, decode_ms, scan_ms, cnn_ms, d2h_ms, total_ms;
     uint64_t h2d_bytes, d2h_bytes;
     uint32_t kernel_launches;   /* kernels of this library launched by the submit */
-    float top_kernel_ms;        /* summed duration of the dominant kernel family (CNN GEMM tiles) */
+    float top_kernel_ms;        /* device time of the dense plan: CUDA events around all launches of the CNN kernel family of this
+                                   submit (the tensor-core kernels plus the ~1 % of small kernels between them) */
     uint32_t top_kernel_launches;
+    double executed_flops;      /* tensor-core FLOPs those launches ISSUED: 2 x MACs x 3 split-precision passes over the rows they
+                                   process (the dense plan shares conv work between windows, so this differs from the per-site
+                                   algorithmic count) */
 } hm_timing;
 
 #define HM_SUBMIT_SKIP_H2D 1u   /* inputs of this slot are already resident in HBM (re-run) */

@@ -147,3 +147,41 @@ def test_oracle_vs_compiled_reference_fresh_inputs():
         # MM/ML round trip through the reference's own parser (src/corelib/bam_mod_parser.cpp:231-286)
         qq, ss, pp = R.parse_mods(rec, len(q) + 1)
         assert (qq == q).all() and (pp == ml).all() and (ss[:nf] == 0).all() and (ss[nf:] == 1).all()
+
+
+def _forward_fp64_numpy(w, feats):
+    """An independent statement of the graph (training/model_cnn.py:76-85): fp64, explicit zero padding and one einsum per conv
+    tap -- no torch, no conv primitive, nothing shared with cnn_oracle.forward_logits but the parsed weights."""
+    x = np.transpose(feats.astype(np.float64), (0, 2, 1))                      # [B, 8, 401]
+    g, b, m, v = (t.astype(np.float64) for t in w.bn0)
+    x = (x - m[None, :, None]) / np.sqrt(v[None, :, None] + w.bn_eps) * g[None, :, None] + b[None, :, None]
+    for cw, cb in w.convs:
+        cw = cw.astype(np.float64)
+        k = cw.shape[2]
+        xp = np.pad(x, ((0, 0), (0, 0), (1, 1)))                                # conv zero padding comes AFTER bn0
+        n_out = (xp.shape[2] - k) // 2 + 1
+        y = np.zeros((x.shape[0], cw.shape[0], n_out))
+        for j in range(k):
+            y += np.einsum("oc,bct->bot", cw[:, :, j], xp[:, :, j:j + 2 * n_out - 1:2])
+        x = np.maximum(y + cb.astype(np.float64)[None, :, None], 0.0)
+    x = x.reshape(x.shape[0], -1)                                              # channel-major flatten: idx = c * 2 + t
+    x = np.maximum(x @ w.fcs[0][0].astype(np.float64).T + w.fcs[0][1], 0.0)
+    return x @ w.fcs[1][0].astype(np.float64).T + w.fcs[1][1]
+
+
+def test_cnn_oracle_against_independent_fp64_forward(golden):
+    """CHG has no TorchScript pin (CHG.pt is another checkpoint): its oracle is pinned here, like the other two
+    contexts, to an independent fp64 numpy forward of the same ONNX weights on the golden feature windows."""
+    models = cnn_oracle.load_models(ROOT / "models")
+    n = {0: 0, 1: 0, 2: 0}
+    for i in range(int(golden["n_reads"])):
+        for c in range(3):
+            if f"feat{i}_{c}" not in golden:
+                continue
+            f = golden[f"feat{i}_{c}"]
+            want = _forward_fp64_numpy(models[c], f)
+            got = cnn_oracle.forward_logits(models[c], f)
+            assert np.abs(got - want).max() < 2e-5, (i, c, float(np.abs(got - want).max()))
+            assert np.abs(golden[f"logits{i}_{c}"] - want).max() < 2e-5
+            n[c] += len(f)
+    assert min(n.values()) > 20, n
