@@ -82,6 +82,12 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar)
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- register redistribution between warp roles (whole warpgroups = 4 consecutive warps, .sync.aligned) -------------------------
+template <int kRegs>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <int kRegs>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+
 // ---- tcgen05: TMEM allocation ---------------------------------------------------------------------------------
 // Whole-warp, .sync.aligned.  ncols: power of two in [32, 512].
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols)
@@ -190,6 +196,61 @@ __device__ __forceinline__ void mma_bf16_w(uint32_t tmem_d, uint32_t a_lo, uint3
         ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// ---- split precision, second form: fp16 x fp16 main product + ONE e4m3 x e4m3 MMA carrying both correction products ---------------
+// (a_f + r) (w_f + w_r) ~= a_f w_f + [a_h8 | a_l8] . [w_l8 ; w_h8]: the corrections are accumulated FIRST, scaled by 2^15 so that
+// they fit the e4m3 range, and the first fp16 MMA of the tile folds them in with D = A*B + D * 2^-15 (scale-input-d, an immediate
+// of kind::f16).  Two tensor-core instructions per (16 channels, tap) instead of the three of the bf16 hi/lo form.
+constexpr uint32_t kCorrScaleLog2 = 15;  // = kActLoScaleLog2 + kWgtHiScaleLog2 (dense_gemm.cuh); the ISA allows 0..15
+__device__ __forceinline__ void mma_f8_w(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma2_f8_w(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// kind::f16 with D = A*B + D * 2^-kCorrScaleLog2 (always accumulating)
+__device__ __forceinline__ void mma_f16_scaled_w(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p, %5;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "n"(kCorrScaleLog2)
+        : "memory");
+}
+__device__ __forceinline__ void mma2_f16_scaled_w(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p, %5;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "n"(kCorrScaleLog2)
+        : "memory");
+}
+// Instruction descriptors of the second form: FP16 x FP16 (kind::f16, a/b format 0) and E4M3 x E4M3 (kind::f8f6f4, a/b format 0)
+// have the same bits -- c_format F32, both operands K-major.
+__host__ __device__ constexpr uint32_t make_idesc_f16_m128(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
+__host__ __device__ constexpr uint32_t make_idesc_f16_m256(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((256u >> 4) << 24); }
+
 __device__ __forceinline__ void mma_commit_if(uint64_t* bar, uint32_t issue)
 {
     asm volatile(
@@ -213,6 +274,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
           "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr)
         : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 {

@@ -65,3 +65,56 @@ def test_bf16_split_precision(models):
     p_ref, _ = cnn_oracle.logits_to_prob_ml(ref[need])
     p_got, _ = cnn_oracle.logits_to_prob_ml(maps["LOGIT"][need])
     assert np.abs(p_ref - p_got).max() < 2e-4
+
+
+def _e4m3(x):
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).clamp(-448, 448).to(torch.float8_e4m3fn).to(torch.float32).numpy()
+
+
+def _f16(x):
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(torch.float16).to(torch.float32).numpy()
+
+
+@pytest.mark.parametrize("ctx", [0, 1, 2])
+def test_fp16_plus_e4m3_split_precision(models, ctx):
+    """Operand form 1 of the tensor kernels (hifimeth_b200/csrc/dense_gemm.cuh): a product is a_f*w_f + 2^-15 (a_h8*w_l8 + a_l8*w_h8)
+    with a_f = fp16(a), a_h8 = e4m3(a), a_l8 = e4m3((a - a_f) 2^12), w_h8 = e4m3(8 w), w_l8 = e4m3((w - w_f) 2^15) -- two tensor-core
+    instructions instead of the three of bf16 hi/lo.  The conv1-form ops (inputs from the X map) stay in bf16 hi/lo.  Emulated over
+    every row of both strands of a 3 kb read: probabilities within 3e-4 of fp32 (bar: 1e-3)."""
+    import torch
+
+    def bf(x):
+        return torch.from_numpy(np.ascontiguousarray(x)).to(torch.bfloat16).to(torch.float32).numpy()
+
+    O = hmoracle.oracle()
+    batch, _ = synth.make_reads(1, 3000, seed=15 + ctx)
+    fwd = O.batch_sites(batch, 7)[0]["fwd"]
+    plan = de.build_plan(models[ctx])
+    worst = 0.0
+    for strand in (0, 1):
+        X = de.place(de.strand_features(fwd, batch.fi, batch.fp, batch.ri, batch.rp, strand))
+        ref = de.run_plan(plan, X)["LOGIT"]
+        maps = {"X": X}
+        rows = X.shape[0]
+        for op in plan:
+            acc = np.tile(op.bias, (rows, 1)).astype(np.float32)
+            for t in op.terms:
+                a = np.zeros_like(maps[t.src])
+                a[:rows - t.shift] = maps[t.src][t.shift:]
+                if t.src == "X":
+                    ah, wh = bf(a), bf(t.w)
+                    acc += ah @ wh + bf(a - ah) @ wh + ah @ bf(t.w - wh)
+                else:
+                    af, wf = _f16(a), _f16(t.w)
+                    corr = _e4m3(a) @ _e4m3((t.w - wf) * np.float32(2.0 ** 15)) + _e4m3((a - af) * np.float32(2.0 ** 12)) @ _e4m3(t.w * np.float32(8.0))
+                    acc += af @ wf + corr * np.float32(2.0 ** -15)
+            maps[op.out] = np.maximum(acc, 0) if op.relu else acc
+        need = slice(de.site_row(0), de.site_row(len(fwd)))
+        p_ref, _ = cnn_oracle.logits_to_prob_ml(ref[need])
+        p_got, _ = cnn_oracle.logits_to_prob_ml(maps["LOGIT"][need])
+        worst = max(worst, float(np.abs(p_ref - p_got).max()))
+    assert worst < 3e-4, worst
