@@ -27,9 +27,6 @@
 #include <string>
 #include <vector>
 
-#include <cuda_fp16.h>
-#include <cuda_fp8.h>
-
 #include "dense_gemm.cuh"
 #include "dense_gemm2.cuh"
 #include "dense_fused12.cuh"
@@ -108,17 +105,6 @@ float bf2f(uint16_t h)
     float f;
     memcpy(&f, &u, 4);
     return f;
-}
-
-// Host-side rounding of operand form 1 (dense_gemm.cuh), with the same conversions the device uses.
-uint16_t f2h(float f) { const __half h = __float2half_rn(f); uint16_t u; memcpy(&u, &h, 2); return u; }
-float h2f(uint16_t u) { __half h; memcpy(&h, &u, 2); return __half2float(h); }
-uint8_t f2e4m3(float f) { return (uint8_t)__nv_cvt_float_to_fp8(f, __NV_SATFINITE, __NV_E4M3); }
-float e4m32f(uint8_t b)
-{
-    const int s = b >> 7, e = (b >> 3) & 15, m = b & 7;
-    const float v = e ? std::ldexp(1.0f + m / 8.0f, e - 7) : std::ldexp(m / 8.0f, -6);
-    return s ? -v : v;
 }
 
 bool build_plan(const CnnModel& m, bool compact, std::vector<HostOp>& ops, std::string& err)
@@ -269,20 +255,15 @@ struct DevOp {
     size_t smem = 0;
     size_t w_off = 0, bias_off = 0, w2_off = 0, b2_off = 0;  // offsets into the model blob
     double macs_per_row = 0;  // executed MACs per output row, one precision pass
-    int passes = 3;           // tensor-core instructions per (16 channels, term): 3 in operand form 0, 2 in form 1
 };
 
 // Lowers output channels [n0, n0 + n) of a plan op to kernel parameters + packed weights.  Returns false with
 // err = "fit" when the slice's resident weights leave no room for a 2-deep ring (the caller then splits it).
 bool lower_op(const HostOp& h, int n0, int n, DevOp& d, std::vector<uint8_t>& blob, std::string& err, bool two_cta = false,
-              bool conv1_pair = false, int in_fmt = -1)
+              bool conv1_pair = false)
 {
     DenseOp& p = d.p;
     p = DenseOp{};
-    // operand form: the conv1-form ops read the X map (form 0: bf16 hi/lo), every other map is in form 1 (fp16 + e4m3);
-    // the fused conv1 + conv2 kernel builds its conv2 operand on chip in form 0 and asks for that explicitly
-    p.in_fmt = in_fmt >= 0 ? in_fmt : (h.conv1_taps > 0 ? 0 : 1);
-    d.passes = p.in_fmt ? 2 : 3;
     const int nfull = h.cout;
     if (n % 16 || n > 256 || h.terms.empty() || (int)h.terms.size() > kMaxTerms) { err = "op shape not supported"; return false; }
     p.n = n;
@@ -324,7 +305,7 @@ bool lower_op(const HostOp& h, int n0, int n, DevOp& d, std::vector<uint8_t>& bl
         }
         d.macs_per_row = (double)p.ksteps * 16 * n;
     } else {
-        if (h.cin % 16 || (p.in_fmt && h.cin % 32)) { err = "cin must be a multiple of 16 (32 in operand form 1)"; return false; }
+        if (h.cin % 16) { err = "cin must be a multiple of 16"; return false; }
         p.n_stages = h.cin / 16; p.ksteps = 1; p.a_q_off = 0; p.planes_per_seg = 4; p.n_segs = 0;
         int term_seg[kMaxTerms] = {0, 0, 0};
         for (size_t k = 0; k < h.terms.size(); ++k) {
@@ -364,34 +345,6 @@ bool lower_op(const HostOp& h, int n0, int n, DevOp& d, std::vector<uint8_t>& bl
     const uint32_t tile_elems = 2u * nw * 8u;
     const size_t n_tiles = (size_t)p.n_stages * p.ksteps * p.n_terms * 2;
     std::vector<uint16_t> img(n_img * n_tiles * tile_elems, 0);
-    if (p.in_fmt && h.conv1_taps == 0) {
-        // form 1: tiles [ring stage][j][term]; ring stage st < n_stages / 2 -> e4m3 tile of 16-channel stage ks = 2 st + j:
-        // K-chunk 0 = w_l8 (meets a_h8), K-chunk 1 = w_h8 (meets a_l8); st >= n_stages / 2 -> fp16 tile of stage 2 (st - half) + j
-        const int half = p.n_stages / 2;
-        const float s_hi = std::ldexp(1.0f, kWgtHiScaleLog2), s_lo = std::ldexp(1.0f, (int)umma::kCorrScaleLog2);
-        for (int r = 0; r < n_img; ++r)
-        for (int st = 0; st < p.n_stages; ++st)
-            for (int j = 0; j < 2; ++j)
-                for (int k = 0; k < p.n_terms; ++k) {
-                    uint16_t* tile = &img[(r * n_tiles + ((size_t)(st * 2 + j) * p.n_terms + k)) * tile_elems];
-                    uint8_t* tile8 = reinterpret_cast<uint8_t*>(tile);
-                    const bool corr = st < half;
-                    const int ks = 2 * (corr ? st : st - half) + j;
-                    for (int o = 0; o < nw; ++o) {
-                        const int col = n0 + r * nw + o;
-                        for (int e = 0; e < 16; ++e) {
-                            const float w = h.terms[k].w[(size_t)(16 * ks + e) * nfull + col];
-                            const uint16_t wf = f2h(w);
-                            if (corr) {
-                                tile8[((size_t)0 * nw + o) * 16 + e] = f2e4m3((w - h2f(wf)) * s_lo);
-                                tile8[((size_t)1 * nw + o) * 16 + e] = f2e4m3(w * s_hi);
-                            } else {
-                                tile[((size_t)(e >> 3) * nw + o) * 8 + (e & 7)] = wf;
-                            }
-                        }
-                    }
-                }
-    } else
     for (int r = 0; r < n_img; ++r)
     for (int st = 0; st < p.n_stages; ++st)
         for (int q = 0; q < p.ksteps; ++q)
@@ -606,7 +559,7 @@ struct TensorModel {
     std::vector<DevOp> ops;
     // conv1 + conv2 fused (dense_fused12_kernel): launched in place of op i_y1, op i_y2 is skipped
     bool fused12 = false;
-    DevOp f12_c1, f12_c2;  // both in operand form 0: the kernel builds conv2's operand on chip as bf16 hi/lo
+    DevOp f12_c1;
     int i_y1 = -1, i_y2 = -1;
     uint8_t* d_blob = nullptr;
     double macs_per_row = 0;  // executed, one precision pass, all ops
@@ -660,16 +613,13 @@ int tensor_model_build(TensorModelHandle& m, const CnnModel& host)
             if (!d.compact && d.out_map == MAP_Y && d.p.n == 128 && d.p.out_g0 == 0) t->i_y1 = (int)i;
             if (!d.compact && d.out_map == MAP_Y + 1 && d.two_cta && d.p.n == 128 && d.p.n_stages == 8 && d.p.n_terms == 3) t->i_y2 = (int)i;
         }
-        const HostOp *h1 = nullptr, *h2 = nullptr;
-        for (const HostOp& h : plan) {
+        const HostOp* h1 = nullptr;
+        for (const HostOp& h : plan)
             if (!h.compact && h.out == MAP_Y && h.conv1_taps > 0) h1 = &h;
-            if (!h.compact && h.out == MAP_Y + 1) h2 = &h;
-        }
-        if (t->i_y1 >= 0 && t->i_y2 >= 0 && h1 && h2 && lower_op(*h1, 0, 128, t->f12_c1, blob, err, true, true) &&
-            lower_op(*h2, 0, 128, t->f12_c2, blob, err, true, false, 0)) {
+        if (t->i_y1 >= 0 && t->i_y2 >= 0 && h1 && lower_op(*h1, 0, 128, t->f12_c1, blob, err, true, true)) {
             Fused12Op probe{};
             probe.c1 = t->f12_c1.p;
-            probe.c2 = t->f12_c2.p;
+            probe.c2 = t->ops[t->i_y2].p;
             t->fused12 = fused12_smem_bytes(probe) <= kSmemMax;
         }
     }
@@ -677,7 +627,7 @@ int tensor_model_build(TensorModelHandle& m, const CnnModel& host)
     if (st == cudaSuccess) st = cudaMemcpy(t->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice);
     if (st != cudaSuccess) { cudaFree(t->d_blob); delete t; return tfail(std::string("weight upload: ") + cudaGetErrorString(st)); }
     for (DevOp& d : t->ops) bind_blob(d, t->d_blob);
-    if (t->fused12) { bind_blob(t->f12_c1, t->d_blob); bind_blob(t->f12_c2, t->d_blob); }
+    if (t->fused12) bind_blob(t->f12_c1, t->d_blob);
     m.p = t;
     return ensure_kernel_attr();
 }
@@ -712,7 +662,7 @@ struct TensorWorkspaceImpl {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // shape of the last tensor_batch_run (debug hooks): sub-batches, compact groups per context, rows of the X map
     uint32_t last_subs = 0, last_groups[3] = {0, 0, 0}, last_x_rows = 0;
-    double macs = 0;  // executed MACs of the running batch x tensor-core instructions per product (launch_op / launch_fused12 add to it)
+    double macs = 0;  // executed MACs of the running batch, one precision pass (launch_op / launch_fused12 add to it)
 };
 
 int tensor_workspace_alloc(TensorWorkspace& w, uint32_t max_bases, uint32_t max_reads, uint32_t max_rows)
@@ -828,7 +778,7 @@ int launch_fused12(const DevOp& d1, const DevOp& d2, TensorWorkspaceImpl& s, uin
         f.dbg = g_f12_dbg;
     }
     f.n_tiles = (rows + kF12OutRows - 1) / kF12OutRows;
-    s.macs += (double)((f.n_tiles + 1) / 2 * 2) * kTileRows * (d1.macs_per_row * d1.passes + d2.macs_per_row * d2.passes);  // 128 rows computed per 124 kept
+    s.macs += (double)((f.n_tiles + 1) / 2 * 2) * kTileRows * (d1.macs_per_row + d2.macs_per_row);  // 128 rows computed per 124 kept
     f.c1 = patch_op(d1, s, f.n_tiles, nullptr);
     f.c2 = patch_op(d2, s, f.n_tiles, nullptr);
     cudaLaunchConfig_t cfg{};
@@ -847,7 +797,7 @@ int launch_fused12(const DevOp& d1, const DevOp& d2, TensorWorkspaceImpl& s, uin
 int launch_op(const DevOp& d, TensorWorkspaceImpl& s, uint32_t n_tiles, float* logit_out, int sm_count, cudaStream_t stream)
 {
     DenseOp p = patch_op(d, s, n_tiles, logit_out);
-    s.macs += (double)(d.two_cta ? (n_tiles + 1) / 2 * 2 : n_tiles) * kTileRows * d.macs_per_row * d.passes;
+    s.macs += (double)(d.two_cta ? (n_tiles + 1) / 2 * 2 : n_tiles) * kTileRows * d.macs_per_row;
     uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)sm_count);
     if (d.two_cta) grid = std::min<uint32_t>(((n_tiles + 1) / 2) * 2, (uint32_t)sm_count & ~1u);
     cudaLaunchConfig_t cfg{};
@@ -1017,7 +967,7 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
                     for (const DevOp& d : tm.ops) {
                         if (!d.compact && !(tm.fused12 && op_i == tm.i_y2)) {
                             stamp(c * 64 + op_i);
-                            if (tm.fused12 && op_i == tm.i_y1) launch_fused12(tm.f12_c1, tm.f12_c2, *s, nt * kTileRows, sm_count, stream);
+                            if (tm.fused12 && op_i == tm.i_y1) launch_fused12(tm.f12_c1, tm.ops[tm.i_y2], *s, nt * kTileRows, sm_count, stream);
                             else launch_op(d, *s, nt, nullptr, sm_count, stream);
                             ++dense_launches;
                         }
@@ -1099,7 +1049,7 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
     }
     if (timing) {
         timing->top_kernel_launches = dense_launches;
-        timing->executed_flops = s->macs * 2.0;
+        timing->executed_flops = s->macs * 2.0 * 3.0;
     }
     return 0;
 }
@@ -1120,7 +1070,7 @@ namespace {
 // out[r][g*8 .. g*8+8) = hi + lo of row rows[r] of a plane-layout map; a negative row gives NaN ("the product path never
 // materialises this value").
 __global__ void __launch_bounds__(256)
-debug_rows_kernel(const uint8_t* __restrict__ map, unsigned long long plane_stride, uint32_t groups, int fmt, const long long* __restrict__ rows,
+debug_rows_kernel(const uint8_t* __restrict__ map, unsigned long long plane_stride, uint32_t groups, const long long* __restrict__ rows,
                   uint32_t n, float* __restrict__ out)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1132,18 +1082,6 @@ debug_rows_kernel(const uint8_t* __restrict__ map, unsigned long long plane_stri
         for (int e = 0; e < 8; ++e) o[e] = __int_as_float(0x7fc00000);
         return;
     }
-    if (fmt == 1) {
-        // operand form 1: fp16 unit of group g + the l8 bytes of its 16-channel stage (the residual, scaled by 2^12)
-        const uint4 f = *reinterpret_cast<const uint4*>(map + (unsigned long long)g * plane_stride + (unsigned long long)row * 16ull);
-        const uint8_t* l8 = map + (unsigned long long)(groups + 2u * (g >> 1) + 1u) * plane_stride + (unsigned long long)row * 16ull + 8u * (g & 1u);
-        const uint32_t fw[4] = {f.x, f.y, f.z, f.w};
-        for (int j = 0; j < 8; ++j) {
-            const __half_raw hr{(unsigned short)((fw[j >> 1] >> (16 * (j & 1))) & 0xffffu)};
-            const __half_raw lr = __nv_cvt_fp8_to_halfraw(l8[j], __NV_E4M3);
-            o[j] = __half2float(__half(hr)) + __half2float(__half(lr)) * (1.0f / (float)(1 << kActLoScaleLog2));
-        }
-        return;
-    }
     const uint4 hi = *reinterpret_cast<const uint4*>(map + (unsigned long long)g * plane_stride + (unsigned long long)row * 16ull);
     const uint4 lo = *reinterpret_cast<const uint4*>(map + (unsigned long long)(groups + g) * plane_stride + (unsigned long long)row * 16ull);
     const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
@@ -1153,7 +1091,7 @@ debug_rows_kernel(const uint8_t* __restrict__ map, unsigned long long plane_stri
     }
 }
 
-int debug_read_rows(const uint8_t* map, unsigned long long plane_stride, uint32_t groups, int fmt, const std::vector<long long>& rows, float* out,
+int debug_read_rows(const uint8_t* map, unsigned long long plane_stride, uint32_t groups, const std::vector<long long>& rows, float* out,
                     cudaStream_t stream)
 {
     if (rows.empty()) return 0;
@@ -1163,7 +1101,7 @@ int debug_read_rows(const uint8_t* map, unsigned long long plane_stride, uint32_
     TCUDA("debug rows", cudaMalloc((void**)&d_rows, n * sizeof(long long)));
     TCUDA("debug rows", cudaMalloc((void**)&d_out, n * groups * 8 * sizeof(float)));
     TCUDA("debug rows", cudaMemcpyAsync(d_rows, rows.data(), n * sizeof(long long), cudaMemcpyHostToDevice, stream));
-    debug_rows_kernel<<<(uint32_t)((n * groups + 255) / 256), 256, 0, stream>>>(map, plane_stride, groups, fmt, d_rows, (uint32_t)n, d_out);
+    debug_rows_kernel<<<(uint32_t)((n * groups + 255) / 256), 256, 0, stream>>>(map, plane_stride, groups, d_rows, (uint32_t)n, d_out);
     TCUDA("debug rows", cudaGetLastError());
     TCUDA("debug rows", cudaMemcpyAsync(out, d_out, n * groups * 8 * sizeof(float), cudaMemcpyDeviceToHost, stream));
     TCUDA("debug rows", cudaStreamSynchronize(stream));
@@ -1195,7 +1133,7 @@ int tensor_debug_xwindow(TensorWorkspace& w, uint32_t n, const uint32_t* read, c
             rows[(size_t)i * 401 + j] = r;
         }
     }
-    return debug_read_rows(s->d_xg, s->xg_stride, 1, 0, rows, out, stream);
+    return debug_read_rows(s->d_xg, s->xg_stride, 1, rows, out, stream);
 }
 
 int tensor_debug_site_acts(const TensorModelHandle& model, int ctx, TensorWorkspace& w, uint32_t n, const uint32_t* read, const uint8_t* rev,
@@ -1246,7 +1184,7 @@ int tensor_debug_site_acts(const TensorModelHandle& model, int ctx, TensorWorksp
         std::vector<float> tmp((size_t)n * C);
         if (!map) {
             for (float& x : tmp) x = NAN;
-        } else if (debug_read_rows(map, stride, groups, 1, rows, tmp.data(), stream)) return -1;
+        } else if (debug_read_rows(map, stride, groups, rows, tmp.data(), stream)) return -1;
         for (uint32_t i = 0; i < n; ++i) memcpy(out + ((size_t)i * nl + v) * C, tmp.data() + (size_t)i * C, (size_t)C * sizeof(float));
     }
     return 0;
@@ -1296,21 +1234,12 @@ int tensor_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int ci
     uint32_t* d_rows = nullptr;
     const size_t in_bytes = (size_t)n_src * 2 * groups * ps;
     std::vector<uint16_t> img(in_bytes / 2, 0);
-    uint8_t* img8 = reinterpret_cast<uint8_t*>(img.data());
     for (int sidx = 0; sidx < n_src; ++sidx)
         for (uint32_t r = 0; r < rows_alloc; ++r)
             for (int c = 0; c < cin; ++c) {
                 const float v = src[sidx][(size_t)r * cin + c];
-                const size_t base = (size_t)sidx * 2 * groups * (ps / 2);
-                if (d.p.in_fmt) {  // operand form 1: fp16 planes, then {h8, l8} planes per 16-channel stage
-                    const uint16_t f = f2h(v);
-                    img[base + ((size_t)(c / 8) * rows_alloc + r) * 8 + c % 8] = f;
-                    const size_t b8 = 2 * base + (size_t)(groups + 2 * (c / 16)) * ps + (size_t)r * 16 + c % 16;
-                    img8[b8] = f2e4m3(v);
-                    img8[b8 + ps] = f2e4m3((v - h2f(f)) * std::ldexp(1.0f, kActLoScaleLog2));
-                    continue;
-                }
                 const uint16_t hi = f2bf(v);
+                const size_t base = (size_t)sidx * 2 * groups * (ps / 2);
                 img[base + ((size_t)(c / 8) * rows_alloc + r) * 8 + c % 8] = hi;
                 img[base + ((size_t)(groups + c / 8) * rows_alloc + r) * 8 + c % 8] = f2bf(v - bf2f(hi));
             }
@@ -1375,12 +1304,11 @@ int tensor_debug_dense_op(int device, uint32_t rows, uint32_t rows_alloc, int ci
     } else {
         std::vector<uint16_t> o(out_bytes / 2);
         TCUDA("debug op", cudaMemcpy(o.data(), d_out, out_bytes, cudaMemcpyDeviceToHost));
-        const uint8_t* o8 = reinterpret_cast<const uint8_t*>(o.data());
         for (uint32_t r = 0; r < rows; ++r)
-            for (int c = 0; c < cout; ++c) {  // every output map is in operand form 1
-                const float f = h2f(o[((size_t)(c / 8) * orows + r) * 8 + c % 8]);
-                const float l8 = e4m32f(o8[(size_t)(ogroups + 2 * (c / 16) + 1) * ops_ + (size_t)r * 16 + c % 16]);
-                out[(size_t)r * cout + c] = f + l8 * std::ldexp(1.0f, -kActLoScaleLog2);
+            for (int c = 0; c < cout; ++c) {
+                const float hi = bf2f(o[((size_t)(c / 8) * orows + r) * 8 + c % 8]);
+                const float lo = bf2f(o[((size_t)(ogroups + c / 8) * orows + r) * 8 + c % 8]);
+                out[(size_t)r * cout + c] = hi + lo;
             }
     }
     cudaFree(d_blob); cudaFree(d_in); cudaFree(d_out); cudaFree(d_logit); cudaFree(d_rows);

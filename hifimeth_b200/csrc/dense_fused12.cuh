@@ -7,8 +7,8 @@
 //   producers   X rows [124 T, +144) (8 channels, hi/lo)  --bulk copy-->  X ring (4 slots)
 //   MMA warp    MMA1: conv1 form (11/13 taps along K, LBO = 16 B) -> accumulator A1[T & 1] in TMEM (Y1 rows 124 T .. +127)
 //   epilogue-1  8 warps: A1 -> + bias1, ReLU, hi/lo bf16 -> the A RING itself, in the plane layout conv2's bulk copies
-//               would have produced (8 stages per tile in a ring of 10 slots, each {hi g0, hi g1, lo g0, lo g1} x 132 rows x 16 B);
-//               a slot may be written as soon as MMA2 has released it and is handed to the MMA warp with an mbarrier arrive
+//               would have produced (8 stages x {hi g0, hi g1, lo g0, lo g1} x 132 rows x 16 B); stage s may be written as
+//               soon as MMA2 of the previous tile has released it and is handed to the MMA warp with an mbarrier arrive
 //               (fence.proxy.async in front: generic-proxy writes read by the tensor core) -- the role the producer warps
 //               play in dense_gemm2_kernel.  It also writes the compact scatter copies of Y1 (operands of F2 / G2).
 //   MMA warp    MMA2: conv2 (3 taps = descriptor row shifts 0 / 2 / 4) over the 8 stages -> accumulator A2[T & 1]
@@ -17,24 +17,14 @@
 // Issue order MMA1(T+1), MMA2(T), MMA1(T+2), ...: epilogue-1 of tile T+1 runs under MMA2(T), so the tensor pipe does not
 // wait for it.  Rows 124 .. 127 of a tile see conv2 taps beyond the 128 Y1 rows the CTA holds; they are computed on
 // whatever the ring holds there and never stored -- the next tile recomputes them (3 % extra conv1 + conv2 work).
-// TMEM: A1 x 2 + A2 x 2 = 4 x 128 columns = all 512.  Shared memory per CTA: W2 half 96 KiB + W1 half 24 / 28 KiB + A ring
-// 82.5 KiB + X ring 18 KiB.
+// TMEM: A1 x 2 + A2 x 2 = 4 x 128 columns = all 512.  Shared memory per CTA: W2 half 96 KiB + W1 half 24 KiB + A ring
+// 66 KiB + X ring 18 KiB.
 #pragma once
 #include "dense_gemm2.cuh"
 
 namespace hm {
 
 constexpr int kF12OutRows = 124;  // conv2 rows per CTA tile (128 - the reach of conv2's taps)
-constexpr int kF12Stages = 8;     // 16-channel stages of one Y1 tile (= c2.n_stages)
-// Slots of the A ring: stage g = 8 * tile + st lives in slot g % kF12Ring.  With exactly one tile of slots (8) the last chunk of
-// tile T+1 can only be written after MMA2 of tile T has read its own last chunk, which looks like one epilogue-1 chunk latency on
-// the critical path of every tile; two spare slots (-DHM_F12_RING=10, fits for both conv1 sizes) remove that dependence -- and
-// measured NO gain on B200 (round 2, A/B on one box: 98.4 vs 98.3 ms per step), so the default stays 8: the step is paced by
-// power (sw_power_cap in every run), i.e. by the work issued, not by this latency.
-#ifndef HM_F12_RING
-#define HM_F12_RING 8
-#endif
-constexpr int kF12Ring = HM_F12_RING;  // even, >= kF12Stages (8 = the round-1 behaviour, kept for A/B builds)
 constexpr int kF12XRing = 4;
 constexpr int kF12Epi1Warps = 8;  // two per TMEM lane group; 32-channel chunks alternate between the two
 constexpr int kF12ProducerWarps = kF12XRing;  // one per X ring slot; fewer threads than the other kernels: 96 registers for the epilogues
@@ -51,8 +41,8 @@ struct Fused12Op {
 
 inline size_t fused12_smem_bytes(const Fused12Op& f)
 {
-    return ((f.c2.w_bytes + 127u) & ~127u) + ((f.c1.w_bytes + 127u) & ~127u) + (size_t)kF12Ring * f.c2.stage_bytes +
-           (size_t)kF12XRing * f.c1.stage_bytes + (2 * kF12Ring + 2 * kF12XRing + 1 + 2 + 2 + 2 + 1) * sizeof(uint64_t) + 16 + 2 * 128 * sizeof(float);
+    return ((f.c2.w_bytes + 127u) & ~127u) + ((f.c1.w_bytes + 127u) & ~127u) + (size_t)f.c2.n_stages * f.c2.stage_bytes +
+           (size_t)kF12XRing * f.c1.stage_bytes + (2 * 8 + 2 * kF12XRing + 1 + 2 + 2 + 2 + 1) * sizeof(uint64_t) + 16 + 2 * 128 * sizeof(float);
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dense_fused12_kernel(const __grid_constant__ Fused12Op f)
@@ -63,15 +53,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = umma::cluster_ctarank();
     const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-    constexpr int kStages = kF12Stages;
+    constexpr int kStages = 8;  // = c2.n_stages: the A ring holds exactly one Y1 tile, slot = stage
     uint8_t* s_w2 = smem;
     uint8_t* s_w1 = s_w2 + ((c2.w_bytes + 127u) & ~127u);
     uint8_t* s_ring = s_w1 + ((c1.w_bytes + 127u) & ~127u);
-    uint8_t* s_xring = s_ring + (size_t)kF12Ring * c2.stage_bytes;
+    uint8_t* s_xring = s_ring + (size_t)kStages * c2.stage_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_xring + (size_t)kF12XRing * c1.stage_bytes);
-    uint64_t* full = bars;                          // [10] leader: one arrive per epilogue-1 warp of both CTAs
-    uint64_t* empty = full + kF12Ring;              // [10] multicast commit from the leader
-    uint64_t* xfull = empty + kF12Ring;             // [4]  leader: own expect_tx arrive + the peer's relay; peer: own arrive
+    uint64_t* full = bars;                          // [8]  leader: one arrive per epilogue-1 warp of both CTAs
+    uint64_t* empty = full + kStages;               // [8]  multicast commit from the leader
+    uint64_t* xfull = empty + kStages;              // [4]  leader: own expect_tx arrive + the peer's relay; peer: own arrive
     uint64_t* xempty = xfull + kF12XRing;           // [4]  multicast commit
     uint64_t* w_full = xempty + kF12XRing;          // [1]
     uint64_t* a1_full = w_full + 1;                 // [2]  multicast commit: MMA1 of a tile has completed
@@ -84,7 +74,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int i = 0; i < kF12Ring; ++i) {
+            for (int i = 0; i < kStages; ++i) {
                 umma::mbar_init(&full[i], 2 * 4);  // the four lane-group warps that own the stage's chunk, in both CTAs
                 umma::mbar_init(&empty[i], 1);
             }
@@ -211,12 +201,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
                 const uint32_t d_addr = tmem_base + 256u + buf * 128u;
                 uint32_t b_cur = b2_base;
                 for (int st = 0; st < kStages; ++st) {
-                    const uint32_t g = (uint32_t)kStages * it + (uint32_t)st, slot = g % (uint32_t)kF12Ring, use = g / (uint32_t)kF12Ring;
-                    umma::mbar_wait(&full[slot], use & 1u);
+                    umma::mbar_wait(&full[st], it & 1u);
                     umma::tc_fence_after();
                     if (lane == 0) stamp(it, 3 + st);
                     if (umma::elect_one()) {
-                        const uint32_t sa = ring16 + slot * stage16;
+                        const uint32_t sa = ring16 + (uint32_t)st * stage16;
                         uint32_t bq = b_cur;
                         #pragma unroll
                         for (int k = 0; k < 3; ++k) {
@@ -226,7 +215,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
                             bq += 2 * b_step;
                         }
                         // epilogue-1 refills the ring one 32-channel chunk (two stages) at a time: one release per chunk
-                        if (st & 1) umma::mma2_commit_mc(&empty[slot]);
+                        if (st & 1) umma::mma2_commit_mc(&empty[st]);
                     }
                     b_cur += 2 * b_step * 3u;
                     __syncwarp();
@@ -305,10 +294,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
             const bool stamper = threadIdx.x == 32u * (kF12ProducerWarps + 1 + kEpilogueWarps);
             if (stamper) stamp(it, 12);
             const uint32_t t_addr = tmem_base + (lane_grp << 16) + buf * 128u;
-            for (int c = (int)half; c < 4; c += 2) {  // 32 channels = stages 2c, 2c + 1 of this tile = ring slots sl, sl + 1
-                const uint32_t g1 = (uint32_t)kF12Stages * it + 2u * (uint32_t)c + 1u;
-                const uint32_t sl = (g1 - 1u) % (uint32_t)kF12Ring, use = g1 / (uint32_t)kF12Ring;  // kF12Ring is even: sl + 1 never wraps
-                umma::mbar_wait(&empty[sl + 1], (use & 1u) ^ 1u);  // committed after the second stage of the chunk
+            for (int c = (int)half; c < 4; c += 2) {  // 32 channels = stages 2c, 2c + 1
+                umma::mbar_wait(&empty[2 * c + 1], (it & 1u) ^ 1u);  // committed after the second stage of the chunk
                 uint32_t v[32];
                 umma::tmem_ld32(t_addr + 32u * (uint32_t)c, v);
                 umma::tmem_ld_wait();
@@ -340,7 +327,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
                 // stage s = 2c + (g >> 1), planes {hi g0, hi g1, lo g0, lo g1}: group g of the chunk is plane (g & 1) / 2 + (g & 1)
                 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    uint8_t* st = s_ring + (size_t)(sl + (uint32_t)(g >> 1)) * c2.stage_bytes + c2.seg[0].smem_off + m * 16u;
+                    uint8_t* st = s_ring + (size_t)(2 * c + (g >> 1)) * c2.stage_bytes + c2.seg[0].smem_off + m * 16u;
                     *reinterpret_cast<uint4*>(st + (uint32_t)(g & 1) * pl_bytes) = vh[g];
                     *reinterpret_cast<uint4*>(st + (uint32_t)(2 + (g & 1)) * pl_bytes) = vl[g];
                 }
@@ -349,56 +336,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
                 __syncwarp();
                 if (lane == 0) {
                     if (rank == 0) {
-                        umma::mbar_arrive(&full[sl]);
-                        umma::mbar_arrive(&full[sl + 1]);
+                        umma::mbar_arrive(&full[2 * c]);
+                        umma::mbar_arrive(&full[2 * c + 1]);
                     } else {
                         // plain remote arrive: the fence above already ordered this CTA's writes for its own tensor-core reads;
                         // a cluster-scope release here costs a GPU-wide membar per chunk (it waits for the scatter stores)
-                        umma::mbar_arrive_cluster(umma::mapa(umma::smem_u32(&full[sl]), 0));
-                        umma::mbar_arrive_cluster(umma::mapa(umma::smem_u32(&full[sl + 1]), 0));
+                        umma::mbar_arrive_cluster(umma::mapa(umma::smem_u32(&full[2 * c]), 0));
+                        umma::mbar_arrive_cluster(umma::mapa(umma::smem_u32(&full[2 * c + 1]), 0));
                     }
                 }
                 // Y1's scatter copies (compact rows are consecutive, so these fill whole lines).  AFTER the hand-over: the proxy fence
                 // above is a memory barrier for this thread, and in front of it these global stores made every chunk wait for their
                 // acknowledgement (HM_F12_STAMPS: ~4 000 cycles per chunk; 3 300 with the stores behind the arrive).  Giving them to
                 // four dedicated warps instead was slower still: one warp needs ~2 200 cycles per 32-column chunk.
-                // (The copies are in operand form 1 like every map in HBM -- the A ring above keeps form 0, this kernel's own business --
-                // so the values are re-summed from hi + lo, 16 mantissa bits, and split again: fp16 + the two e4m3 bytes.)
-                bool any = false;
                 #pragma unroll
-                for (int k = 0; k < kMaxScatter; ++k) any |= msc[k] >= 0;
-                if (any) {
-                    uint4 vf[4], v8h[2], v8l[2];
-                    #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        uint2 h8[2], l8[2];
+                for (int k = 0; k < kMaxScatter; ++k) {
+                    if (msc[k] >= 0) {
+                        uint8_t* q_hi = c1.sc_out[k] + (unsigned long long)(4 * c) * c1.sc_plane_stride + (unsigned long long)msc[k] * 16ull;
+                        uint8_t* q_lo = q_hi + (unsigned long long)c1.out_groups * c1.sc_plane_stride;
                         #pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int g = 2 * u + e;
-                            const uint32_t hw[4] = {vh[g].x, vh[g].y, vh[g].z, vh[g].w}, lw[4] = {vl[g].x, vl[g].y, vl[g].z, vl[g].w};
-                            float xs[8];
-                            #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                xs[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
-                                xs[2 * j + 1] = __uint_as_float(hw[j] & 0xffff0000u) + __uint_as_float(lw[j] & 0xffff0000u);
-                            }
-                            split_form1(xs, vf[g], h8[e], l8[e]);
-                        }
-                        v8h[u] = make_uint4(h8[0].x, h8[0].y, h8[1].x, h8[1].y);
-                        v8l[u] = make_uint4(l8[0].x, l8[0].y, l8[1].x, l8[1].y);
-                    }
-                    #pragma unroll
-                    for (int k = 0; k < kMaxScatter; ++k) {
-                        if (msc[k] >= 0) {
-                            uint8_t* q_f = c1.sc_out[k] + (unsigned long long)(4 * c) * c1.sc_plane_stride + (unsigned long long)msc[k] * 16ull;
-                            uint8_t* q_8 = c1.sc_out[k] + (unsigned long long)(c1.out_groups + 4 * c) * c1.sc_plane_stride + (unsigned long long)msc[k] * 16ull;
-                            #pragma unroll
-                            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(q_f + g * c1.sc_plane_stride) = vf[g];
-                            #pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                *reinterpret_cast<uint4*>(q_8 + (2 * u) * c1.sc_plane_stride) = v8h[u];
-                                *reinterpret_cast<uint4*>(q_8 + (2 * u + 1) * c1.sc_plane_stride) = v8l[u];
-                            }
+                        for (int g = 0; g < 4; ++g) {
+                            *reinterpret_cast<uint4*>(q_hi + g * c1.sc_plane_stride) = vh[g];
+                            *reinterpret_cast<uint4*>(q_lo + g * c1.sc_plane_stride) = vl[g];
                         }
                     }
                 }

@@ -23,27 +23,11 @@
 #pragma once
 #include <cstdint>
 #include <cuda_bf16.h>
-#include <cuda_fp16.h>
-#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 
 #include "umma.cuh"
 
 namespace hm {
-
-// Operand formats ("split precision").  Every activation map except X is stored in the SECOND form:
-//   form 0 (X map, conv1-form ops): bf16 hi + bf16 lo per value; three MMAs per product: hi*hi + lo*hi + hi*lo.
-//   form 1 (every other map):       fp16 a_f = rn(a), plus two e4m3 bytes per value: a_h8 = rn(a) and a_l8 = rn((a - a_f) * 2^12).
-//       Weights likewise: w_f = rn_f16(w), w_h8 = rn_e4m3(w * 2^3), w_l8 = rn_e4m3((w - w_f) * 2^15).  A product is
-//       a_f*w_f + 2^-15 * (a_h8*w_l8 + a_l8*w_h8): ONE kind::f16 MMA and ONE kind::f8f6f4 MMA whose K = 32 holds both
-//       corrections, [a_h8 | a_l8] . [w_l8 ; w_h8] -- two tensor-core instructions instead of three.  The corrections of a whole
-//       tile are accumulated first (scaled by 2^15) and folded in by the first fp16 MMA through scale-input-d (umma.cuh).
-//       Same 4 bytes per value and the same plane structure as form 0: planes [f16 g = 0 .. G-1][e4m3 of 16-channel stage k:
-//       h8(k), l8(k)], a 16-byte unit being 8 fp16 channels or 16 e4m3 channels of one row.
-//   Emulated on 3 x 6 kb of rows per model (tests/test_dense_plan.py): max |dp| 1.4e-4 against the 1e-3 bar (bf16 hi/lo: 6.8e-5).
-constexpr int kActLoScaleLog2 = 12;
-constexpr int kWgtHiScaleLog2 = 3;
-static_assert(kActLoScaleLog2 + kWgtHiScaleLog2 == (int)umma::kCorrScaleLog2, "both correction products must carry the scale the fp16 MMA removes");
 
 constexpr int kTileRows = 128;
 constexpr int kMaxTerms = 3;
@@ -78,15 +62,11 @@ struct DenseOp {
     uint32_t a_q_off;        // byte advance of the A view per k-step inside a stage (conv1 form: 32)
     int32_t planes_per_seg;  // planes copied per segment and stage (4 = {hi,lo} x 2 groups; conv1 form: 2;
                              // gathered conv1 form: 2 * gather_taps, plane p = {hl = p / taps, row + p % taps})
-    int32_t in_fmt;          // operand form of the input maps and the weight image: 0 = bf16 hi/lo (3 MMAs), 1 = fp16 + e4m3 (2 MMAs);
-                             // form 1: ring stage st < n_stages / 2 holds the e4m3 planes of 16-channel stages 2 st, 2 st + 1, stage
-                             // st >= n_stages / 2 the fp16 planes of stages 2 (st - n_stages / 2), + 1 (n_stages is even)
     int32_t gather_taps;     // > 0: gathered conv1 form
     const uint32_t* gather_rows;  // [n_tiles * 128] source row of every compact row (gather segments)
     uint32_t stage_bytes;    // bytes of one ring stage
     int32_t ring;            // ring depth
-    const uint8_t* w_img;    // packed weights, tiles of N * 32 bytes: form 0 [stage][kstep][term][hl], each [2][N][8] bf16;
-                             // form 1 [ring stage][j][term], each [2][N][16 B]: e4m3 {w_l8, w_h8} or fp16 {channels 0-7, 8-15}
+    const uint8_t* w_img;    // packed weights: tiles [stage][kstep][term][hl], each [2][N][8] bf16 (N*32 bytes)
     uint32_t w_bytes;
     const float* bias;       // [N]
     int32_t n;               // output channels (multiple of 16, <= 256)
@@ -117,66 +97,50 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
-// 8 fp32 values -> one fp16 unit (16 B) + the 8 e4m3 bytes of a_h8 and of a_l8 (half of a 16-channel unit each).
-__device__ __forceinline__ void split_form1(const float* x, uint4& f16u, uint2& h8, uint2& l8)
-{
-    uint32_t fw[4], hb[4], lb[4];
-    #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float x0 = x[2 * j], x1 = x[2 * j + 1];
-        const __half2 h = __floats2half2_rn(x0, x1);
-        const float2 hf = __half22float2(h);
-        fw[j] = *reinterpret_cast<const uint32_t*>(&h);
-        hb[j] = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(x0, x1), __NV_SATFINITE, __NV_E4M3);
-        lb[j] = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2((x0 - hf.x) * (float)(1 << kActLoScaleLog2), (x1 - hf.y) * (float)(1 << kActLoScaleLog2)),
-                                                   __NV_SATFINITE, __NV_E4M3);
-    }
-    f16u = make_uint4(fw[0], fw[1], fw[2], fw[3]);
-    h8 = make_uint2(hb[0] | (hb[1] << 16), hb[2] | (hb[3] << 16));
-    l8 = make_uint2(lb[0] | (lb[1] << 16), lb[2] | (lb[3] << 16));
-}
-
-// Epilogue of one chunk of NG 8-column groups (32 or 16 columns, c0 a multiple of 16) of one row: ReLU'd values -> form 1 -> the op's
-// own map (plane layout) and the compact scatter copies.  msc[k] = compact row for scatter k, or -1.
+// Epilogue of one chunk of NG 8-column groups (32 or 16 columns) of one row: ReLU'd values -> hi/lo bf16 -> the op's own map
+// (plane layout) and the compact scatter copies.  msc[k] = compact row for scatter k, or -1.
 template <int NG>
 __device__ __forceinline__ void epilogue_store_groups(const DenseOp& op, unsigned long long row, int c0, const float (&f)[8 * NG],
                                                       const int (&msc)[kMaxScatter], bool skip_store)
 {
-    static_assert(NG % 2 == 0, "form 1 packs 16 channels per e4m3 unit");
-    uint4 vf[NG], vh[NG / 2], vl[NG / 2];
+    uint4 vh[NG], vl[NG];
     #pragma unroll
-    for (int u = 0; u < NG / 2; ++u) {
-        uint2 h0, l0, h1, l1;
-        split_form1(f + 16 * u, vf[2 * u], h0, l0);
-        split_form1(f + 16 * u + 8, vf[2 * u + 1], h1, l1);
-        vh[u] = make_uint4(h0.x, h0.y, h1.x, h1.y);
-        vl[u] = make_uint4(l0.x, l0.y, l1.x, l1.y);
+    for (int g = 0; g < NG; ++g) {
+        uint32_t hi[4], lo[4];
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            // hi = bf16(x) for two values in one cvt; lo = bf16(x - hi), hi widened back with integer ops
+            const float x0 = f[8 * g + 2 * j], x1 = f[8 * g + 2 * j + 1];
+            const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+            const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+            const __nv_bfloat162 e = __floats2bfloat162_rn(x0 - __uint_as_float(hb << 16), x1 - __uint_as_float(hb & 0xffff0000u));
+            hi[j] = hb;
+            lo[j] = *reinterpret_cast<const uint32_t*>(&e);
+        }
+        vh[g] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        vl[g] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
     if (skip_store) return;
-    const uint32_t g0 = op.out_g0 + ((uint32_t)c0 >> 3);  // even
+    const uint32_t g0 = op.out_g0 + ((uint32_t)c0 >> 3);
     {
-        uint8_t* p_f = op.out + (unsigned long long)g0 * op.out_plane_stride + row * 16ull;
-        uint8_t* p_8 = op.out + (unsigned long long)(op.out_groups + g0) * op.out_plane_stride + row * 16ull;  // h8 plane of stage g0 / 2
+        uint8_t* p_hi = op.out + (unsigned long long)g0 * op.out_plane_stride + row * 16ull;
+        uint8_t* p_lo = p_hi + (unsigned long long)op.out_groups * op.out_plane_stride;
         #pragma unroll
-        for (int g = 0; g < NG; ++g) *reinterpret_cast<uint4*>(p_f + g * op.out_plane_stride) = vf[g];
-        #pragma unroll
-        for (int u = 0; u < NG / 2; ++u) {
-            *reinterpret_cast<uint4*>(p_8 + (2 * u) * op.out_plane_stride) = vh[u];
-            *reinterpret_cast<uint4*>(p_8 + (2 * u + 1) * op.out_plane_stride) = vl[u];
+        for (int g = 0; g < NG; ++g) {
+            *reinterpret_cast<uint4*>(p_hi + g * op.out_plane_stride) = vh[g];
+            *reinterpret_cast<uint4*>(p_lo + g * op.out_plane_stride) = vl[g];
         }
     }
     // compact copies: msc[k] = -1 for rows that feed no site (and for k >= n_scatter)
     #pragma unroll
     for (int k = 0; k < kMaxScatter; ++k) {
         if (msc[k] >= 0) {
-            uint8_t* q_f = op.sc_out[k] + (unsigned long long)g0 * op.sc_plane_stride + (unsigned long long)msc[k] * 16ull;
-            uint8_t* q_8 = op.sc_out[k] + (unsigned long long)(op.out_groups + g0) * op.sc_plane_stride + (unsigned long long)msc[k] * 16ull;
+            uint8_t* q_hi = op.sc_out[k] + (unsigned long long)g0 * op.sc_plane_stride + (unsigned long long)msc[k] * 16ull;
+            uint8_t* q_lo = q_hi + (unsigned long long)op.out_groups * op.sc_plane_stride;
             #pragma unroll
-            for (int g = 0; g < NG; ++g) *reinterpret_cast<uint4*>(q_f + g * op.sc_plane_stride) = vf[g];
-            #pragma unroll
-            for (int u = 0; u < NG / 2; ++u) {
-                *reinterpret_cast<uint4*>(q_8 + (2 * u) * op.sc_plane_stride) = vh[u];
-                *reinterpret_cast<uint4*>(q_8 + (2 * u + 1) * op.sc_plane_stride) = vl[u];
+            for (int g = 0; g < NG; ++g) {
+                *reinterpret_cast<uint4*>(q_hi + g * op.sc_plane_stride) = vh[g];
+                *reinterpret_cast<uint4*>(q_lo + g * op.sc_plane_stride) = vl[g];
             }
         }
     }
@@ -240,16 +204,6 @@ __device__ __forceinline__ void scatter_rows(const DenseOp& op, unsigned long lo
         msc[k] = -1;
         if (k < op.n_scatter && row >= (unsigned long long)op.sc_shift[k]) msc[k] = __ldg(op.site_of_row + (row - (unsigned long long)op.sc_shift[k]));
     }
-}
-
-// Plane (of the source map) that plane p of ring stage st holds.  Normal form, 4 planes per stage.
-__device__ __forceinline__ uint32_t stage_plane(const DenseOp& op, uint32_t groups, int st, uint32_t p)
-{
-    if (!op.in_fmt) return (p >> 1) * groups + (uint32_t)(2 * st) + (p & 1u);  // {hi g0, hi g1, lo g0, lo g1}
-    const uint32_t half = (uint32_t)op.n_stages >> 1;
-    const bool f16 = (uint32_t)st >= half;
-    const uint32_t ks = 2u * ((uint32_t)st - (f16 ? half : 0u)) + (p >> 1);   // 16-channel stage
-    return (f16 ? 0u : groups) + 2u * ks + (p & 1u);                          // {f16 g 2ks, 2ks + 1} or {h8(ks), l8(ks)}
 }
 
 // Shared memory: [weights image][ring stages][barriers]
@@ -349,10 +303,11 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel_t(const __
                     if (c < ncopies) {
                         const uint32_t p = c % (uint32_t)op.planes_per_seg;
                         const DenseSeg& sg = op.seg[bulk_seg[c / (uint32_t)op.planes_per_seg]];
-                        // planes of a stage: normal form see stage_plane(); conv1 form {hi, lo}
-                        const uint32_t pi = (op.planes_per_seg == 4) ? stage_plane(op, sg.groups, st, p) : p * sg.groups;
+                        // planes of a stage: normal form {hi g0, hi g1, lo g0, lo g1}; conv1 form {hi, lo}
+                        const uint32_t hl = (op.planes_per_seg == 4) ? (p >> 1) : p;
+                        const uint32_t g = (op.planes_per_seg == 4) ? (uint32_t)(2 * st) + (p & 1u) : 0u;
                         const uint32_t pl_bytes = sg.nrows * 16u;
-                        const uint8_t* plane = sg.src + (unsigned long long)pi * sg.plane_stride;
+                        const uint8_t* plane = sg.src + (unsigned long long)(hl * sg.groups + g) * sg.plane_stride;
                         umma::bulk_g2s(stage + sg.smem_off + p * pl_bytes, plane + (row0 + sg.row_off) * 16ll, pl_bytes, &full[slot]);
                     }
                 }
@@ -363,10 +318,10 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel_t(const __
                         const uint32_t pl_bytes = sg.nrows * 16u;
                         for (int p = 0; p < op.planes_per_seg; ++p) {
                             // normal form {hi g0, hi g1, lo g0, lo g1}; gathered conv1 form {hi tap 0.., lo tap 0..}
-                            uint32_t pi, extra = 0;
-                            if (op.gather_taps > 0) { pi = ((uint32_t)p / (uint32_t)op.gather_taps) * sg.groups; extra = (uint32_t)p % (uint32_t)op.gather_taps; }
-                            else pi = stage_plane(op, sg.groups, st, (uint32_t)p);
-                            const uint8_t* plane = sg.src + (unsigned long long)pi * sg.plane_stride;
+                            uint32_t hl, g, extra = 0;
+                            if (op.gather_taps > 0) { hl = (uint32_t)p / (uint32_t)op.gather_taps; g = 0; extra = (uint32_t)p % (uint32_t)op.gather_taps; }
+                            else { hl = (uint32_t)p >> 1; g = (uint32_t)(2 * st + (p & 1)); }
+                            const uint8_t* plane = sg.src + (unsigned long long)(hl * sg.groups + g) * sg.plane_stride;
                             uint8_t* dst = stage + sg.smem_off + p * pl_bytes;
                             #pragma unroll
                             for (int j = 0; j < 4; ++j)
@@ -382,7 +337,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel_t(const __
         // ===================================== MMA issuer ===================================================
         // One lane issues every tcgen05.mma of the CTA, so the per-MMA instruction count matters: all descriptors are
         // built once and advanced by adding 16-byte units to their address field (bits [0,14), never carries out).
-        const uint32_t idesc = op.in_fmt ? umma::make_idesc_f16_m128((uint32_t)op.n) : umma::make_idesc_bf16_m128((uint32_t)op.n);
+        const uint32_t idesc = umma::make_idesc_bf16_m128((uint32_t)op.n);
         // Only the low word of a descriptor changes (address bits [0,14), LBO bits [16,30)); the high word (SBO, version)
         // is the same for every operand, so descriptor arithmetic is 32-bit adds on the low word.
         const uint32_t desc_hi = (uint32_t)(umma::make_desc(0, 0, 128) >> 32);
@@ -412,30 +367,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel_t(const __
                 umma::mbar_wait(&full[slot], phase);
                 umma::tc_fence_after();
                 if ((variant & 32u) && blockIdx.x == 0 && lane == 0 && it * n_stages + st < 256) op.dbg[256 + it * n_stages + st] = clock64();
-                if (op.in_fmt) {
-                    // form 1: this ring stage holds two 16-channel stages (j = 0, 1: the hi / lo view offsets of form 0 are the
-                    // offsets of the second stage here); e4m3 corrections in the first half of the tile's stages, fp16 after
-                    if (umma::elect_one()) {
-                        const uint32_t sa = ring16 + slot * stage16;
-                        uint32_t bq = b_cur, a0 = acc;
-                        const bool corr = 2 * st < n_stages, fold = 2 * st == n_stages;
-                        #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            #pragma unroll
-                            for (int k = 0; k < kMaxTerms; ++k) {
-                                if (k < n_terms) {
-                                    const uint32_t a = (j ? a_lo[k] : a_hi[k]) + sa;
-                                    if (corr) umma::mma_f8_w(d_addr, a, bq, desc_hi, idesc, a0);
-                                    else if (fold && j == 0 && k == 0) umma::mma_f16_scaled_w(d_addr, a, bq, desc_hi, idesc);
-                                    else umma::mma_bf16_w(d_addr, a, bq, desc_hi, idesc, 1);
-                                    a0 = 1;
-                                    bq += b_step;
-                                }
-                            }
-                        }
-                        umma::mma_commit(&empty[slot]);
-                    }
-                } else if (umma::elect_one()) {
+                if (umma::elect_one()) {
                     uint32_t sa = ring16 + slot * stage16, bq = b_cur;
                     uint32_t a0 = acc;
                     for (int q = 0; q < ksteps; ++q, sa += aq16) {

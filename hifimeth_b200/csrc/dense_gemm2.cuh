@@ -85,7 +85,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) de
                     const uint32_t p = lane & 3u;
                     const DenseSeg& sg = op.seg[lane >> 2];
                     const uint32_t pl_bytes = sg.nrows * 16u;
-                    const uint8_t* plane = sg.src + (unsigned long long)stage_plane(op, sg.groups, st, p) * sg.plane_stride;
+                    const uint8_t* plane = sg.src + (unsigned long long)((p >> 1) * sg.groups + (uint32_t)(2 * st) + (p & 1u)) * sg.plane_stride;
                     umma::bulk_g2s(stage + sg.smem_off + p * pl_bytes, plane + (row0 + sg.row_off) * 16ll, pl_bytes, &full[slot]);
                 }
                 __syncwarp();
@@ -101,7 +101,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) de
         const int n_terms = op.n_terms, n_stages = op.n_stages, ring = op.ring;
         if (rank == 0) {
             // ===================================== MMA issuer (leader) ============================================
-            const uint32_t idesc = op.in_fmt ? umma::make_idesc_f16_m256((uint32_t)op.n) : umma::make_idesc_bf16_m256((uint32_t)op.n);
+            const uint32_t idesc = umma::make_idesc_bf16_m256((uint32_t)op.n);
             const uint32_t desc_hi = (uint32_t)(umma::make_desc(0, 0, 128) >> 32);
             const uint32_t nh = (uint32_t)op.n >> 1;                       // B rows held by each CTA
             const uint32_t b_step = (nh * 32u) >> 4;
@@ -124,30 +124,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) de
                 for (int st = 0; st < n_stages; ++st) {
                     umma::mbar_wait(&full[slot], phase);
                     umma::tc_fence_after();
-                    if (op.in_fmt) {
-                        // form 1 (dense_gemm.cuh): two 16-channel stages per ring stage, one MMA per (stage, term): e4m3 corrections
-                        // while st < n_stages / 2, fp16 products after; the first fp16 MMA folds the corrections in
-                        if (umma::elect_one()) {
-                            const uint32_t sa = ring16 + slot * stage16;
-                            uint32_t bq = b_cur, a0 = acc;
-                            const bool corr = 2 * st < n_stages, fold = 2 * st == n_stages;
-                            #pragma unroll
-                            for (int j = 0; j < 2; ++j) {
-                                #pragma unroll
-                                for (int k = 0; k < kMaxTerms; ++k) {
-                                    if (k < n_terms) {
-                                        const uint32_t a = (j ? a_lo[k] : a_hi[k]) + sa;
-                                        if (corr) umma::mma2_f8_w(d_addr, a, bq, desc_hi, idesc, a0);
-                                        else if (fold && j == 0 && k == 0) umma::mma2_f16_scaled_w(d_addr, a, bq, desc_hi, idesc);
-                                        else umma::mma2_bf16_w(d_addr, a, bq, desc_hi, idesc, 1);
-                                        a0 = 1;
-                                        bq += b_step;
-                                    }
-                                }
-                            }
-                            umma::mma2_commit_mc(&empty[slot]);
-                        }
-                    } else if (umma::elect_one()) {
+                    if (umma::elect_one()) {
                         const uint32_t sa = ring16 + slot * stage16;
                         uint32_t bq = b_cur, a0 = acc;
                         #pragma unroll

@@ -5,6 +5,8 @@
 //   pattern 1: the split-precision triple of the engine: (a_hi, w_hi) (a_lo, w_hi) (a_hi, w_lo), each M x N x 16
 //   pattern 2: the same products with w_hi | w_lo side by side: (a_hi, [w_hi | w_lo]) as ONE M x 2N x 16 MMA + (a_lo, w_hi) M x N x 16
 //              (cta_group::1 only: in a pair the halves of N come from different CTAs)
+//   pattern 3: operand form 1 of round 2: one kind::f16 MMA (fp16, K = 16) + one kind::f8f6f4 MMA (e4m3, K = 32) per product
+//   pattern 4: the e4m3 K = 32 MMA alone          pattern 5: the fp16 K = 16 MMA alone
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../hifimeth_b200/csrc -o mma_rate_probe mma_rate_probe.cu ; run on a B200:
 //   ./mma_rate_probe <pair 0|1> <N> <pattern> [reps]
 #include <cstdio>
@@ -66,9 +68,16 @@ __global__ void __launch_bounds__(128, 1) probe(int n, int pattern, int reps, un
                     mma(tmem, a0, b0, idesc);
                     mma(tmem, a1, b0, idesc);
                     mma(tmem, a0, b1, idesc);
-                } else {
+                } else if (pattern == 2) {
                     mma(tmem, a0, b2_base + (uint32_t)(r & 3) * 2 * b_step, idesc2);
                     mma(tmem, a1, b0, idesc);
+                } else {
+                    const uint32_t idf = kPair ? umma::make_idesc_f16_m256((uint32_t)n) : umma::make_idesc_f16_m128((uint32_t)n);
+                    if (pattern == 3 || pattern == 5) mma(tmem, a0, b0, idf);
+                    if (pattern == 3 || pattern == 4) {
+                        if (kPair) umma::mma2_f8_w(tmem, a1, b1, desc_hi, idf, 1);
+                        else umma::mma_f8_w(tmem, a1, b1, desc_hi, idf, 1);
+                    }
                 }
             }
             if (kPair) umma::mma2_commit_mc(&bar);
@@ -126,8 +135,8 @@ int main(int argc, char** argv)
     }
     unsigned long long h[256] = {};
     cudaMemcpy(h, d_cyc, grid * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-    const int per_round = pattern == 0 ? 1 : pattern == 1 ? 3 : 2;
-    const double macs_round = (double)(pair ? 256 : 128) * n * 16 * (pattern == 0 ? 1 : 3);
+    const int per_round = pattern == 0 ? 1 : pattern == 1 ? 3 : (pattern == 2 || pattern == 3) ? 2 : 1;
+    const double macs_round = (double)(pair ? 256 : 128) * n * 16 * (pattern == 0 ? 1 : pattern == 4 ? 2 : pattern == 5 ? 1 : 3);
     const int issuers = pair ? grid / 2 : grid;
     printf("pair %d N %3d pattern %d: %8.1f cycles/round (%6.1f per MMA issued), %7.1f TFLOP/s chip-wide (%.3f ms)\n", pair, n, pattern,
            (double)h[0] / reps, (double)h[0] / reps / per_round, 2.0 * macs_round * reps * issuers / (ms * 1e-3) / 1e12, ms);
