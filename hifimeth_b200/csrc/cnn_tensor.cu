@@ -31,6 +31,7 @@
 #include "dense_gemm2.cuh"
 #include "dense_fused12.cuh"
 #include "postprocess.cuh"
+#include "site_chain.cuh"
 
 namespace hm {
 namespace {
@@ -252,6 +253,7 @@ struct DevOp {
     bool compact = false;
     int sc_map[kMaxScatter] = {0, 0, 0, 0, 0};
     bool two_cta = false;  // launched as dense_gemm2_kernel (CTA pairs, each holding half of every weight tile)
+    bool conv1 = false;    // conv1 form (reads the X map)
     size_t smem = 0;
     size_t w_off = 0, bias_off = 0, w2_off = 0, b2_off = 0;  // offsets into the model blob
     double macs_per_row = 0;  // executed MACs per output row, one precision pass
@@ -277,6 +279,7 @@ bool lower_op(const HostOp& h, int n0, int n, DevOp& d, std::vector<uint8_t>& bl
     uint32_t stage = 0;
     d.compact = h.compact;
     d.two_cta = two_cta;
+    d.conv1 = h.conv1_taps > 0;
     p.n_scatter = (int)h.scatter.size();
     for (int k = 0; k < p.n_scatter; ++k) { p.sc_shift[k] = h.scatter[k].first; d.sc_map[k] = h.scatter[k].second; }
     if (p.n_scatter && (n0 != 0 || n != h.cout)) { err = "a scattering op cannot be split over output channels"; return false; }
@@ -416,6 +419,14 @@ bool fuse12_enabled()
     return v;
 }
 
+// the compact chain (F2.. head) of a site tile in one kernel (site_chain.cuh): HM_CHAIN=1.  Off by default while it is slower
+// than the op-by-op launches (round 2: 30 ms against 24 ms per step).
+bool chain_enabled()
+{
+    static const bool v = getenv("HM_CHAIN") != nullptr && getenv("HM_NO_CHAIN") == nullptr;
+    return v;
+}
+
 bool two_cta_enabled()
 {
     static const bool v = getenv("HM_NO_2CTA") == nullptr;
@@ -436,6 +447,7 @@ int ensure_kernel_attr()
     TCUDA("dense kernel attribute", cudaFuncSetAttribute(dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     TCUDA("dense kernel attribute", cudaFuncSetAttribute(dense_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     TCUDA("dense kernel attribute", cudaFuncSetAttribute(dense_fused12_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    TCUDA("dense kernel attribute", cudaFuncSetAttribute(site_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     if (dev >= 0 && dev < 64) done[dev] = true;
     return 0;
 }
@@ -564,6 +576,16 @@ struct TensorModel {
     uint8_t* d_blob = nullptr;
     double macs_per_row = 0;  // executed, one precision pass, all ops
     int lens[9] = {};         // per-site output length of every layer (lens[0] = 401)
+    // the compact chain as one kernel (site_chain_kernel): every compact op except the conv1-form ones, in chain order
+    struct ChainItem {
+        DevOp d;                      // pair lowering: weights / bias offsets in the blob, n, macs
+        int term_map[kMaxTerms] = {0, 0, 0};  // source map of each term (streamed terms; resident ones carry dep / res_off in c)
+        int out_map = -1;
+        ChainOp c{};                  // template: pointers are patched per launch
+    };
+    bool chain = false;
+    std::vector<ChainItem> chain_ops;
+    size_t chain_w2_off = 0, chain_b2_off = 0;
 };
 
 const char* tensor_last_error() { return g_err.c_str(); }
@@ -623,11 +645,96 @@ int tensor_model_build(TensorModelHandle& m, const CnnModel& host)
             t->fused12 = fused12_smem_bytes(probe) <= kSmemMax;
         }
     }
+    if (compact_mode() && chain_enabled() && two_cta_enabled()) {
+        // ---- chain order: F2 G2 .. F6 G6 | T7_1 T7_2 T7_0 T7_3 | T8_0 T8_1 | head ------------------------------------------------
+        // F and G alternate so that the MMAs of one run under the epilogue of the other; T7_1 / T7_2 read scatter copies only and
+        // go first; the four T7 accumulators stay in TMEM until T7_0 / T7_3 have read F6 / G6, whose buffers their outputs reuse.
+        std::vector<const HostOp*> order;
+        auto add = [&](int out, bool head) {
+            for (const HostOp& h : plan)
+                if (h.compact && h.conv1_taps == 0 && ((head && h.head) || (!head && !h.head && h.out == out))) { order.push_back(&h); return true; }
+            return false;
+        };
+        bool ok = true;
+        for (int l = 2; l <= 6 && ok; ++l) ok = add(MAP_F + l - 1, false) && add(MAP_G + l - 1, false);
+        for (int v : {1, 2, 0, 3}) ok = ok && add(MAP_T7 + v, false);
+        ok = ok && add(MAP_T8 + 0, false) && add(MAP_T8 + 1, false) && add(-1, true);
+        size_t n_compact = 0;
+        for (const HostOp& h : plan) n_compact += (h.compact && h.conv1_taps == 0) ? 1 : 0;
+        ok = ok && order.size() == n_compact && order.size() <= (size_t)kChainMaxOps;
+        int i_t73 = -1;
+        std::vector<TensorModel::ChainItem> items;
+        for (size_t i = 0; i < order.size() && ok; ++i) {
+            const HostOp& h = *order[i];
+            TensorModel::ChainItem it;
+            HostOp hw = h;       // the pair lowering packs the weights; the head is lowered as a plain op (fc2 lives in the epilogue)
+            hw.head = false;
+            hw.scatter.clear();
+            std::vector<uint8_t> trial = blob;
+            if (!lower_op(hw, 0, h.cout, it.d, trial, err, true)) { ok = false; break; }
+            blob.swap(trial);
+            ChainOp& c = it.c;
+            c.n = h.cout; c.cin = h.cin; c.n_terms = (int)h.terms.size(); c.head = h.head ? 1 : 0;
+            c.wait_op = (int)i;
+            it.out_map = h.out;
+            // a ring slot holds the term's weight tiles (cout x 32 bytes for this CTA) after the 8 KiB slab of a streamed term;
+            // the head's terms are resident (checked below), every other op may stream
+            if (h.cin % 16 || h.cout % 32 || (uint32_t)h.cout * 32u + (h.head ? 0u : kChainSlabBytes) > kChainSlotBytes) { ok = false; break; }
+            if (h.head) { c.tmem_col = 256; c.regions = 0xf0u; }
+            else if (h.out >= MAP_F && h.out < MAP_G) { c.out_off = 0; c.tmem_col = 0; c.regions = 0x03u; }
+            else if (h.out >= MAP_G && h.out < MAP_T7) { c.out_off = kChainResBytes; c.tmem_col = 128; c.regions = 0x0cu; }
+            else if (h.out >= MAP_T7 && h.out < MAP_T8) {
+                const int v = h.out - MAP_T7;
+                static const uint32_t off[4] = {0, kChainResBytes / 2, kChainResBytes, kChainResBytes + kChainResBytes / 2};
+                static const uint32_t col[4] = {384, 256, 320, 448};   // T7_1 -> 256, T7_2 -> 320, T7_0 -> 384, T7_3 -> 448
+                c.out_off = off[v]; c.tmem_col = col[v]; c.regions = 1u << (col[v] / 64);
+                if (v == 3) i_t73 = (int)i;
+                if (h.cout != 64) { ok = false; break; }
+            } else if (h.out >= MAP_T8 && h.out < MAP_S) {
+                const int w = h.out - MAP_T8;
+                c.out_off = w ? kChainResBytes / 2 : 0; c.tmem_col = w ? 128 : 0; c.regions = w ? 0x04u : 0x01u;
+                if (h.cout != 64) { ok = false; break; }
+            } else { ok = false; break; }
+            for (size_t k = 0; k < h.terms.size(); ++k) {
+                if (h.terms[k].shift != 0 || h.terms[k].gather) { ok = false; break; }
+                it.term_map[k] = h.terms[k].src;
+                c.term[k].dep = -1;
+                for (size_t j = 0; j < i; ++j)
+                    if (items[j].out_map == h.terms[k].src && !items[j].c.head) { c.term[k].dep = (int)j; c.term[k].res_off = items[j].c.out_off; }
+                const int sm = h.terms[k].src;
+                const bool streamed_kind = sm >= MAP_S || sm == MAP_F || sm == MAP_G;  // scatter copies, F1, G1
+                if ((c.term[k].dep < 0) != streamed_kind || (h.head && streamed_kind)) { ok = false; break; }
+            }
+            items.push_back(it);
+        }
+        if (ok && i_t73 >= 0) {
+            // the T7 outputs overwrite F6 / G6, which T7_0 / T7_3 read: their epilogues wait for the last T7 op's MMAs
+            for (auto& it : items)
+                if (it.out_map >= MAP_T7 && it.out_map < MAP_T8) it.c.wait_op = i_t73;
+        }
+        if (ok) {
+            const HostOp& hh = *order.back();
+            size_t o = (blob.size() + 255) & ~(size_t)255;
+            blob.resize(o + hh.w2.size() * 4);
+            memcpy(blob.data() + o, hh.w2.data(), hh.w2.size() * 4);
+            t->chain_w2_off = o;
+            o = (blob.size() + 255) & ~(size_t)255;
+            blob.resize(o + hh.b2.size() * 4);
+            memcpy(blob.data() + o, hh.b2.data(), hh.b2.size() * 4);
+            t->chain_b2_off = o;
+            t->chain_ops = std::move(items);
+            t->chain = true;
+        }
+    }
     cudaError_t st = cudaMalloc((void**)&t->d_blob, blob.size());
     if (st == cudaSuccess) st = cudaMemcpy(t->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice);
     if (st != cudaSuccess) { cudaFree(t->d_blob); delete t; return tfail(std::string("weight upload: ") + cudaGetErrorString(st)); }
     for (DevOp& d : t->ops) bind_blob(d, t->d_blob);
     if (t->fused12) bind_blob(t->f12_c1, t->d_blob);
+    for (auto& it : t->chain_ops) {
+        it.c.w_img = t->d_blob + it.d.w_off;
+        it.c.bias = reinterpret_cast<const float*>(t->d_blob + it.d.bias_off);
+    }
     m.p = t;
     return ensure_kernel_attr();
 }
@@ -663,6 +770,8 @@ struct TensorWorkspaceImpl {
     // shape of the last tensor_batch_run (debug hooks): sub-batches, compact groups per context, rows of the X map
     uint32_t last_subs = 0, last_groups[3] = {0, 0, 0}, last_x_rows = 0;
     double macs = 0;  // executed MACs of the running batch, one precision pass (launch_op / launch_fused12 add to it)
+    bool spill_chain = false;  // debug reruns: the chain kernel also stores its maps to HBM (hm_debug_dump_acts reads them)
+    bool no_chain = false;
 };
 
 int tensor_workspace_alloc(TensorWorkspace& w, uint32_t max_bases, uint32_t max_reads, uint32_t max_rows)
@@ -812,6 +921,36 @@ int launch_op(const DevOp& d, TensorWorkspaceImpl& s, uint32_t n_tiles, float* l
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     if (d.two_cta) return cudaLaunchKernelEx(&cfg, dense_gemm2_kernel, p) == cudaSuccess ? 0 : -1;
     return cudaLaunchKernelEx(&cfg, dense_gemm_kernel, p) == cudaSuccess ? 0 : -1;
+}
+
+// The compact chain of n_tiles site tiles in one launch (site_chain_kernel).  spill: also store every map to its HBM buffer (debug).
+int launch_chain(const TensorModel& tm, TensorWorkspaceImpl& s, uint32_t n_tiles, float* logit_out, bool spill, int sm_count, cudaStream_t stream)
+{
+    ChainProgram p{};
+    p.n_ops = (int)tm.chain_ops.size();
+    p.n_tiles = n_tiles;
+    p.plane_stride = s.cplane_stride;
+    p.w2 = reinterpret_cast<const float*>(tm.d_blob + tm.chain_w2_off);
+    p.b2 = reinterpret_cast<const float*>(tm.d_blob + tm.chain_b2_off);
+    p.logits = logit_out;
+    for (int i = 0; i < p.n_ops; ++i) {
+        const TensorModel::ChainItem& it = tm.chain_ops[i];
+        p.op[i] = it.c;
+        for (int k = 0; k < it.c.n_terms; ++k) p.op[i].term[k].src = it.c.term[k].dep < 0 ? s.map[it.term_map[k]] : nullptr;
+        p.op[i].spill = (spill && !it.c.head) ? s.map[it.out_map] : nullptr;
+        s.macs += (double)((n_tiles + 1) / 2 * 2) * kTileRows * it.d.macs_per_row;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(std::min<uint32_t>(((n_tiles + 1) / 2) * 2, (uint32_t)sm_count & ~1u));
+    cfg.blockDim = dim3(kDenseThreads);
+    cfg.dynamicSmemBytes = chain_smem_bytes();
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, site_chain_kernel, p) == cudaSuccess ? 0 : -1;
 }
 
 struct SubBatch {
@@ -980,13 +1119,19 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
                 if (m_off) {
                     const uint32_t n_tiles = (m_off + kTileRows - 1) / kTileRows;
                     int op_i = 0;
+                    const bool chain = tm.chain && !s->no_chain;
                     for (const DevOp& d : tm.ops) {
-                        if (d.compact) {
+                        if (d.compact && (!chain || d.conv1)) {  // with the chain kernel only F1 / G1 (conv1 form) are launches of their own
                             stamp(c * 64 + op_i);
                             launch_op(d, *s, n_tiles, s->d_clogit, sm_count, stream);
                             ++dense_launches;
                         }
                         ++op_i;
+                    }
+                    if (chain) {
+                        stamp(c * 64 + 63);
+                        launch_chain(tm, *s, n_tiles, s->d_clogit, s->spill_chain, sm_count, stream);
+                        ++dense_launches;
                     }
                     stamp(-1);
                     for (const Seg& sg : segs) {
@@ -1021,7 +1166,8 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
                 fprintf(stderr, " %s%.2f", models[c].p->ops[k].compact ? "c" : "D", acc[c][k]);
                 tot += acc[c][k];
             }
-            fprintf(stderr, "  | total %.2f\n", tot);
+            if (acc[c][63] > 0) fprintf(stderr, "  chain %.2f", acc[c][63]);
+            fprintf(stderr, "  | total %.2f\n", tot + acc[c][63]);
         }
     }
     // ---- per-site lookup (dense-all mode only; compact runs finish per sub-batch) ----------------------------------------------
@@ -1118,6 +1264,12 @@ long long site_s_row(const TensorWorkspaceImpl& s, uint32_t read, bool rev, int 
 }
 
 }  // namespace
+
+// Debug reruns (hm_debug_dump_acts): the chain kernel also stores the maps it normally keeps in shared memory.
+void tensor_debug_spill(TensorWorkspace& w, bool on)
+{
+    if (w.impl) w.impl->spill_chain = on;
+}
 
 int tensor_debug_xwindow(TensorWorkspace& w, uint32_t n, const uint32_t* read, const uint8_t* rev, const int32_t* o, float* out, cudaStream_t stream)
 {

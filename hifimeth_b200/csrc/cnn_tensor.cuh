@@ -63,6 +63,7 @@ float tensor_last_dense_ms(TensorWorkspace& w);
 //              behind: Y_l (dense) for interior positions, F_l / G_l (compact) for the first / last, T7 / T8 for layers 7, 8;
 //              NaN where the product path never holds the value in HBM (interior of layer 1 when conv1 + conv2 are fused,
 //              except the rows scattered for F2 / G2).  The last run must have been this context alone, in one sub-batch.
+void tensor_debug_spill(TensorWorkspace& w, bool on);  // debug reruns: the chain kernel also stores its shared-memory maps to HBM
 int tensor_debug_xwindow(TensorWorkspace& w, uint32_t n, const uint32_t* read, const uint8_t* rev, const int32_t* o, float* out, cudaStream_t stream);
 int tensor_debug_site_acts(const TensorModelHandle& model, int ctx, TensorWorkspace& w, uint32_t n, const uint32_t* read, const uint8_t* rev,
                            const int32_t* o, const uint32_t* compact_row, int layer, float* out, int* n_out, int* channels, cudaStream_t stream);

@@ -857,7 +857,9 @@ int hm_debug_dump_acts(hm_engine* e, int slot, int ctx, int layer, uint32_t firs
     tb.h_base_off = s.host.base_off; tb.h_valid = s.host.valid; tb.h_read_pref = s.h_read_pref; tb.n_reads = s.n_reads;
     for (int k = 0; k < 4; ++k) tb.class_count[k] = s.totals[k];
     tb.d_logits = s.d_logits; tb.d_ml = s.d_ml;
+    hm::tensor_debug_spill(s.tws, true);  // F2.. T8 live in shared memory in the product path: this rerun also stores them
     const int run = hm::tensor_batch_run(e->tensor, 1u << ctx, s.tws, tb, s.stream, e->sm_count, &launches, &s.timing);
+    hm::tensor_debug_spill(s.tws, false);
     s.timing = keep;
     if (run) return fail(e, HM_ERR_CUDA, "CUDA error in tensor CNN: %s", hm::tensor_last_error());
     HM_CUDA(e, "debug activations", cudaStreamSynchronize(s.stream));

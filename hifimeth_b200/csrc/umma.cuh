@@ -71,6 +71,12 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  : "memory");
 }
 
+// Pulls a global range into L2 ahead of a later bulk copy (no completion tracking; bytes a multiple of 16).
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+
 // ---- cp.async (16 B, gather path) -----------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 {
