@@ -586,6 +586,8 @@ struct TensorModel {
     bool chain = false;
     std::vector<ChainItem> chain_ops;
     size_t chain_w2_off = 0, chain_b2_off = 0;
+    size_t blob_stride = 0;   // the blob is stored blob_copies times, blob_stride bytes apart (site_chain.cuh: one copy per few CTA pairs)
+    uint32_t blob_copies = 1;
 };
 
 const char* tensor_last_error() { return g_err.c_str(); }
@@ -726,8 +728,14 @@ int tensor_model_build(TensorModelHandle& m, const CnnModel& host)
             t->chain = true;
         }
     }
-    cudaError_t st = cudaMalloc((void**)&t->d_blob, blob.size());
-    if (st == cudaSuccess) st = cudaMemcpy(t->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+    if (t->chain) {
+        const char* env = getenv("HM_CHAIN_WCOPIES");
+        t->blob_copies = (uint32_t)std::max(1, std::min(64, env ? atoi(env) : 16));
+    }
+    t->blob_stride = (blob.size() + 4095) & ~(size_t)4095;
+    cudaError_t st = cudaMalloc((void**)&t->d_blob, t->blob_stride * t->blob_copies);
+    for (uint32_t c = 0; c < t->blob_copies && st == cudaSuccess; ++c)
+        st = cudaMemcpy(t->d_blob + c * t->blob_stride, blob.data(), blob.size(), cudaMemcpyHostToDevice);
     if (st != cudaSuccess) { cudaFree(t->d_blob); delete t; return tfail(std::string("weight upload: ") + cudaGetErrorString(st)); }
     for (DevOp& d : t->ops) bind_blob(d, t->d_blob);
     if (t->fused12) bind_blob(t->f12_c1, t->d_blob);
@@ -930,6 +938,8 @@ int launch_chain(const TensorModel& tm, TensorWorkspaceImpl& s, uint32_t n_tiles
     p.n_ops = (int)tm.chain_ops.size();
     p.n_tiles = n_tiles;
     p.plane_stride = s.cplane_stride;
+    p.w_copy_stride = tm.blob_stride;
+    p.w_copies = tm.blob_copies;
     p.w2 = reinterpret_cast<const float*>(tm.d_blob + tm.chain_w2_off);
     p.b2 = reinterpret_cast<const float*>(tm.d_blob + tm.chain_b2_off);
     p.logits = logit_out;

@@ -475,12 +475,27 @@ int hm_engine_create(const hm_config* cfg, hm_engine** out)
     e->ctx_mask = (cfg->ctx_mask & 7) ? (uint32_t)(cfg->ctx_mask & 7) : 7u;
     e->n_slots = cfg->n_slots;
     e->sm_count = prop.multiProcessorCount;
-    static const char* files[3] = {"CpG.onnx", "CHG.onnx", "CHH.onnx"};
+    // The CPU reference loads <dir>/{CpG,CHG,CHH}.onnx (mod_main.cpp:76,85,94), its app-gpu binary the .pt exports of the same
+    // networks (5mc_call_gpu.cpp:48).  .onnx is used when present; HM_MODEL_FORMAT=pt (or a directory holding only .pt files)
+    // selects the TorchScript archives.  Note that the shipped CHG.pt is a different checkpoint from CHG.onnx.
+    static const char* names[3] = {"CpG", "CHG", "CHH"};
+    const char* fmt_env = getenv("HM_MODEL_FORMAT");
     int rc = HM_OK;
     for (int c = 0; c < 3 && rc == HM_OK; ++c) {
         if (!(e->ctx_mask & (1u << c))) continue;
         std::string err;
-        if (!hm::load_onnx_model(e->model_dir + "/" + files[c], e->host_model[c], err)) { rc = fail(e, HM_ERR_MODEL, "%s", err.c_str()); break; }
+        std::string path = e->model_dir + "/" + names[c] + ".onnx";
+        bool use_pt = fmt_env && std::string(fmt_env) == "pt";
+        if (!use_pt && !fmt_env) {
+            FILE* probe = fopen(path.c_str(), "rb");
+            if (probe) fclose(probe);
+            else {
+                FILE* p2 = fopen((e->model_dir + "/" + names[c] + ".pt").c_str(), "rb");
+                if (p2) { fclose(p2); use_pt = true; }
+            }
+        }
+        if (use_pt) path = e->model_dir + "/" + names[c] + ".pt";
+        if (!hm::load_model_file(path, e->host_model[c], err)) { rc = fail(e, HM_ERR_MODEL, "%s", err.c_str()); break; }
         if ((rc = check_geometry(e, c))) break;
         e->have_model[c] = true;
         if (cfg->cnn_mode == HM_CNN_FP32_SIMT) rc = build_fp32_model(e, c);
@@ -501,6 +516,26 @@ int hm_engine_create(const hm_config* cfg, hm_engine** out)
         return rc;
     }
     *out = e;
+    return HM_OK;
+}
+
+int hm_model_weights(const char* path, float* out, size_t cap, size_t* n_floats, int32_t* conv1_k)
+{
+    if (!path || !n_floats) return fail(nullptr, HM_ERR_ARG, "hm_model_weights: null argument");
+    hm::CnnModel m;
+    std::string err;
+    if (!hm::load_model_file(path, m, err)) return fail(nullptr, HM_ERR_MODEL, "%s", err.c_str());
+    std::vector<float> v;
+    auto add = [&](const std::vector<float>& a) { v.insert(v.end(), a.begin(), a.end()); };
+    add(m.bn_w); add(m.bn_b); add(m.bn_mean); add(m.bn_var);
+    for (const hm::ConvLayer& cv : m.convs) { add(cv.w); add(cv.b); }
+    add(m.fc1_w); add(m.fc1_b); add(m.fc2_w); add(m.fc2_b);
+    *n_floats = v.size();
+    if (conv1_k) *conv1_k = m.convs.empty() ? 0 : m.convs[0].k;
+    if (out) {
+        if (cap < v.size()) return fail(nullptr, HM_ERR_ARG, "hm_model_weights: %zu floats needed", v.size());
+        memcpy(out, v.data(), v.size() * sizeof(float));
+    }
     return HM_OK;
 }
 

@@ -6,6 +6,7 @@
 #include "onnx_weights.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -319,6 +320,96 @@ bool load_onnx_model(const std::string& path, CnnModel& m, std::string& err)
         return false;
     }
     return true;
+}
+
+
+// ---- TorchScript archive (.pt) ------------------------------------------------------------------------------------------------------
+namespace {
+uint16_t z16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+uint32_t z32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+}  // namespace
+
+bool load_pt_model(const std::string& path, CnnModel& m, std::string& err)
+{
+    FILE* fp = fopen(path.c_str(), "rb");
+    if (!fp) { err = "cannot open model file " + path; return false; }
+    std::vector<uint8_t> buf;
+    uint8_t tmp[65536];
+    size_t got;
+    while ((got = fread(tmp, 1, sizeof(tmp), fp)) > 0) buf.insert(buf.end(), tmp, tmp + got);
+    fclose(fp);
+    const size_t n = buf.size();
+    // end-of-central-directory record: signature 0x06054b50 within the last 64 KiB + 22 bytes
+    size_t eocd = (size_t)-1;
+    for (size_t back = 22; back <= n && back <= 22 + 65535; ++back)
+        if (z32(&buf[n - back]) == 0x06054b50u) { eocd = n - back; break; }
+    if (eocd == (size_t)-1) { err = "not a TorchScript archive (no ZIP directory): " + path; return false; }
+    uint64_t n_entries = z16(&buf[eocd + 10]), cd_size = z32(&buf[eocd + 12]), cd_off = z32(&buf[eocd + 16]);
+    if (cd_off == 0xffffffffu || n_entries == 0xffffu) {  // ZIP64: locator 20 bytes before the EOCD -> ZIP64 EOCD record
+        if (eocd < 20 || z32(&buf[eocd - 20]) != 0x07064b50u) { err = "corrupt ZIP64 directory in " + path; return false; }
+        uint64_t rec = 0;
+        for (int i = 7; i >= 0; --i) rec = (rec << 8) | buf[eocd - 20 + 8 + i];
+        if (rec + 56 > n || z32(&buf[rec]) != 0x06064b50u) { err = "corrupt ZIP64 directory in " + path; return false; }
+        auto z64 = [&](size_t o) { uint64_t v = 0; for (int i = 7; i >= 0; --i) v = (v << 8) | buf[o + i]; return v; };
+        n_entries = z64(rec + 32); cd_size = z64(rec + 40); cd_off = z64(rec + 48);
+    }
+    if (cd_off + cd_size > n) { err = "corrupt ZIP directory in " + path; return false; }
+    std::vector<float> c[24];
+    bool have[24] = {};
+    size_t p = cd_off;
+    for (uint64_t e = 0; e < n_entries; ++e) {
+        if (p + 46 > n || z32(&buf[p]) != 0x02014b50u) { err = "corrupt ZIP directory entry in " + path; return false; }
+        const uint16_t method = z16(&buf[p + 10]), nl = z16(&buf[p + 28]), xl = z16(&buf[p + 30]), cl = z16(&buf[p + 32]);
+        uint64_t csize = z32(&buf[p + 20]), usize = z32(&buf[p + 24]), lho = z32(&buf[p + 42]);
+        if (p + 46 + nl + xl + cl > n) { err = "corrupt ZIP directory entry in " + path; return false; }
+        const std::string name(reinterpret_cast<const char*>(&buf[p + 46]), nl);
+        p += 46 + (size_t)nl + xl + cl;
+        const size_t k = name.rfind("/constants/");
+        if (k == std::string::npos) continue;
+        const std::string idx = name.substr(k + 11);
+        if (idx.empty() || idx.size() > 2 || idx.find_first_not_of("0123456789") != std::string::npos) continue;
+        const int i = atoi(idx.c_str());
+        if (i < 0 || i > 23) continue;
+        if (method != 0 || csize != usize || usize % 4 || csize == 0xffffffffu || lho == 0xffffffffu) { err = "constant " + idx + " of " + path + " is not a stored f32 member"; return false; }
+        if (lho + 30 > n || z32(&buf[lho]) != 0x04034b50u) { err = "corrupt ZIP member header in " + path; return false; }
+        const uint64_t data = lho + 30 + z16(&buf[lho + 26]) + z16(&buf[lho + 28]);
+        if (data + usize > n) { err = "truncated ZIP member in " + path; return false; }
+        c[i].resize(usize / 4);
+        memcpy(c[i].data(), &buf[data], usize);
+        have[i] = true;
+    }
+    for (int i = 0; i < 24; ++i)
+        if (!have[i]) { err = "TorchScript archive " + path + " lacks constant " + std::to_string(i) + " (expected the 24 frozen tensors of model_cnn)"; return false; }
+    static const int cin[8] = {8, 128, 128, 128, 96, 96, 96, 64}, cout[8] = {128, 128, 128, 96, 96, 96, 64, 64};
+    m = CnnModel{};
+    m.kmer = 401; m.features = 8;  // the exported module has no shape record; training/make-torch-script.py traces [B, 401, 8]
+    if (c[0].size() != 8 || c[1].size() != 8 || c[2].size() != 8 || c[3].size() != 8) { err = "bn0 tensors of " + path + " are not [8]"; return false; }
+    m.bn_w = c[0]; m.bn_b = c[1]; m.bn_mean = c[2]; m.bn_var = c[3];
+    m.convs.resize(8);
+    for (int l = 0; l < 8; ++l) {
+        ConvLayer& cv = m.convs[l];
+        const size_t per = (size_t)cout[l] * cin[l];
+        if (c[4 + 2 * l].size() % per || (int)c[5 + 2 * l].size() != cout[l]) { err = "conv" + std::to_string(l + 1) + " of " + path + " does not fit the channel plan"; return false; }
+        cv.cout = cout[l]; cv.cin = cin[l]; cv.k = (int)(c[4 + 2 * l].size() / per);
+        cv.w = c[4 + 2 * l]; cv.b = c[5 + 2 * l];
+    }
+    if (c[20].size() != 128 * 256 || c[21].size() != 256 || c[22].size() != 256 * 2 || c[23].size() != 2) { err = "FC tensors of " + path + " have unexpected sizes"; return false; }
+    m.fc1_in = 128; m.fc1_out = 256; m.fc2_out = 2;
+    m.fc1_w.resize(256 * 128);
+    for (int o = 0; o < 256; ++o)
+        for (int i = 0; i < 128; ++i) m.fc1_w[(size_t)o * 128 + i] = c[20][(size_t)i * 256 + o];   // stored [in][out]
+    m.fc1_b = c[21];
+    m.fc2_w.resize(2 * 256);
+    for (int o = 0; o < 2; ++o)
+        for (int i = 0; i < 256; ++i) m.fc2_w[(size_t)o * 256 + i] = c[22][(size_t)i * 2 + o];
+    m.fc2_b = c[23];
+    return true;
+}
+
+bool load_model_file(const std::string& path, CnnModel& out, std::string& err)
+{
+    if (path.size() > 3 && path.compare(path.size() - 3, 3, ".pt") == 0) return load_pt_model(path, out, err);
+    return load_onnx_model(path, out, err);
 }
 
 }  // namespace hm

@@ -30,4 +30,15 @@ struct CnnModel {
 // Returns true on success; on failure err holds a one-line reason.
 bool load_onnx_model(const std::string& path, CnnModel& out, std::string& err);
 
+// models/{CpG,CHG,CHH}.pt -- the TorchScript exports the reference's app-gpu binary loads (torch::jit::load,
+// src/app-gpu/hifimeth-gpu/5mc_call_gpu.cpp:48; written by training/make-torch-script.py:28-30).  A .pt file is a ZIP archive
+// whose 24 frozen constants are STORED (uncompressed) members `<name>/constants/0..23`, little-endian f32, in graph order
+// (SURVEY.md appendix A): bn0 weight, bias, mean, var; 8 x (conv W [cout][cin][k], b); fc1 [in][out] (transposed), b; fc2
+// [in][out], b.  Shapes follow from the member sizes and the fixed channel plan; conv1's kernel size comes from the file.
+// No libtorch, no pickle: the central directory is enough.
+bool load_pt_model(const std::string& path, CnnModel& out, std::string& err);
+
+// By extension: ".pt" -> load_pt_model, anything else -> load_onnx_model.
+bool load_model_file(const std::string& path, CnnModel& out, std::string& err);
+
 }  // namespace hm

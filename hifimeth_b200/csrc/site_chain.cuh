@@ -63,6 +63,11 @@ struct ChainProgram {
     int32_t n_ops;
     uint32_t n_tiles;                  // 128-site tiles
     unsigned long long plane_stride;   // of every compact map (streamed sources and spill targets)
+    // Every CTA pair streams the SAME weight tiles at about the same time: with one copy in memory 74 pairs hit the same L2 lines
+    // together and the ring ran at ~460 cycles per slot with no MMAs and no epilogue work at all.  The model blob is therefore
+    // replicated: pair p reads copy p % w_copies, w_copy_stride bytes apart.
+    unsigned long long w_copy_stride;
+    uint32_t w_copies;
     const float* w2;                   // head: [2][256], [2]
     const float* b2;
     float* logits;                     // [rows][2]
@@ -171,17 +176,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) si
             const ChainOp& op = prog.op[cur.oi];
             const uint32_t n_stages = (uint32_t)op.cin >> 4, groups = (uint32_t)op.cin >> 3;
             const uint32_t w_step = (uint32_t)op.n * 32u;                          // hi + lo tile of this CTA's half of N
-            const uint8_t* w_rank = op.w_img + (size_t)rank * n_stages * (uint32_t)op.n_terms * w_step;
+            const uint8_t* w_rank = op.w_img + (unsigned long long)(pair % prog.w_copies) * prog.w_copy_stride + (size_t)rank * n_stages * (uint32_t)op.n_terms * w_step;
             const unsigned long long row0 = (unsigned long long)(2 * cur.t2 + rank) * kTileRows;  // odd n_tiles: the peer's last tile lies in the slack rows
             const uint32_t slot = warp, phase = (step / kChainSlots) & 1u;
             const uint8_t* src = op.term[cur.k].src;
             if (valid(ahead)) prefetch(ahead);
             umma::mbar_wait(&empty[slot], phase ^ 1u);
             uint8_t* dst = s_ring + (size_t)slot * kChainSlotBytes;
-            if (lane == 0) umma::mbar_arrive_expect_tx(&full[slot], (src ? kChainSlabBytes : 0u) + w_step);
+            if (lane == 0) umma::mbar_arrive_expect_tx(&full[slot], ((src && !(HM_CHAIN_EXPERIMENT & 4)) ? kChainSlabBytes : 0u) + w_step);
             __syncwarp();
             if (lane < 4u) {
-                if (src) {  // planes {hi g0, hi g1, lo g0, lo g1} of the stage
+                if (src && !(HM_CHAIN_EXPERIMENT & 4)) {  // planes {hi g0, hi g1, lo g0, lo g1} of the stage
                     const uint8_t* plane = src + (unsigned long long)((lane >> 1) * groups + 2u * cur.s + (lane & 1u)) * prog.plane_stride;
                     umma::bulk_g2s(dst + lane * kChainPlaneBytes, plane + row0 * 16ull, kChainPlaneBytes, &full[slot]);
                 }

@@ -62,7 +62,7 @@ class hm_timing(C.Structure):
 
 
 ABI_SYMBOLS = ["hm_engine_create", "hm_engine_destroy", "hm_last_error", "hm_version", "hm_batch_acquire", "hm_batch_submit",
-               "hm_batch_collect", "hm_batch_timing", "hm_codev1_encode", "hm_codev1_decode", "hm_pack_record", "hm_pack_records",
+               "hm_batch_collect", "hm_batch_timing", "hm_model_weights", "hm_codev1_encode", "hm_codev1_decode", "hm_pack_record", "hm_pack_records",
                "hm_mod_record_bound", "hm_build_mod_record", "hm_build_mod_record_mm", "hm_parse_mod_record", "hm_ml_threshold", "hm_call_main", "hm_bam_copy", "hm_debug_dump_decode", "hm_debug_dump_ctx",
                "hm_debug_dump_features", "hm_debug_dump_logits", "hm_debug_dump_xmap", "hm_debug_dump_acts", "hm_debug_dense_op", "hm_debug_last_op_ms", "hm_microbench"]
 
@@ -83,6 +83,7 @@ def load_library() -> C.CDLL:
     L.hm_last_error.argtypes = [C.c_void_p]
     L.hm_last_error.restype = C.c_char_p
     L.hm_version.restype = C.c_char_p
+    L.hm_model_weights.argtypes = [C.c_char_p, _f32p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int32)]
     L.hm_batch_acquire.argtypes = [C.c_void_p, C.c_int, C.POINTER(hm_read_batch)]
     L.hm_batch_submit.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32]
     L.hm_batch_collect.argtypes = [C.c_void_p, C.c_int, C.POINTER(hm_call_batch)]
@@ -294,6 +295,18 @@ class Engine:
         self._check(self.lib.hm_microbench(self.h, slot, name.encode(), n_sites, iters, C.byref(ms), C.byref(by), C.byref(fl)),
                     "hm_microbench")
         return ms.value, by.value, fl.value
+
+
+def model_weights(path) -> tuple:
+    """hm_model_weights: (flattened parameters in graph order, conv1 kernel size) of an .onnx or .pt model file."""
+    L = load_library()
+    n, k = C.c_size_t(), C.c_int32()
+    if L.hm_model_weights(str(path).encode(), None, 0, C.byref(n), C.byref(k)) != 0:
+        raise HmError(L.hm_last_error(None).decode())
+    out = np.empty(n.value, np.float32)
+    if L.hm_model_weights(str(path).encode(), out.ctypes.data_as(_f32p), n.value, C.byref(n), C.byref(k)) != 0:
+        raise HmError(L.hm_last_error(None).decode())
+    return out, k.value
 
 
 def build_mod_record(body: bytes, keep_kinetics: bool, fwd_qoff, fwd_ml, rev_qoff, rev_ml) -> bytes:

@@ -144,6 +144,14 @@ void hm_engine_destroy(hm_engine* e);
 const char* hm_last_error(const hm_engine* e); /* e may be NULL: error of the last failed create */
 const char* hm_version(void);
 
+/* Weight loader on its own (no device): parses models/<ctx>.onnx -- either ONNX dialect that ships, what the CPU reference reads
+ * (src/app/hifimeth/mod_main.cpp:32-67) -- or models/<ctx>.pt, the TorchScript export its app-gpu binary loads
+ * (src/app-gpu/hifimeth-gpu/5mc_call_gpu.cpp:48), by extension, and returns the network's parameters flattened in graph order:
+ * bn0 weight, bias, mean, var [8 each]; 8 x (conv W [cout][cin][k], b [cout]); fc1 W [256][128], b; fc2 W [2][256], b.
+ * out may be NULL to query *n_floats.  hm_engine_create uses <model_dir>/<ctx>.onnx, or <ctx>.pt when HM_MODEL_FORMAT=pt is set
+ * or no .onnx is there. */
+int hm_model_weights(const char* path, float* out, size_t cap, size_t* n_floats, int32_t* conv1_k);
+
 int hm_batch_acquire(hm_engine* e, int slot, hm_read_batch* out);
 int hm_batch_submit(hm_engine* e, int slot, uint32_t n_reads, uint32_t flags);
 int hm_batch_collect(hm_engine* e, int slot, hm_call_batch* out);

@@ -334,3 +334,33 @@ def test_existing_mn_tag_keeps_its_width_like_bam_aux_update_int(lib_built):
         want = R.build_mod_bam(body, False, q, m, [], [])
         got = hme.build_mod_record(body, False, q, m, [], [])
         assert got == want and got[-(3 + {b"C": 1, b"S": 2, b"I": 4}[typ]):][:3] == b"MN" + typ, (L, typ)
+
+
+def test_model_loader_onnx_and_torchscript(lib_built, tmp_path):
+    """The weight loader reads both ONNX dialects and the TorchScript .pt exports (ZIP directory + the 24 stored constants):
+    parameters equal the oracle's own parse of the .onnx files; CpG.pt / CHH.pt equal their .onnx (<= 2.4e-7 / bit-equal) and
+    CHG.pt is the different checkpoint SURVEY.md s0.5 describes; damaged archives are errors, not crashes."""
+    from oracle import cnn_oracle
+
+    md = ROOT / "models"
+    for name, k1 in (("CpG", 11), ("CHG", 11), ("CHH", 13)):
+        w = cnn_oracle.CnnWeights(md / f"{name}.onnx")
+        want = np.concatenate([np.ravel(t) for t in w.bn0] + [np.ravel(x) for cw, cb in w.convs for x in (cw, cb)] +
+                              [np.ravel(w.fcs[0][0]), np.ravel(w.fcs[0][1]), np.ravel(w.fcs[1][0]), np.ravel(w.fcs[1][1])]).astype(np.float32)
+        got, k = hme.model_weights(md / f"{name}.onnx")
+        assert k == k1 and got.shape == want.shape and (got == want).all(), name
+        pt, kp = hme.model_weights(md / f"{name}.pt")
+        assert kp == k1 and pt.shape == want.shape
+        d = float(np.abs(pt - want).max())
+        if name == "CHH":
+            assert d == 0.0
+        elif name == "CpG":
+            assert d < 1e-6
+        else:
+            assert d > 1e-2  # CHG.pt is another checkpoint
+    raw = (md / "CpG.pt").read_bytes()
+    for bad in (raw[:1000], raw[:-30], b"PK" + bytes(100), raw.replace(b"constants/7", b"constantz/7")):
+        f = tmp_path / "bad.pt"
+        f.write_bytes(bad)
+        with pytest.raises(hme.HmError):
+            hme.model_weights(f)
