@@ -499,3 +499,29 @@ def test_product_feature_map_and_layer_activations_direct(lib_built, models):
         assert (again.ml == got.ml).all() and (again.qoff == got.qoff).all()
     finally:
         eng.close()
+
+
+def test_torchscript_weights_give_the_same_calls(lib_built, monkeypatch):
+    """north_star: "the same models/{CpG,CHG,CHH}.onnx/.pt weights".  An engine created from the .pt exports (HM_MODEL_FORMAT=pt; the
+    files the reference's app-gpu binary loads, 5mc_call_gpu.cpp:48) calls CHH bit-identically to the .onnx engine (the two files hold
+    the same bits) and CpG within float noise (weights differ by <= 2.4e-7).  CHG.pt is another checkpoint and is not compared."""
+    batch, _ = synth.make_reads(6, (1000, 3000), seed=31337, flag_rev_every=3)
+    a = hme.Engine(ctx_mask=5, max_reads=16, max_bases=1 << 16, keep_debug=True)
+    try:
+        ra = a.call(batch)
+        la = a.dump_logits(0, ra.n_calls)
+        ctx = a.dump_ctx(0, ra.n_calls)
+    finally:
+        a.close()
+    monkeypatch.setenv("HM_MODEL_FORMAT", "pt")
+    b = hme.Engine(ctx_mask=5, max_reads=16, max_bases=1 << 16, keep_debug=True)
+    try:
+        rb = b.call(batch)
+        lb = b.dump_logits(0, rb.n_calls)
+    finally:
+        b.close()
+    assert ra.n_calls == rb.n_calls and (ra.qoff == rb.qoff).all()
+    chh, cpg = ctx == 2, ctx == 0
+    assert chh.sum() > 1000 and cpg.sum() > 100
+    assert (la[chh].view(np.uint32) == lb[chh].view(np.uint32)).all() and (ra.ml[chh] == rb.ml[chh]).all()
+    assert np.abs(la[cpg] - lb[cpg]).max() < 1e-4 and np.abs(ra.ml[cpg].astype(int) - rb.ml[cpg].astype(int)).max() <= 1
