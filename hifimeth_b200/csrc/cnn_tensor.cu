@@ -419,11 +419,11 @@ bool fuse12_enabled()
     return v;
 }
 
-// the compact chain (F2.. head) of a site tile in one kernel (site_chain.cuh): HM_CHAIN=1.  Off by default while it is slower
-// than the op-by-op launches (round 2: 30 ms against 24 ms per step).
+// the compact chain (F2.. head) of a site tile in one kernel (site_chain.cuh), running maps in tensor memory; HM_NO_CHAIN=1 launches
+// the compact ops one by one instead (A/B measurements: 97.7 / 99.2 ms per step op by op against 93.0 / 94.4 ms on the same box).
 bool chain_enabled()
 {
-    static const bool v = getenv("HM_CHAIN") != nullptr && getenv("HM_NO_CHAIN") == nullptr;
+    static const bool v = getenv("HM_NO_CHAIN") == nullptr;
     return v;
 }
 
@@ -579,15 +579,14 @@ struct TensorModel {
     // the compact chain as one kernel (site_chain_kernel): every compact op except the conv1-form ones, in chain order
     struct ChainItem {
         DevOp d;                      // pair lowering: weights / bias offsets in the blob, n, macs
-        int term_map[kMaxTerms] = {0, 0, 0};  // source map of each term (streamed terms; resident ones carry dep / res_off in c)
+        int term_map[kMaxTerms] = {0, 0, 0};  // source map of each term
+        bool resident[kMaxTerms] = {false, false, false};  // the term reads a packed map in TMEM (written by an earlier chain op)
         int out_map = -1;
         ChainOp c{};                  // template: pointers are patched per launch
     };
     bool chain = false;
     std::vector<ChainItem> chain_ops;
     size_t chain_w2_off = 0, chain_b2_off = 0;
-    size_t blob_stride = 0;   // the blob is stored blob_copies times, blob_stride bytes apart (site_chain.cuh: one copy per few CTA pairs)
-    uint32_t blob_copies = 1;
 };
 
 const char* tensor_last_error() { return g_err.c_str(); }
@@ -650,7 +649,10 @@ int tensor_model_build(TensorModelHandle& m, const CnnModel& host)
     if (compact_mode() && chain_enabled() && two_cta_enabled()) {
         // ---- chain order: F2 G2 .. F6 G6 | T7_1 T7_2 T7_0 T7_3 | T8_0 T8_1 | head ------------------------------------------------
         // F and G alternate so that the MMAs of one run under the epilogue of the other; T7_1 / T7_2 read scatter copies only and
-        // go first; the four T7 accumulators stay in TMEM until T7_0 / T7_3 have read F6 / G6, whose buffers their outputs reuse.
+        // go first.  TMEM columns (site_chain.cuh): packed F map [0,128) | packed G map [128,256) | F accumulator [256,384) |
+        // G accumulator [384,512).  Tail: T7 accumulators T7_1 256, T7_2 320 (over the drained F accumulator), T7_0 384, T7_3 448
+        // (over the drained G accumulator); packed T7 outputs over what F6 / G6 (96 channels) leave free or dead; T8 accumulators
+        // 256 / 320, packed T8 outputs [384,512); head accumulator [0,256).
         std::vector<const HostOp*> order;
         auto add = [&](int out, bool head) {
             for (const HostOp& h : plan)
@@ -659,60 +661,106 @@ int tensor_model_build(TensorModelHandle& m, const CnnModel& host)
         };
         bool ok = true;
         for (int l = 2; l <= 6 && ok; ++l) ok = add(MAP_F + l - 1, false) && add(MAP_G + l - 1, false);
-        for (int v : {1, 2, 0, 3}) ok = ok && add(MAP_T7 + v, false);
+        for (int v : {1, 0, 3, 2}) ok = ok && add(MAP_T7 + v, false);
         ok = ok && add(MAP_T8 + 0, false) && add(MAP_T8 + 1, false) && add(-1, true);
         size_t n_compact = 0;
         for (const HostOp& h : plan) n_compact += (h.compact && h.conv1_taps == 0) ? 1 : 0;
         ok = ok && order.size() == n_compact && order.size() <= (size_t)kChainMaxOps;
-        int i_t73 = -1;
         std::vector<TensorModel::ChainItem> items;
+        auto index_of = [&](int out_map) {
+            for (size_t j = 0; j < items.size(); ++j)
+                if (items[j].out_map == out_map && !items[j].c.head) return (int)j;
+            return -1;
+        };
+        size_t steps = 0;
         for (size_t i = 0; i < order.size() && ok; ++i) {
             const HostOp& h = *order[i];
             TensorModel::ChainItem it;
             HostOp hw = h;       // the pair lowering packs the weights; the head is lowered as a plain op (fc2 lives in the epilogue)
             hw.head = false;
             hw.scatter.clear();
-            std::vector<uint8_t> trial = blob;
-            if (!lower_op(hw, 0, h.cout, it.d, trial, err, true)) { ok = false; break; }
-            blob.swap(trial);
+            std::vector<uint8_t> tmp;
+            if (h.cin % 32 || h.cout % 32 || !lower_op(hw, 0, h.cout, it.d, tmp, err, true)) { ok = false; break; }
+            // ---- chain image: per rank [stage pair][term][stage][hl] tiles, so that a ring step is one contiguous block -------------
+            const uint32_t n_terms = (uint32_t)h.terms.size(), tile = (uint32_t)h.cout * 16u, rank_bytes = it.d.p.w_bytes;
+            if (rank_bytes != (uint32_t)(h.cin / 16) * n_terms * 2u * tile) { ok = false; break; }
+            {
+                size_t o = (blob.size() + 255) & ~(size_t)255;
+                blob.resize(o + 2 * (size_t)rank_bytes);
+                const uint8_t* src = tmp.data() + it.d.w_off;  // where lower_op put the [stage][term][hl] image of rank 0
+                it.d.w_off = o;
+                uint8_t* dst = blob.data() + o;
+                for (uint32_t r = 0; r < 2; ++r)
+                    for (uint32_t S = 0; S < (uint32_t)h.cin / 32; ++S)
+                        for (uint32_t k = 0; k < n_terms; ++k)
+                            for (uint32_t st = 0; st < 2; ++st)
+                                for (uint32_t hl = 0; hl < 2; ++hl) {
+                                    memcpy(dst, src + (size_t)r * rank_bytes + ((size_t)((2 * S + st) * n_terms + k) * 2 + hl) * tile, tile);
+                                    dst += tile;
+                                }
+                o = (blob.size() + 255) & ~(size_t)255;
+                blob.resize(o + (size_t)h.cout * 4);
+                memcpy(blob.data() + o, h.bias.data(), (size_t)h.cout * 4);
+                it.d.bias_off = o;
+            }
+            steps += (size_t)(h.cin / 32) * n_terms;
             ChainOp& c = it.c;
-            c.n = h.cout; c.cin = h.cin; c.n_terms = (int)h.terms.size(); c.head = h.head ? 1 : 0;
+            c.n = h.cout; c.cin = h.cin; c.n_terms = (int)n_terms; c.head = h.head ? 1 : 0;
+            c.w_rank_bytes = rank_bytes;
             c.wait_op = (int)i;
+            for (int q = 0; q < kChainMaxWait; ++q) c.mma_wait[q] = -1;
             it.out_map = h.out;
-            // a ring slot holds the term's weight tiles (cout x 32 bytes for this CTA) after the 8 KiB slab of a streamed term;
-            // the head's terms are resident (checked below), every other op may stream
-            if (h.cin % 16 || h.cout % 32 || (uint32_t)h.cout * 32u + (h.head ? 0u : kChainSlabBytes) > kChainSlotBytes) { ok = false; break; }
-            if (h.head) { c.tmem_col = 256; c.regions = 0xf0u; }
-            else if (h.out >= MAP_F && h.out < MAP_G) { c.out_off = 0; c.tmem_col = 0; c.regions = 0x03u; }
-            else if (h.out >= MAP_G && h.out < MAP_T7) { c.out_off = kChainResBytes; c.tmem_col = 128; c.regions = 0x0cu; }
+            // a ring slot holds the step's weight tiles (cout x 64 bytes for this CTA) in front of the 16 KiB slab of a streamed term
+            if ((uint32_t)h.cout * 64u > (h.head ? kChainSlotBytes : kChainWBytes)) { ok = false; break; }
+            int extra_wait[2] = {-1, -1};
+            const uint32_t nh2 = (uint32_t)h.cout / 2;  // columns of the packed hi half (and of the lo half)
+            if (h.head) { c.acc_col = 0; if (h.cout != 256) { ok = false; break; } }
+            else if (h.out >= MAP_F && h.out < MAP_G) { c.acc_col = 256; c.out_hi_col = 0; c.out_lo_col = nh2; }
+            else if (h.out >= MAP_G && h.out < MAP_T7) { c.acc_col = 384; c.out_hi_col = 128; c.out_lo_col = 128 + nh2; }
             else if (h.out >= MAP_T7 && h.out < MAP_T8) {
-                const int v = h.out - MAP_T7;
-                static const uint32_t off[4] = {0, kChainResBytes / 2, kChainResBytes, kChainResBytes + kChainResBytes / 2};
-                static const uint32_t col[4] = {384, 256, 320, 448};   // T7_1 -> 256, T7_2 -> 320, T7_0 -> 384, T7_3 -> 448
-                c.out_off = off[v]; c.tmem_col = col[v]; c.regions = 1u << (col[v] / 64);
-                if (v == 3) i_t73 = (int)i;
-                if (h.cout != 64) { ok = false; break; }
+                if (h.cout != 64 || h.cin != 96) { ok = false; break; }
+                const int v = h.out - MAP_T7, f6 = index_of(MAP_F + 5), g6 = index_of(MAP_G + 5);
+                // T7_0 is the only reader of F6 and T7_3 of G6: their packed outputs go over their own inputs; T7_1 goes to the 2 x 32
+                // columns the 96-channel maps leave free, T7_2 (issued last) to the 2 x 32 columns left in the dead F6 / G6
+                static const uint32_t acc[4] = {384, 256, 320, 448}, ohi[4] = {0, 96, 64, 128}, olo[4] = {32, 224, 192, 160};
+                c.acc_col = acc[v]; c.out_hi_col = ohi[v]; c.out_lo_col = olo[v];
+                extra_wait[0] = (v == 1 || v == 2) ? f6 : g6;  // the accumulator columns were F6's / G6's accumulator
+                if (f6 < 0 || g6 < 0) { ok = false; break; }
             } else if (h.out >= MAP_T8 && h.out < MAP_S) {
+                if (h.cout != 64 || h.cin != 64) { ok = false; break; }
                 const int w = h.out - MAP_T8;
-                c.out_off = w ? kChainResBytes / 2 : 0; c.tmem_col = w ? 128 : 0; c.regions = w ? 0x04u : 0x01u;
-                if (h.cout != 64) { ok = false; break; }
+                c.acc_col = w ? 320 : 256; c.out_hi_col = w ? 448 : 384; c.out_lo_col = w ? 480 : 416;
             } else { ok = false; break; }
-            for (size_t k = 0; k < h.terms.size(); ++k) {
+            int nw = 0;
+            auto add_wait = [&](int j) {
+                if (j < 0) return true;
+                for (int q = 0; q < nw; ++q) if (c.mma_wait[q] == j) return true;
+                if (nw == kChainMaxWait) return false;
+                c.mma_wait[nw++] = j;
+                return true;
+            };
+            for (size_t k = 0; k < h.terms.size() && ok; ++k) {
                 if (h.terms[k].shift != 0 || h.terms[k].gather) { ok = false; break; }
                 it.term_map[k] = h.terms[k].src;
-                c.term[k].dep = -1;
-                for (size_t j = 0; j < i; ++j)
-                    if (items[j].out_map == h.terms[k].src && !items[j].c.head) { c.term[k].dep = (int)j; c.term[k].res_off = items[j].c.out_off; }
                 const int sm = h.terms[k].src;
                 const bool streamed_kind = sm >= MAP_S || sm == MAP_F || sm == MAP_G;  // scatter copies, F1, G1
-                if ((c.term[k].dep < 0) != streamed_kind || (h.head && streamed_kind)) { ok = false; break; }
+                const int dep = index_of(sm);
+                it.resident[k] = dep >= 0;
+                if ((dep < 0) != streamed_kind || (h.head && streamed_kind)) { ok = false; break; }
+                if (dep >= 0) {
+                    if (items[dep].c.n != h.cin) { ok = false; break; }
+                    c.term[k].a_hi_col = items[dep].c.out_hi_col;
+                    c.term[k].a_lo_col = items[dep].c.out_lo_col;
+                    ok = add_wait(dep);
+                }
             }
+            ok = ok && add_wait(extra_wait[0]) && add_wait(extra_wait[1]);
+            if (!ok) break;
             items.push_back(it);
         }
-        if (ok && i_t73 >= 0) {
-            // the T7 outputs overwrite F6 / G6, which T7_0 / T7_3 read: their epilogues wait for the last T7 op's MMAs
-            for (auto& it : items)
-                if (it.out_map >= MAP_T7 && it.out_map < MAP_T8) it.c.wait_op = i_t73;
+        if (ok) {
+            // every T7 output goes to columns that only EARLIER MMAs read (order T7_1 T7_0 T7_3 T7_2): no epilogue waits for a later op
+            ok = steps < (size_t)kChainMaxSteps && steps >= (size_t)kChainSlots;
         }
         if (ok) {
             const HostOp& hh = *order.back();
@@ -728,14 +776,8 @@ int tensor_model_build(TensorModelHandle& m, const CnnModel& host)
             t->chain = true;
         }
     }
-    if (t->chain) {
-        const char* env = getenv("HM_CHAIN_WCOPIES");
-        t->blob_copies = (uint32_t)std::max(1, std::min(64, env ? atoi(env) : 16));
-    }
-    t->blob_stride = (blob.size() + 4095) & ~(size_t)4095;
-    cudaError_t st = cudaMalloc((void**)&t->d_blob, t->blob_stride * t->blob_copies);
-    for (uint32_t c = 0; c < t->blob_copies && st == cudaSuccess; ++c)
-        st = cudaMemcpy(t->d_blob + c * t->blob_stride, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+    cudaError_t st = cudaMalloc((void**)&t->d_blob, blob.size());
+    if (st == cudaSuccess) st = cudaMemcpy(t->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice);
     if (st != cudaSuccess) { cudaFree(t->d_blob); delete t; return tfail(std::string("weight upload: ") + cudaGetErrorString(st)); }
     for (DevOp& d : t->ops) bind_blob(d, t->d_blob);
     if (t->fused12) bind_blob(t->f12_c1, t->d_blob);
@@ -882,6 +924,7 @@ DenseOp patch_op(const DevOp& d, const TensorWorkspaceImpl& s, uint32_t n_tiles,
 }
 
 long long* g_f12_dbg = nullptr;
+long long* g_chain_dbg = nullptr;
 
 // conv1 + conv2 of `rows` dense rows in one launch (dense_fused12_kernel): tiles of 124 output rows, CTA pairs.
 int launch_fused12(const DevOp& d1, const DevOp& d2, TensorWorkspaceImpl& s, uint32_t rows, int sm_count, cudaStream_t stream)
@@ -938,15 +981,20 @@ int launch_chain(const TensorModel& tm, TensorWorkspaceImpl& s, uint32_t n_tiles
     p.n_ops = (int)tm.chain_ops.size();
     p.n_tiles = n_tiles;
     p.plane_stride = s.cplane_stride;
-    p.w_copy_stride = tm.blob_stride;
-    p.w_copies = tm.blob_copies;
     p.w2 = reinterpret_cast<const float*>(tm.d_blob + tm.chain_w2_off);
     p.b2 = reinterpret_cast<const float*>(tm.d_blob + tm.chain_b2_off);
     p.logits = logit_out;
+    // HM_CHAIN_STAMPS=1: pair 0 stamps the third tile round of every launch; the last launch's stamps are printed after the batch
+    static const bool stamps = getenv("HM_CHAIN_STAMPS") != nullptr;
+    if (stamps) {
+        if (!g_chain_dbg) cudaMalloc((void**)&g_chain_dbg, 512 * sizeof(long long));
+        cudaMemsetAsync(g_chain_dbg, 0, 512 * sizeof(long long), stream);
+        p.dbg = g_chain_dbg;
+    }
     for (int i = 0; i < p.n_ops; ++i) {
         const TensorModel::ChainItem& it = tm.chain_ops[i];
         p.op[i] = it.c;
-        for (int k = 0; k < it.c.n_terms; ++k) p.op[i].term[k].src = it.c.term[k].dep < 0 ? s.map[it.term_map[k]] : nullptr;
+        for (int k = 0; k < it.c.n_terms; ++k) p.op[i].term[k].src = it.resident[k] ? nullptr : s.map[it.term_map[k]];
         p.op[i].spill = (spill && !it.c.head) ? s.map[it.out_map] : nullptr;
         s.macs += (double)((n_tiles + 1) / 2 * 2) * kTileRows * it.d.macs_per_row;
     }
@@ -1202,6 +1250,17 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
             for (int k = 0; k < 16; ++k) fprintf(stderr, " %7lld%s", h[16 * t + k] ? h[16 * t + k] - t0 : -1, (k == 2 || k == 10 || k == 11 || k == 14) ? " |" : "");
             fprintf(stderr, "\n");
         }
+    }
+    if (g_chain_dbg) {  // HM_CHAIN_STAMPS: ring timeline of pair 0 of the last chain launch (cycles; each SM has its own clock)
+        cudaStreamSynchronize(stream);
+        std::vector<long long> h(512);
+        cudaMemcpy(h.data(), g_chain_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "chain MMA warp of pair 0, steps of tile round 2: [cycles waiting for the slot] cycles until the next wait ...\n");
+        for (int i = 0; i < 124 && h[2 * i]; ++i)
+            fprintf(stderr, " [%lld] %lld", h[2 * i + 1] - h[2 * i], i < 123 && h[2 * i + 2] ? h[2 * i + 2] - h[2 * i + 1] : -1);
+        fprintf(stderr, "\nchain epilogue warp 0 of pair 0, ops of tile round 2: wait for the MMAs / work (cycles), start relative to op 0\n");
+        for (int i = 0; i < kChainMaxOps && h[256 + 3 * i]; ++i)
+            fprintf(stderr, " op%d @%lld: %lld / %lld\n", i, h[256 + 3 * i] - h[256], h[256 + 3 * i + 1] - h[256 + 3 * i], h[256 + 3 * i + 2] - h[256 + 3 * i + 1]);
     }
     if (timing) {
         timing->top_kernel_launches = dense_launches;

@@ -158,6 +158,20 @@ __device__ __forceinline__ void mma2_commit_mc(uint64_t* bar)
                  "h"((uint16_t)3)
                  : "memory");
 }
+// Same with the A operand in TENSOR MEMORY (cute's SM100_MMA_F16BF16_2x1SM_TS): row m of this CTA's 128 rows is TMEM lane m, K runs
+// along the columns, two bf16 per 32-bit column (element 2c in the low half of column c), so a K = 16 tile is 8 columns.  The layout
+// and the rate were checked on a B200 (tools/mma_ts_probe.cu): exact results, and N = 96 / 64 take 48 / 46 cycles per MMA instead of
+// the 64 of the shared-memory form (no 4 KB A fetch).
+__device__ __forceinline__ void mma2_ts_bf16_w(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, {%6, %6, %6, %6, %6, %6, %6, %6}, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
 __host__ __device__ constexpr uint32_t make_idesc_bf16_m256(uint32_t n)
 {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((256u >> 4) << 24);
@@ -301,6 +315,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- tcgen05: registers -> TMEM (whole warp; lane i of warp w writes TMEM lane 32*(w%4)+i, N consecutive columns) -------------
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+                 "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+                 "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 }  // namespace umma
 }  // namespace hm

@@ -3,6 +3,7 @@
 Bars (BASELINE.json north_star): decoded kinetics, base codes, site lists, call order and feature tensors BIT-EXACT;
 per-site probability within 1e-3 absolute; ML byte within +-1.
 """
+import os
 import numpy as np
 import pytest
 
@@ -525,3 +526,33 @@ def test_torchscript_weights_give_the_same_calls(lib_built, monkeypatch):
     assert chh.sum() > 1000 and cpg.sum() > 100
     assert (la[chh].view(np.uint32) == lb[chh].view(np.uint32)).all() and (ra.ml[chh] == rb.ml[chh]).all()
     assert np.abs(la[cpg] - lb[cpg]).max() < 1e-4 and np.abs(ra.ml[cpg].astype(int) - rb.ml[cpg].astype(int)).max() <= 1
+
+
+def test_chain_kernel_and_op_by_op_compact_ops_agree(lib_built, tmp_path):
+    """The compact chain of a site tile runs in one kernel with its maps in tensor memory (site_chain.cuh); HM_NO_CHAIN=1 launches
+    the same ops one by one through HBM.  Same split-precision products, different fp32 accumulation order only: logits agree to
+    float noise, site lists exactly, ML bytes within the +-1 of a truncation boundary."""
+    import subprocess
+    import sys
+
+    code = (
+        "import numpy as np, sys\n"
+        "from hifimeth_b200 import engine as hme, synth\n"
+        "batch, _ = synth.make_reads(5, (1500, 4000), seed=4242, flag_rev_every=2)\n"
+        "e = hme.Engine(max_reads=16, max_bases=1 << 16, keep_debug=True)\n"
+        "r = e.call(batch)\n"
+        "np.savez(sys.argv[1], qoff=r.qoff, ml=r.ml, logits=e.dump_logits(0, r.n_calls), launches=e.timing(0).kernel_launches)\n"
+        "e.close()\n"
+    )
+    out = {}
+    for name, env in (("chain", {}), ("ops", {"HM_NO_CHAIN": "1"})):
+        path = tmp_path / f"{name}.npz"
+        full = dict(os.environ, **env)
+        full.pop("HM_NO_CHAIN", None) if not env else None
+        subprocess.run([sys.executable, "-c", code, str(path)], check=True, env=full, cwd=str(ROOT), timeout=300)
+        out[name] = np.load(path)
+    a, b = out["chain"], out["ops"]
+    assert (a["qoff"] == b["qoff"]).all() and len(a["qoff"]) > 3000
+    assert int(a["launches"]) < int(b["launches"])  # one chain launch per context instead of 17 compact ops
+    assert np.abs(a["logits"] - b["logits"]).max() < 2e-4
+    assert np.abs(a["ml"].astype(int) - b["ml"].astype(int)).max() <= 1
