@@ -530,11 +530,13 @@ __global__ void __launch_bounds__(256)
 site_rows_kernel(const uint32_t* __restrict__ track_row_fwd, const uint32_t* __restrict__ track_row_rev,
                  const uint32_t* __restrict__ base_off, const uint32_t* __restrict__ site_read, const uint32_t* __restrict__ site_pos,
                  uint32_t first_a, uint32_t n_a, uint32_t first_b, uint32_t n, uint32_t n_pad, uint32_t row_base, uint32_t m_off,
-                 uint32_t* __restrict__ rows, int32_t* __restrict__ site_of_row)
+                 const uint32_t* __restrict__ site_out, uint32_t* __restrict__ rows, int32_t* __restrict__ site_of_row,
+                 uint32_t* __restrict__ out_idx)
 {
     const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= n_pad) return;
     uint32_t row = 0;  // padding rows read row 0 (any valid row) and are never looked at
+    out_idx[m_off + m] = m < n ? site_out[run_site(m, first_a, n_a, first_b)] : 0xffffffffu;  // where the chain kernel's head writes the call
     if (m < n) {
         const uint32_t k = run_site(m, first_a, n_a, first_b);
         const uint32_t r = site_read[k];
@@ -815,6 +817,7 @@ struct TensorWorkspaceImpl {
     const uint8_t* x_cur = nullptr;   // X rows of the sub-batch being launched (points into d_xg) and their plane stride
     unsigned long long x_stride_cur = 0;
     uint32_t* d_site_rows = nullptr;  // [compact_cap] compact row -> X row (global)
+    uint32_t* d_out_idx = nullptr;    // [compact_cap + 2 tiles] compact row -> site index in hm_call_batch order (0xffffffff: padding)
     float* d_clogit = nullptr;        // [rows_cap][2] logits of the compact rows
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // shape of the last tensor_batch_run (debug hooks): sub-batches, compact groups per context, rows of the X map
@@ -864,6 +867,7 @@ int tensor_workspace_alloc(TensorWorkspace& w, uint32_t max_bases, uint32_t max_
     if (!compact_mode())
         for (int c = 0; c < 3; ++c) TCUDA("logit rows", cudaMalloc((void**)&s->d_logit[c], total_rows * 2 * sizeof(float)));
     TCUDA("site rows", cudaMalloc((void**)&s->d_site_rows, (cap + kTileRows) * sizeof(uint32_t)));
+    TCUDA("site rows", cudaMalloc((void**)&s->d_out_idx, (cap + 2 * kTileRows) * sizeof(uint32_t)));
     TCUDA("site rows", cudaMalloc((void**)&s->d_clogit, (cap + kTileRows) * 2 * sizeof(float)));
     s->tiles_cap = (uint32_t)(total_rows / kTileRows + 1);
     s->reads_cap = max_reads;
@@ -884,7 +888,7 @@ void tensor_workspace_free(TensorWorkspace& w)
     if (!s) return;
     cudaFree(s->d_maps);
     for (float* p : s->d_logit) cudaFree(p);
-    cudaFree(s->d_site_rows); cudaFree(s->d_clogit); cudaFree(s->d_site_of_row); cudaFree(s->d_xg);
+    cudaFree(s->d_site_rows); cudaFree(s->d_out_idx); cudaFree(s->d_clogit); cudaFree(s->d_site_of_row); cudaFree(s->d_xg);
     cudaFreeHost(s->h_tile_read); cudaFreeHost(s->h_tile_first); cudaFree(s->d_tile_read); cudaFree(s->d_tile_first);
     cudaFreeHost(s->h_track_row); cudaFree(s->d_track_row);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -975,7 +979,7 @@ int launch_op(const DevOp& d, TensorWorkspaceImpl& s, uint32_t n_tiles, float* l
 }
 
 // The compact chain of n_tiles site tiles in one launch (site_chain_kernel).  spill: also store every map to its HBM buffer (debug).
-int launch_chain(const TensorModel& tm, TensorWorkspaceImpl& s, uint32_t n_tiles, float* logit_out, bool spill, int sm_count, cudaStream_t stream)
+int launch_chain(const TensorModel& tm, TensorWorkspaceImpl& s, uint32_t n_tiles, float* logits, uint8_t* ml, bool spill, int sm_count, cudaStream_t stream)
 {
     ChainProgram p{};
     p.n_ops = (int)tm.chain_ops.size();
@@ -983,7 +987,11 @@ int launch_chain(const TensorModel& tm, TensorWorkspaceImpl& s, uint32_t n_tiles
     p.plane_stride = s.cplane_stride;
     p.w2 = reinterpret_cast<const float*>(tm.d_blob + tm.chain_w2_off);
     p.b2 = reinterpret_cast<const float*>(tm.d_blob + tm.chain_b2_off);
-    p.logits = logit_out;
+    p.logits = logits;
+    p.ml = ml;
+    p.out_idx = s.d_out_idx;
+    // an odd tile count: the peer CTA of the last pair works on one tile of padding rows
+    if (n_tiles & 1u) cudaMemsetAsync(s.d_out_idx + (size_t)n_tiles * kTileRows, 0xff, kTileRows * sizeof(uint32_t), stream);
     // HM_CHAIN_STAMPS=1: pair 0 stamps the third tile round of every launch; the last launch's stamps are printed after the batch
     static const bool stamps = getenv("HM_CHAIN_STAMPS") != nullptr;
     if (stamps) {
@@ -1157,7 +1165,8 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
                     const uint32_t n_pad = ((m_off + n + kTileRows - 1) / kTileRows) * kTileRows - m_off;
                     site_rows_kernel<<<(n_pad + 255) / 256, 256, 0, stream>>>(s->d_track_row, s->d_track_row + s->reads_cap, b.d_base_off,
                                                                               b.d_site_read, b.d_site_pos, first_a, n_a, first_b, n, n_pad,
-                                                                              sb.gtile0 * kTileRows, m_off, s->d_site_rows, s->d_site_of_row);
+                                                                              sb.gtile0 * kTileRows, m_off, b.d_site_out, s->d_site_rows,
+                                                                              s->d_site_of_row, s->d_out_idx);
                     ++*launches;
                     s->x_cur = s->d_xg + (size_t)sb.gtile0 * kTileRows * 16;
                     int op_i = 0;
@@ -1188,11 +1197,12 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
                     }
                     if (chain) {
                         stamp(c * 64 + 63);
-                        launch_chain(tm, *s, n_tiles, s->d_clogit, s->spill_chain, sm_count, stream);
+                        launch_chain(tm, *s, n_tiles, b.d_logits, b.d_ml, s->spill_chain, sm_count, stream);  // writes logits + ML bytes itself
                         ++dense_launches;
                     }
                     stamp(-1);
                     for (const Seg& sg : segs) {
+                        if (chain) break;
                         site_finish_kernel<<<(sg.n + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const float2*>(s->d_clogit) + sg.m_off, b.d_site_out,
                                                                                    sg.first_a, sg.n_a, sg.first_b, sg.n, b.d_logits, b.d_ml);
                         ++*launches;
@@ -1261,6 +1271,8 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
         fprintf(stderr, "\nchain epilogue warp 0 of pair 0, ops of tile round 2: wait for the MMAs / work (cycles), start relative to op 0\n");
         for (int i = 0; i < kChainMaxOps && h[256 + 3 * i]; ++i)
             fprintf(stderr, " op%d @%lld: %lld / %lld\n", i, h[256 + 3 * i] - h[256], h[256 + 3 * i + 1] - h[256 + 3 * i], h[256 + 3 * i + 2] - h[256 + 3 * i + 1]);
+        fprintf(stderr, "chain MMA warp, op prologues of tile round 2: start (relative to op 0) / cycles waiting for epilogues\n");
+        for (int i = 0; i < kChainMaxOps && h[320 + 2 * i]; ++i) fprintf(stderr, " op%d @%lld: %lld\n", i, h[320 + 2 * i] - h[320], h[321 + 2 * i] - h[320 + 2 * i]);
     }
     if (timing) {
         timing->top_kernel_launches = dense_launches;

@@ -22,7 +22,7 @@
 //              operands also run faster: N = 96 / 64 take 48 / 46 cycles per MMA from TMEM against 64 from shared memory
 //              (tools/mma_ts_probe.cu)
 //   epilogue   8 warps per CTA: accumulator -> + bias, ReLU -> hi / lo bf16 pairs -> tcgen05.st into the op's packed columns; the
-//              head's epilogue applies fc2 and writes the site's two logits
+//              head's epilogue applies fc2, the softmax and the `(int)(255 p)` truncation and writes the site's logits and ML byte
 //
 // Who may overwrite what (the column plan is made by the host, cnn_tensor.cu): MMAs execute in issue order, so an accumulator may
 // overwrite columns that EARLIER MMAs read; an MMA waits (mma_wait) for the epilogues that produce its resident inputs and that drain
@@ -30,10 +30,11 @@
 // MMAs still read the columns its packed output goes to; the epilogue warps of a CTA meet at a named barrier after the head, because
 // the next round's F2 / G2 outputs go where the head's accumulator was.
 //
-// HBM traffic per site: the scatter copies and F1 / G1 read once (~7.5 KB) and 8 B of logits written.  conv1-form ops (F1, G1:
+// HBM traffic per site: the scatter copies and F1 / G1 read once (~7.5 KB) and 9 B of logits + ML byte written.  conv1-form ops (F1, G1:
 // gathered from the X map) stay separate launches of dense_gemm_kernel.
 #pragma once
 #include "dense_gemm2.cuh"
+#include "postprocess.cuh"
 
 namespace hm {
 
@@ -74,7 +75,9 @@ struct ChainProgram {
     unsigned long long plane_stride;   // of every compact map (streamed sources and spill targets)
     const float* w2;                   // head: [2][256], [2]
     const float* b2;
-    float* logits;                     // [rows][2]
+    const uint32_t* out_idx;           // [rows] compact row -> index of the site in hm_call_batch order; 0xffffffff = padding row
+    float* logits;                     // [sites][2] in hm_call_batch order
+    uint8_t* ml;                       // [sites] the quantised ML byte (s_logits_to_methy_probs, src/app/hifimeth/mod_batch.cpp:46-64)
     long long* dbg;                    // HM_CHAIN_STAMPS: clock64 timeline of pair 0 (third tile round), else nullptr
 };
 
@@ -211,6 +214,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) si
             const uint32_t ring16 = umma::smem_u32(s_ring) >> 4;
             const uint32_t a_desc = (uint32_t)umma::make_desc(0, kChainPlaneBytes, 128);  // K-adjacent core matrices one plane apart
             uint32_t step = 0, it = 0, mstep = 0;
+            bool ready = false;  // the NEXT step's slot is probed before this step's MMAs are issued: hides the barrier round trip
             for (uint32_t t2 = pair; 2 * t2 < prog.n_tiles; t2 += n_pairs, ++it) {
                 for (int oi = 0; oi < n_ops; ++oi) {
                     const ChainOp& op = s_ops[oi];
@@ -219,11 +223,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) si
                     const uint32_t idesc = umma::make_idesc_bf16_m256((uint32_t)op.n);
                     const uint32_t b_desc = (uint32_t)umma::make_desc(0, nh * 16u, 128);
                     const uint32_t b_tile16 = (nh * 32u) >> 4;  // the {hi} or the {lo} tile of one stage
+                    const bool sto = prog.dbg && pair == 0 && it == 2 && lane == 0;
+                    if (sto) prog.dbg[320 + 2 * oi] = clock64();
                     // resident inputs written and accumulator columns drained by earlier epilogues (both CTAs)
                     #pragma unroll
                     for (int q = 0; q < kChainMaxWait; ++q)
                         if (op.mma_wait[q] >= 0) umma::mbar_wait(&res_ready[op.mma_wait[q]], it & 1u);
                     umma::tc_fence_after();
+                    if (sto) prog.dbg[321 + 2 * oi] = clock64();
                     const uint32_t d_addr = tmem_base + op.acc_col;
                     uint32_t acc = 0;
                     for (uint32_t S = 0; S < n_spairs; ++S) {
@@ -231,7 +238,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) si
                             const uint32_t slot = step % (uint32_t)kChainSlots, phase = (step / (uint32_t)kChainSlots) & 1u;
                             const bool st = prog.dbg && pair == 0 && it == 2 && lane == 0 && mstep < 124u;
                             if (st) prog.dbg[2 * mstep] = clock64();
-                            umma::mbar_wait(&full[slot], phase);
+                            if (!ready) umma::mbar_wait(&full[slot], phase);
+                            {
+                                const uint32_t ns = step + 1u;
+                                ready = umma::mbar_test_wait(&full[ns % (uint32_t)kChainSlots], (ns / (uint32_t)kChainSlots) & 1u);
+                            }
                             if (st) {
                                 prog.dbg[2 * mstep + 1] = clock64();
                                 ++mstep;
@@ -314,8 +325,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) si
                     umma::tc_fence_before();
                     asm volatile("bar.sync 1, 256;" ::: "memory");
                     if (!half) {
-                        const float2 o = s_hand[m];
-                        *reinterpret_cast<float2*>(prog.logits + row * 2ull) = make_float2((l0 + o.x) + __ldg(prog.b2), (l1 + o.y) + __ldg(prog.b2 + 1));
+                        // logits -> max-subtracted softmax -> ML byte, written where the caller reads it: no per-site pass of its own
+                        const uint32_t site = __ldg(prog.out_idx + row);
+                        if (site != 0xffffffffu) {
+                            const float2 o = s_hand[m];
+                            const float v0 = (l0 + o.x) + __ldg(prog.b2), v1 = (l1 + o.y) + __ldg(prog.b2 + 1);
+                            *reinterpret_cast<float2*>(prog.logits + 2ull * site) = make_float2(v0, v1);
+                            prog.ml[site] = prob_to_ml(softmax_p1(v0, v1));
+                        }
                     }
                 } else {
                     const int mid = ((n >> 1) + 15) & ~15;

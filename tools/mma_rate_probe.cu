@@ -7,6 +7,8 @@
 //              (cta_group::1 only: in a pair the halves of N come from different CTAs)
 //   pattern 3: operand form 1 of round 2: one kind::f16 MMA (fp16, K = 16) + one kind::f8f6f4 MMA (e4m3, K = 32) per product
 //   pattern 4: the e4m3 K = 32 MMA alone          pattern 5: the fp16 K = 16 MMA alone
+//   pattern 6 / 7: pattern 1 with the accumulator alternating between two column ranges every round / every 8 rounds (does a switch
+//              of accumulator drain the pipe?)
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../hifimeth_b200/csrc -o mma_rate_probe mma_rate_probe.cu ; run on a B200:
 //   ./mma_rate_probe <pair 0|1> <N> <pattern> [reps]
 #include <cstdio>
@@ -68,6 +70,17 @@ __global__ void __launch_bounds__(128, 1) probe(int n, int pattern, int reps, un
                     mma(tmem, a0, b0, idesc);
                     mma(tmem, a1, b0, idesc);
                     mma(tmem, a0, b1, idesc);
+                } else if (pattern == 6) {  // the triple, accumulator alternating between two column ranges every round
+                    const uint32_t d = tmem + ((uint32_t)r & 1u) * 256u;
+                    mma(d, a0, b0, idesc);
+                    mma(d, a1, b0, idesc);
+                    mma(d, a0, b1, idesc);
+                } else if (pattern == 7) {  // the triple, accumulator switched every 8 rounds, first MMA after a switch overwrites
+                    const uint32_t d = tmem + (((uint32_t)r >> 3) & 1u) * 256u;
+                    if ((r & 7) == 0) { if (kPair) umma::mma2_bf16_w(d, a0, b0, desc_hi, idesc, 0); else umma::mma_bf16_w(d, a0, b0, desc_hi, idesc, 0); }
+                    else mma(d, a0, b0, idesc);
+                    mma(d, a1, b0, idesc);
+                    mma(d, a0, b1, idesc);
                 } else if (pattern == 2) {
                     mma(tmem, a0, b2_base + (uint32_t)(r & 3) * 2 * b_step, idesc2);
                     mma(tmem, a1, b0, idesc);
@@ -135,7 +148,7 @@ int main(int argc, char** argv)
     }
     unsigned long long h[256] = {};
     cudaMemcpy(h, d_cyc, grid * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-    const int per_round = pattern == 0 ? 1 : pattern == 1 ? 3 : (pattern == 2 || pattern == 3) ? 2 : 1;
+    const int per_round = pattern == 0 ? 1 : (pattern == 1 || pattern == 6 || pattern == 7) ? 3 : (pattern == 2 || pattern == 3) ? 2 : 1;
     const double macs_round = (double)(pair ? 256 : 128) * n * 16 * (pattern == 0 ? 1 : pattern == 4 ? 2 : pattern == 5 ? 1 : 3);
     const int issuers = pair ? grid / 2 : grid;
     printf("pair %d N %3d pattern %d: %8.1f cycles/round (%6.1f per MMA issued), %7.1f TFLOP/s chip-wide (%.3f ms)\n", pair, n, pattern,
