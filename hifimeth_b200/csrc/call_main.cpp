@@ -32,6 +32,7 @@
 
 #include <dlfcn.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include "../../include/hm_engine.h"
 #include "bgzf_bam.h"
@@ -287,7 +288,10 @@ struct Shared {
     std::chrono::steady_clock::time_point t_start = std::chrono::steady_clock::now();
     std::atomic<uint64_t> at_ready{0}, at_input_done{0}, at_last_collect{0}, at_destroyed{0};
     uint64_t since_start() const { return (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_start).count(); }
+    std::atomic<int> producers{0};  // GPU workers that may still hand batches to the writer
     explicit Shared(const Options& o, size_t depth) : opt(o), raw(depth), outbox(depth) { for (auto& v : n_sites) v = 0; }
+    // a worker has handed over its last batch (its engine is torn down AFTER this): the last one lets the writer finish
+    void producer_done() { if (--producers == 0) outbox.finish(); }
     void fail(const std::string& msg)
     {
         {
@@ -356,6 +360,12 @@ void reader_body(Shared& S, hm::BamReader& in)
 void gpu_worker_body(Shared& S, int device, int threads)
 {
     const Options& opt = S.opt;
+    struct Done {  // exactly one producer_done() per worker, whatever path leaves this function
+        Shared& S;
+        bool fired = false;
+        void fire() { if (!fired) { fired = true; S.producer_done(); } }
+        ~Done() { fire(); }
+    } done{S};
     Stopwatch sw;
     hm_config cfg{};
     cfg.model_dir = opt.model_dir.c_str();
@@ -470,6 +480,7 @@ void gpu_worker_body(Shared& S, int device, int threads)
     // drain, older batch first: slot `cur` was finished inside the loop unless it ended early, slot cur ^ 1 holds the newest
     for (int k = 0; k < 2 && ok && !S.failed; ++k)
         if (fl[cur ^ k].live) ok = finish(cur ^ k);
+    done.fire();  // the writer may close the output while this engine's pinned and device memory is being released
     hm_engine_destroy(eng);
     eng = nullptr;
     S.at_destroyed = S.since_start();
@@ -519,6 +530,9 @@ void writer_thread(Shared& S, hm::BamWriter& out)
 }  // namespace
 
 static int call_main_impl(int argc, char** argv);
+static std::atomic<bool> g_fast_exit{false};
+// The CLI executable: do not wait for the engines' teardown once the output is closed; the caller must leave with _exit().
+extern "C" void hm_call_fast_exit(int on) { g_fast_exit = on != 0; }
 
 // Nothing throws across the C boundary: an allocation failure or any other exception ends the run with EXIT_FAILURE (the calling
 // thread is guarded here, the reader / worker / writer threads by guarded() above, pool tasks by parallel_for itself).
@@ -564,19 +578,24 @@ static int call_main_impl(int argc, char** argv)
         opt.max_bases = std::min<long long>(24ll << 20, std::max<long long>(2ll << 20, est));
     }
     Shared S(opt, (size_t)2 * n_workers);
+    S.producers = n_workers;
     std::thread reader(reader_thread, std::ref(S), std::ref(in));
     std::vector<std::thread> workers;
     const int worker_threads = std::max(1, opt.threads / n_workers);
     for (int d : opt.devices) workers.emplace_back(gpu_worker, std::ref(S), d, worker_threads);
     std::thread writer(writer_thread, std::ref(S), std::ref(out));
     reader.join();
-    for (auto& w : workers) w.join();
-    S.outbox.finish();
-    writer.join();
+    writer.join();  // ends when the last worker has handed over its last batch and the writer has written it
     bool failed = S.failed;
     if (!failed && !out.close(err)) { S.err = opt.out_path + ": " + err; failed = true; }
-    if (failed) { fprintf(stderr, "[hifimeth-b200] %s\n", S.err.c_str()); return EXIT_FAILURE; }
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+    // The output is complete and closed here.  The workers are still releasing their engines (pinned host memory, ~25 GB of device
+    // maps, the CUDA context: 0.2 - 1.5 s per device, measured); the executable skips that wait and leaves through _exit
+    // (hm_call_fast_exit, main.cpp) -- the driver reclaims everything at process exit -- while in-process callers get a clean join.
+    const bool fast = g_fast_exit && !failed;
+    if (fast) for (auto& w : workers) w.detach();  // they still use S: this function does not return on that path (see the end)
+    else for (auto& w : workers) w.join();
+    if (failed) { fprintf(stderr, "[hifimeth-b200] %s\n", S.err.c_str()); return EXIT_FAILURE; }
     const uint64_t sites = S.n_sites[0] + S.n_sites[1] + S.n_sites[2];
     fprintf(stderr, "[hifimeth-b200] phases (s, summed per thread role): read+inflate %.2f, engine create %.2f, pack %.2f, submit %.2f, "
                     "collect(wait) %.2f, assemble %.2f, write+deflate %.2f; %llu batches of <= %lld bases on %d worker(s), %d host threads\n",
@@ -604,6 +623,10 @@ static int call_main_impl(int argc, char** argv)
         for (int b = 0; b < 256; ++b)
             fprintf(hf, "%d\t%llu\t%llu\t%llu\n", b, (unsigned long long)S.ml_hist[0][b], (unsigned long long)S.ml_hist[1][b], (unsigned long long)S.ml_hist[2][b]);
         fclose(hf);
+    }
+    if (fast) {
+        fflush(nullptr);
+        _exit(EXIT_SUCCESS);
     }
     return EXIT_SUCCESS;
 }

@@ -433,8 +433,13 @@ const char* hm_last_error(const hm_engine* e)
 void hm_engine_destroy(hm_engine* e)
 {
     if (!e) return;
+    const bool verbose = getenv("HM_VERBOSE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     cudaSetDevice(e->cfg.device);
     for (auto& s : e->slots) free_slot(s);
+    if (verbose)
+        fprintf(stderr, "[hm_engine_destroy] device %d: slots freed after %.3f s\n", e->cfg.device,
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
     for (int c = 0; c < 3; ++c) {
         Fp32Model& d = e->fp32[c];
         cudaFree(d.bn_scale); cudaFree(d.bn_shift);

@@ -63,7 +63,7 @@ class hm_timing(C.Structure):
 
 ABI_SYMBOLS = ["hm_engine_create", "hm_engine_destroy", "hm_last_error", "hm_version", "hm_batch_acquire", "hm_batch_submit",
                "hm_batch_collect", "hm_batch_timing", "hm_model_weights", "hm_codev1_encode", "hm_codev1_decode", "hm_pack_record", "hm_pack_records",
-               "hm_mod_record_bound", "hm_build_mod_record", "hm_build_mod_record_mm", "hm_parse_mod_record", "hm_ml_threshold", "hm_call_main", "hm_bam_copy", "hm_debug_dump_decode", "hm_debug_dump_ctx",
+               "hm_mod_record_bound", "hm_build_mod_record", "hm_build_mod_record_mm", "hm_parse_mod_record", "hm_ml_threshold", "hm_call_main", "hm_call_fast_exit", "hm_bam_copy", "hm_debug_dump_decode", "hm_debug_dump_ctx",
                "hm_debug_dump_features", "hm_debug_dump_logits", "hm_debug_dump_xmap", "hm_debug_dump_acts", "hm_debug_dense_op", "hm_debug_last_op_ms", "hm_microbench"]
 
 _lib = None

@@ -210,6 +210,9 @@ uint8_t hm_ml_threshold(const uint64_t bins[256], uint64_t* n_samples);
  * (src/app/hifimeth/mod_main.cpp:303-412, options src/app/hifimeth/mod_options.cpp:61-181).  argv[0] = program name,
  * argv[1] = "call".  Returns EXIT_SUCCESS / EXIT_FAILURE like the reference's main(). */
 int hm_call_main(int argc, char** argv);
+/* on != 0: hm_call_main returns as soon as the output is closed, with the GPU workers' engine teardown still running on detached
+ * threads -- for executables that leave through _exit() right after (hifimeth_b200/csrc/main.cpp).  Default: join. */
+void hm_call_fast_exit(int on);
 /* Reads every record of a BAM file and writes it unchanged (block-parallel BGZF inflate / deflate); returns the number of
  * records or a negative hm_status.  Test hook for the codec. */
 int hm_bam_copy(const char* in_path, const char* out_path, int threads, int level);
