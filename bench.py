@@ -506,7 +506,7 @@ def main():
                 "traffic": traffic, "traffic_unit": "DRAM bytes per step (read + write) of the kernel family", "hbm_frac": hbm_frac,
                 "hbm_peak_gbs": peak_gbs, "traffic_source": (tr[2] + f" ({tr[1]}-read step, scaled by reads; tools/traffic_from_ncu.py)") if tr else None,
                 "algorithmic_bytes": int(h2d + d2h),
-                "kernel": "dense_gemm2_kernel + dense_fused12_kernel + dense_gemm_kernel (every op of the dense plan)",
+                "kernel": "dense_gemm2_kernel + dense_fused12_kernel + site_chain_kernel + dense_gemm_kernel (every op of the dense plan)",
                 "plan_ms_per_step": top_ms / max(args.steps, 1), "plan_ms_is": "CUDA events around all launches of the family on their stream (includes "
                 "the ~1 % of small kernels between them)", "launches_per_step": top_launches // max(args.steps, 1), "peak_source": peak_src}
         line = {
