@@ -658,15 +658,16 @@ int tensor_model_build(TensorModelHandle& m, const CnnModel& host)
         std::vector<const HostOp*> order;
         auto add = [&](int out, bool head) {
             for (const HostOp& h : plan)
-                if (h.compact && h.conv1_taps == 0 && ((head && h.head) || (!head && !h.head && h.out == out))) { order.push_back(&h); return true; }
+                if (h.compact && ((head && h.head) || (!head && !h.head && h.out == out))) { order.push_back(&h); return true; }
             return false;
         };
         bool ok = true;
-        for (int l = 2; l <= 6 && ok; ++l) ok = add(MAP_F + l - 1, false) && add(MAP_G + l - 1, false);
+        // F1 / G1 (conv1 form, gathered from the X map) open the chain: their outputs never leave the chip either
+        for (int l = 1; l <= 6 && ok; ++l) ok = add(MAP_F + l - 1, false) && add(MAP_G + l - 1, false);
         for (int v : {1, 0, 3, 2}) ok = ok && add(MAP_T7 + v, false);
         ok = ok && add(MAP_T8 + 0, false) && add(MAP_T8 + 1, false) && add(-1, true);
         size_t n_compact = 0;
-        for (const HostOp& h : plan) n_compact += (h.compact && h.conv1_taps == 0) ? 1 : 0;
+        for (const HostOp& h : plan) n_compact += h.compact ? 1 : 0;
         ok = ok && order.size() == n_compact && order.size() <= (size_t)kChainMaxOps;
         std::vector<TensorModel::ChainItem> items;
         auto index_of = [&](int out_map) {
@@ -682,22 +683,28 @@ int tensor_model_build(TensorModelHandle& m, const CnnModel& host)
             hw.head = false;
             hw.scatter.clear();
             std::vector<uint8_t> tmp;
-            if (h.cin % 32 || h.cout % 32 || !lower_op(hw, 0, h.cout, it.d, tmp, err, true)) { ok = false; break; }
+            const bool c1 = h.conv1_taps > 0;
+            if (c1) hw.terms[0].gather = false;  // the pair lowering only has to pack the weights
+            if ((!c1 && h.cin % 32) || h.cout % 32 || !lower_op(hw, 0, h.cout, it.d, tmp, err, true, c1)) { ok = false; break; }
             // ---- chain image: per rank [stage pair][term][stage][hl] tiles, so that a ring step is one contiguous block -------------
-            const uint32_t n_terms = (uint32_t)h.terms.size(), tile = (uint32_t)h.cout * 16u, rank_bytes = it.d.p.w_bytes;
-            if (rank_bytes != (uint32_t)(h.cin / 16) * n_terms * 2u * tile) { ok = false; break; }
+            // conv1 form: a "stage" is a K-step of two taps; their number is padded to an even one with zero tiles
+            const uint32_t n_terms = (uint32_t)h.terms.size(), tile = (uint32_t)h.cout * 16u, src_rank_bytes = it.d.p.w_bytes;
+            const uint32_t n_st = c1 ? (uint32_t)it.d.p.ksteps : (uint32_t)h.cin / 16, n_st_pad = (n_st + 1u) & ~1u;
+            const uint32_t rank_bytes = n_st_pad * n_terms * 2u * tile;
+            if (src_rank_bytes != n_st * n_terms * 2u * tile || (c1 && n_terms != 1)) { ok = false; break; }
             {
                 size_t o = (blob.size() + 255) & ~(size_t)255;
-                blob.resize(o + 2 * (size_t)rank_bytes);
-                const uint8_t* src = tmp.data() + it.d.w_off;  // where lower_op put the [stage][term][hl] image of rank 0
+                blob.resize(o + 2 * (size_t)rank_bytes, 0);
+                const size_t src_off = it.d.w_off;  // where lower_op put the [stage][term][hl] image of rank 0
                 it.d.w_off = o;
                 uint8_t* dst = blob.data() + o;
                 for (uint32_t r = 0; r < 2; ++r)
-                    for (uint32_t S = 0; S < (uint32_t)h.cin / 32; ++S)
+                    for (uint32_t S = 0; S < n_st_pad / 2; ++S)
                         for (uint32_t k = 0; k < n_terms; ++k)
                             for (uint32_t st = 0; st < 2; ++st)
                                 for (uint32_t hl = 0; hl < 2; ++hl) {
-                                    memcpy(dst, src + (size_t)r * rank_bytes + ((size_t)((2 * S + st) * n_terms + k) * 2 + hl) * tile, tile);
+                                    if (2 * S + st < n_st)
+                                        memcpy(dst, tmp.data() + src_off + (size_t)r * src_rank_bytes + ((size_t)((2 * S + st) * n_terms + k) * 2 + hl) * tile, tile);
                                     dst += tile;
                                 }
                 o = (blob.size() + 255) & ~(size_t)255;
@@ -705,9 +712,12 @@ int tensor_model_build(TensorModelHandle& m, const CnnModel& host)
                 memcpy(blob.data() + o, h.bias.data(), (size_t)h.cout * 4);
                 it.d.bias_off = o;
             }
-            steps += (size_t)(h.cin / 32) * n_terms;
+            const int cin_eff = (int)(16u * n_st_pad);  // conv1 form: 8 features x padded taps
+            steps += (size_t)(cin_eff / 32) * n_terms;
             ChainOp& c = it.c;
-            c.n = h.cout; c.cin = h.cin; c.n_terms = (int)n_terms; c.head = h.head ? 1 : 0;
+            c.n = h.cout; c.cin = cin_eff; c.n_terms = (int)n_terms; c.head = h.head ? 1 : 0;
+            c.gather = c1 ? 1 : 0;
+            c.gather_shift = c1 ? h.terms[0].shift : 0;
             c.w_rank_bytes = rank_bytes;
             c.wait_op = (int)i;
             for (int q = 0; q < kChainMaxWait; ++q) c.mma_wait[q] = -1;
@@ -742,10 +752,11 @@ int tensor_model_build(TensorModelHandle& m, const CnnModel& host)
                 return true;
             };
             for (size_t k = 0; k < h.terms.size() && ok; ++k) {
-                if (h.terms[k].shift != 0 || h.terms[k].gather) { ok = false; break; }
                 it.term_map[k] = h.terms[k].src;
+                if (c1) { ok = h.terms[k].src == MAP_X && h.terms[k].gather; continue; }  // gathered from the batch-wide X map
+                if (h.terms[k].shift != 0 || h.terms[k].gather) { ok = false; break; }
                 const int sm = h.terms[k].src;
-                const bool streamed_kind = sm >= MAP_S || sm == MAP_F || sm == MAP_G;  // scatter copies, F1, G1
+                const bool streamed_kind = sm >= MAP_S;  // scatter copies of the dense maps
                 const int dep = index_of(sm);
                 it.resident[k] = dep >= 0;
                 if ((dep < 0) != streamed_kind || (h.head && streamed_kind)) { ok = false; break; }
@@ -990,8 +1001,13 @@ int launch_chain(const TensorModel& tm, TensorWorkspaceImpl& s, uint32_t n_tiles
     p.logits = logits;
     p.ml = ml;
     p.out_idx = s.d_out_idx;
+    p.site_rows = s.d_site_rows;
+    p.x_lo_off = s.xg_stride;
     // an odd tile count: the peer CTA of the last pair works on one tile of padding rows
-    if (n_tiles & 1u) cudaMemsetAsync(s.d_out_idx + (size_t)n_tiles * kTileRows, 0xff, kTileRows * sizeof(uint32_t), stream);
+    if (n_tiles & 1u) {
+        cudaMemsetAsync(s.d_out_idx + (size_t)n_tiles * kTileRows, 0xff, kTileRows * sizeof(uint32_t), stream);
+        cudaMemsetAsync(s.d_site_rows + (size_t)n_tiles * kTileRows, 0, kTileRows * sizeof(uint32_t), stream);  // they gather X row 0
+    }
     // HM_CHAIN_STAMPS=1: pair 0 stamps the third tile round of every launch; the last launch's stamps are printed after the batch
     static const bool stamps = getenv("HM_CHAIN_STAMPS") != nullptr;
     if (stamps) {
@@ -1002,7 +1018,8 @@ int launch_chain(const TensorModel& tm, TensorWorkspaceImpl& s, uint32_t n_tiles
     for (int i = 0; i < p.n_ops; ++i) {
         const TensorModel::ChainItem& it = tm.chain_ops[i];
         p.op[i] = it.c;
-        for (int k = 0; k < it.c.n_terms; ++k) p.op[i].term[k].src = it.resident[k] ? nullptr : s.map[it.term_map[k]];
+        for (int k = 0; k < it.c.n_terms; ++k)
+            p.op[i].term[k].src = it.resident[k] ? nullptr : it.c.gather ? s.d_xg : s.map[it.term_map[k]];
         p.op[i].spill = (spill && !it.c.head) ? s.map[it.out_map] : nullptr;
         s.macs += (double)((n_tiles + 1) / 2 * 2) * kTileRows * it.d.macs_per_row;
     }
@@ -1188,7 +1205,7 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
                     int op_i = 0;
                     const bool chain = tm.chain && !s->no_chain;
                     for (const DevOp& d : tm.ops) {
-                        if (d.compact && (!chain || d.conv1)) {  // with the chain kernel only F1 / G1 (conv1 form) are launches of their own
+                        if (d.compact && !chain) {  // the chain kernel runs every compact op, F1 / G1 included
                             stamp(c * 64 + op_i);
                             launch_op(d, *s, n_tiles, s->d_clogit, sm_count, stream);
                             ++dense_launches;

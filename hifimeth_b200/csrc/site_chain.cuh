@@ -65,6 +65,9 @@ struct ChainOp {
     int32_t n, cin, n_terms;
     int32_t head;           // 1: fc1 + ReLU -> fc2 -> logits instead of a packed map
     int32_t wait_op;        // the epilogue waits for the MMAs of THIS op (>= own index)
+    int32_t gather;         // 1: conv1 form (F1, G1): term 0 is gathered from the X map -- a ring step holds 4 TAPS (= 2 K-steps of two
+                            // 8-feature taps) of the 128 sites' windows, rows site_rows[site] + gather_shift + tap; cin = 8 * padded taps
+    int32_t gather_shift;
     int32_t mma_wait[kChainMaxWait];  // the first MMA waits for the epilogues of these ops; -1 = unused
 };
 
@@ -75,6 +78,8 @@ struct ChainProgram {
     unsigned long long plane_stride;   // of every compact map (streamed sources and spill targets)
     const float* w2;                   // head: [2][256], [2]
     const float* b2;
+    const uint32_t* site_rows;         // [rows] compact row -> row of the batch-wide X map (gathered conv1-form ops)
+    unsigned long long x_lo_off;       // byte distance from the X map's hi plane to its lo plane
     const uint32_t* out_idx;           // [rows] compact row -> index of the site in hm_call_batch order; 0xffffffff = padding row
     float* logits;                     // [sites][2] in hm_call_batch order
     uint8_t* ml;                       // [sites] the quantised ML byte (s_logits_to_methy_probs, src/app/hifimeth/mod_batch.cpp:46-64)
@@ -116,7 +121,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) si
     if (warp == 0) {
         if (lane == 0) {
             for (int i = 0; i < kChainSlots; ++i) {
-                umma::mbar_init(&full[i], rank == 0 ? 2u : 1u);
+                umma::mbar_init(&full[i], (rank == 0 ? 2u : 1u) + 32u);  // + one cp.async-tracking arrival per producer lane
                 umma::mbar_init(&empty[i], 1);
             }
             for (int i = 0; i < kChainMaxOps; ++i) {
@@ -188,14 +193,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) si
                 umma::mbar_wait(&empty[slot], phase ^ 1u);
             }
             uint8_t* dst = s_ring + (size_t)slot * kChainSlotBytes;
-            if (lane == 0) umma::mbar_arrive_expect_tx(&full[slot], (src ? kChainSlabBytes : 0u) + w_bytes);
+            if (lane == 0) umma::mbar_arrive_expect_tx(&full[slot], ((src && !op.gather) ? kChainSlabBytes : 0u) + w_bytes);
             __syncwarp();
-            if (lane < 8u) {
+            if (op.gather) {
+                // conv1 form: planes {hi, lo} x {tap 4 S .. 4 S + 3}, every row fetched with its own 16-byte copy (the four taps of a
+                // site are 64 consecutive bytes of the X map)
+                #pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t r = lane + 32u * (uint32_t)q;
+                    const unsigned long long xr = (unsigned long long)__ldg(prog.site_rows + row0 + r) + (unsigned long long)(op.gather_shift + (int)(4u * S));
+                    #pragma unroll
+                    for (uint32_t pl = 0; pl < 8u; ++pl)
+                        umma::cp_async16(dst + kChainWBytes + pl * kChainPlaneBytes + r * 16u,
+                                         src + (pl >> 2) * prog.x_lo_off + (xr + (pl & 3u)) * 16ull);
+                }
+            } else if (lane < 8u) {
                 if (src) {  // planes {hi, lo} x {g = 4 S .. 4 S + 3}
                     const uint8_t* plane = src + (unsigned long long)((lane >> 2) * groups + 4u * S + (lane & 3u)) * prog.plane_stride;
                     umma::bulk_g2s(dst + kChainWBytes + lane * kChainPlaneBytes, plane + row0 * 16ull, kChainPlaneBytes, &full[slot]);
                 }
-            } else if (lane < 12u) {  // the weight tiles in four pieces
+            }
+            umma::cp_async_mbar_arrive_noinc(&full[slot]);  // every lane, every step: the barrier counts 32 of these
+            if (lane >= 8u && lane < 12u) {  // the weight tiles in four pieces
                 const uint32_t per = w_bytes >> 2, piece = lane - 8u;
                 umma::bulk_g2s(dst + piece * per, w_src + piece * per, per, &full[slot]);
             }
