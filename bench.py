@@ -269,7 +269,7 @@ def queue_bench(n_gpus: int, reads_per_gpu: int, read_len: int = 20000, level: i
                 out["steady_sites_per_s"] = sites / (collected - ready)
             # the phase that ends last names the limiter
             # (the executable leaves through _exit without waiting for the engines' teardown: `destroyed` is then 0)
-            lim = "reader (BGZF inflate + framing)" if inflated >= collected - 0.05 else \
+            lim = "reader (BGZF inflate + framing)" if inflated >= collected - max(0.05, 0.1 * (collected - ready)) else \
                   "writer (record assembly hand-over + BGZF deflate)" if closed - max(destroyed, collected) > 0.25 * wall else \
                   "engine creation (CUDA context + pinned / device allocation)" if ready > 0.5 * wall else "GPU workers"
             out["limiter"] = lim

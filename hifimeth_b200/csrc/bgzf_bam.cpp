@@ -139,20 +139,35 @@ void parallel_for(size_t n, int threads, const std::function<void(size_t)>& fn)
 }
 
 // ---- BgzfReader ----------------------------------------------------------------------------------------------------------
+namespace {
+constexpr size_t kRawAhead = 2;     // compressed slabs queued between the I/O thread and the drivers
+constexpr int kInflateDrivers = 2;  // slabs being inflated at the same time
+
+// One inflate stream per thread for the life of the thread: inflateInit2 / inflateEnd per 64 KiB block was an allocation and a
+// reset of the stream state for every block.
+struct TlInflate {
+    z_stream zs{};
+    bool init = false;
+    ~TlInflate() { if (init) inflateEnd(&zs); }
+};
+}  // namespace
+
 BgzfReader::~BgzfReader() { close(); }
 void BgzfReader::close()
 {
-    if (worker_.joinable()) {
-        {
-            std::lock_guard<std::mutex> lk(m_);
-            stop_ = true;
-            cv_.notify_all();
-        }
-        worker_.join();
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        stop_ = true;
+        cv_.notify_all();
     }
+    if (io_.joinable()) io_.join();
+    for (auto& d : drivers_)
+        if (d.joinable()) d.join();
+    drivers_.clear();
     if (f_) fclose(f_);
     f_ = nullptr;
-    ready_.clear();
+    raw_q_.clear();
+    done_.clear();
 }
 
 bool BgzfReader::open(const char* path, int threads, std::string& err)
@@ -163,116 +178,174 @@ bool BgzfReader::open(const char* path, int threads, std::string& err)
     threads_ = std::max(threads, 1);
     slab_bytes_ = kReadSlab;
     if (const char* e = getenv("HM_BGZF_SLAB")) slab_bytes_ = std::max<size_t>(1024, (size_t)atoll(e));  // tests: force records to straddle slabs
-    raw_.clear();
-    eof_ = done_ = stop_ = false;
-    worker_err_.clear();
-    worker_ = std::thread(&BgzfReader::run, this);
+    carry_.clear();
+    eof_ = io_done_ = stop_ = false;
+    next_seq_ = n_slabs_ = 0;
+    err_.clear();
+    io_ = std::thread(&BgzfReader::io_loop, this);
+    for (int k = 0; k < kInflateDrivers; ++k) drivers_.emplace_back(&BgzfReader::driver_loop, this);
     return true;
 }
 
-void BgzfReader::run()
+void BgzfReader::fail(const std::string& err)
+{
+    std::lock_guard<std::mutex> lk(m_);
+    if (err_.empty()) err_ = err.empty() ? std::string("BGZF reader: unknown error") : err;
+    stop_ = true;
+    cv_.notify_all();
+}
+
+// Reads until the buffer holds at least one complete block, then cuts it at the last block boundary (the tail is carried over).
+bool BgzfReader::read_raw(RawSlab& rs, std::string& err)
 {
     for (;;) {
-        std::shared_ptr<Slab> slab;
-        std::string err;
-        bool more = false;
-        try {  // an allocation failure ends the stream with an error instead of terminating the process
-            slab = std::make_shared<Slab>();
-            more = inflate_more(slab->data, err);
-        } catch (const std::exception& e) {
-            err = std::string("BGZF reader: ") + e.what();
-        } catch (...) {
-            err = "BGZF reader: unknown exception";
+        rs.blks.clear();
+        rs.total = 0;
+        size_t off = 0;
+        Bytes& buf = carry_;
+        while (off < buf.size()) {
+            bool bad;
+            const size_t bs = bgzf_block_size(buf.data() + off, buf.size() - off, bad);
+            if (bad) { err = "not a BGZF block (is the input a BAM file?)"; return false; }
+            if (!bs || off + bs > buf.size()) break;
+            // header (12) + extra field + at least the empty deflate stream (2) + CRC32 / ISIZE (8): XLEN comes from the file, and a
+            // block shorter than that would make the inflate length below wrap around
+            if (bs < 12 + (size_t)rd16(buf.data() + off + 10) + 2 + 8) { err = "corrupt BGZF block (BSIZE smaller than its own header and trailer)"; return false; }
+            const size_t isize = rd32(buf.data() + off + bs - 4);
+            if (isize > 65536) { err = "corrupt BGZF block (ISIZE above 64 KiB)"; return false; }  // BGZF payloads are <= 64 KiB
+            rs.blks.push_back({off, bs, isize, rs.total});
+            rs.total += isize;
+            off += bs;
         }
-        std::unique_lock<std::mutex> lk(m_);
-        if (!more) {
-            worker_err_ = err;
-            done_ = true;
+        if (!rs.blks.empty()) {
+            Bytes tail(buf.begin() + off, buf.end());  // < one block
+            buf.resize(off);
+            rs.raw.swap(buf);
+            carry_.swap(tail);
+            if (rs.total) return true;
+            continue;  // only empty blocks (EOF markers): look for more
+        }
+        if (eof_) {
+            if (!buf.empty()) err = "truncated BGZF block at end of file";
+            return false;
+        }
+        const size_t have = buf.size();
+        buf.resize(have + slab_bytes_);
+        const size_t got = fread(buf.data() + have, 1, slab_bytes_, f_);
+        buf.resize(have + got);
+        if (got < slab_bytes_) eof_ = true;
+    }
+}
+
+void BgzfReader::io_loop()
+{
+    uint64_t seq = 0;
+    try {  // an allocation failure ends the stream with an error instead of terminating the process
+        for (;;) {
+            RawSlab rs;
+            std::string err;
+            if (!read_raw(rs, err)) {
+                if (!err.empty()) { fail(err); return; }
+                break;
+            }
+            rs.seq = seq++;
+            std::unique_lock<std::mutex> lk(m_);
+            cv_.wait(lk, [&] { return raw_q_.size() < kRawAhead || stop_; });
+            if (stop_) return;
+            raw_q_.push_back(std::move(rs));
             cv_.notify_all();
-            return;
         }
-        cv_.wait(lk, [&] { return ready_.size() < kReadAhead || stop_; });
-        if (stop_) return;
-        ready_.push_back(std::move(slab));
-        cv_.notify_all();
+    } catch (const std::exception& e) {
+        fail(std::string("BGZF reader: ") + e.what());
+        return;
+    } catch (...) {
+        fail("BGZF reader: unknown exception");
+        return;
+    }
+    std::lock_guard<std::mutex> lk(m_);
+    n_slabs_ = seq;
+    io_done_ = true;
+    cv_.notify_all();
+}
+
+void BgzfReader::driver_loop()
+{
+    try {
+        for (;;) {
+            RawSlab rs;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                // take the next compressed slab, but do not run more than kReadAhead slabs ahead of the consumer
+                cv_.wait(lk, [&] { return stop_ || (!raw_q_.empty() && raw_q_.front().seq < next_seq_ + kReadAhead) || (raw_q_.empty() && io_done_); });
+                if (stop_ || raw_q_.empty()) return;
+                rs = std::move(raw_q_.front());
+                raw_q_.pop_front();
+                cv_.notify_all();
+            }
+            auto slab = std::make_shared<Slab>();
+            slab->data.resize(rs.total);
+            std::atomic<bool> ok{true};
+            uint8_t* out = slab->data.data();
+            parallel_for(rs.blks.size(), threads_, [&](size_t i) {
+                const Blk& b = rs.blks[i];
+                if (!b.isize) return;
+                static thread_local TlInflate tl;
+                if (!tl.init) {
+                    if (inflateInit2(&tl.zs, -15) != Z_OK) { ok = false; return; }
+                    tl.init = true;
+                } else if (inflateReset(&tl.zs) != Z_OK) { ok = false; return; }
+                const uint8_t* p = rs.raw.data() + b.off;
+                const size_t xlen = rd16(p + 10);
+                z_stream& zs = tl.zs;
+                zs.next_in = const_cast<Bytef*>(p + 12 + xlen);
+                zs.avail_in = (uInt)(b.size - 12 - xlen - 8);
+                zs.next_out = out + b.dst;
+                zs.avail_out = (uInt)b.isize;
+                const int rc = inflate(&zs, Z_FINISH);
+                if (rc != Z_STREAM_END || zs.total_out != b.isize ||
+                    crc32(crc32(0L, Z_NULL, 0), out + b.dst, (uInt)b.isize) != rd32(p + b.size - 8))
+                    ok = false;
+            });
+            if (!ok) { fail("BGZF block failed to inflate or its CRC does not match"); return; }
+            std::lock_guard<std::mutex> lk(m_);
+            done_.emplace_back(rs.seq, std::move(slab));
+            cv_.notify_all();
+        }
+    } catch (const std::exception& e) {
+        fail(std::string("BGZF reader: ") + e.what());
+    } catch (...) {
+        fail("BGZF reader: unknown exception");
     }
 }
 
 std::shared_ptr<Slab> BgzfReader::next_slab(std::string& err)
 {
     std::unique_lock<std::mutex> lk(m_);
-    cv_.wait(lk, [&] { return !ready_.empty() || done_; });
-    if (ready_.empty()) {
-        err = worker_err_;
-        return nullptr;
-    }
-    std::shared_ptr<Slab> s = std::move(ready_.front());
-    ready_.pop_front();
-    cv_.notify_all();
-    return s;
-}
-
-// Appends the inflated payload of the next group of complete blocks to `out`; false at end of file or on error (err set).
-bool BgzfReader::inflate_more(std::vector<uint8_t>& out, std::string& err)
-{
     for (;;) {
-        // complete blocks currently buffered
-        struct Blk { size_t off, size, isize, dst; };
-        std::vector<Blk> blks;
-        size_t off = 0, total = 0;
-        while (off < raw_.size()) {
-            bool bad;
-            const size_t bs = bgzf_block_size(raw_.data() + off, raw_.size() - off, bad);
-            if (bad) { err = "not a BGZF block (is the input a BAM file?)"; return false; }
-            if (!bs || off + bs > raw_.size()) break;
-            // header (12) + extra field + at least the empty deflate stream (2) + CRC32 / ISIZE (8): XLEN comes from the file, and a
-            // block shorter than that would make the inflate length below wrap around
-            if (bs < 12 + (size_t)rd16(raw_.data() + off + 10) + 2 + 8) { err = "corrupt BGZF block (BSIZE smaller than its own header and trailer)"; return false; }
-            const size_t isize = rd32(raw_.data() + off + bs - 4);
-            if (isize > 65536) { err = "corrupt BGZF block (ISIZE above 64 KiB)"; return false; }  // BGZF payloads are <= 64 KiB
-            blks.push_back({off, bs, isize, total});
-            total += isize;
-            off += bs;
+        for (auto it = done_.begin(); it != done_.end(); ++it) {
+            if (it->first != next_seq_) continue;
+            std::shared_ptr<Slab> s = std::move(it->second);
+            done_.erase(it);
+            ++next_seq_;
+            cv_.notify_all();
+            return s;
         }
-        if (!blks.empty()) {
-            const size_t base = out.size();
-            out.resize(base + total);
-            std::atomic<bool> ok{true};
-            parallel_for(blks.size(), threads_, [&](size_t i) {
-                const Blk& b = blks[i];
-                if (!b.isize) return;
-                const uint8_t* p = raw_.data() + b.off;
-                const size_t xlen = rd16(p + 10);
-                z_stream zs{};
-                if (inflateInit2(&zs, -15) != Z_OK) { ok = false; return; }
-                zs.next_in = const_cast<Bytef*>(p + 12 + xlen);
-                zs.avail_in = (uInt)(b.size - 12 - xlen - 8);
-                zs.next_out = out.data() + base + b.dst;
-                zs.avail_out = (uInt)b.isize;
-                const int rc = inflate(&zs, Z_FINISH);
-                inflateEnd(&zs);
-                if (rc != Z_STREAM_END || zs.total_out != b.isize ||
-                    crc32(crc32(0L, Z_NULL, 0), out.data() + base + b.dst, (uInt)b.isize) != rd32(p + b.size - 8))
-                    ok = false;
-            });
-            if (!ok) { err = "BGZF block failed to inflate or its CRC does not match"; return false; }
-            raw_.erase(raw_.begin(), raw_.begin() + off);
-            if (total) return true;
-            continue;  // only empty blocks (EOF markers): look for more
-        }
-        if (eof_) {
-            if (!raw_.empty()) { err = "truncated BGZF block at end of file"; return false; }
-            return false;
-        }
-        const size_t have = raw_.size();
-        raw_.resize(have + slab_bytes_);
-        const size_t got = fread(raw_.data() + have, 1, slab_bytes_, f_);
-        raw_.resize(have + got);
-        if (got < slab_bytes_) eof_ = true;
+        if (!err_.empty()) { err = err_; return nullptr; }
+        if (stop_ || (io_done_ && next_seq_ == n_slabs_)) return nullptr;
+        cv_.wait(lk);
     }
 }
 
 // ---- BgzfWriter ----------------------------------------------------------------------------------------------------------
+namespace {
+struct TlDeflate {
+    z_stream zs{};
+    bool init = false;
+    int level = -2;
+    ~TlDeflate() { if (init) deflateEnd(&zs); }
+};
+}  // namespace
+
 BgzfWriter::~BgzfWriter()
 {
     if (f_) fclose(f_);
@@ -301,22 +374,30 @@ bool BgzfWriter::flush(bool all, std::string& err)
     size_t nblk = pending_.size() / kBlockPayload;
     if (all && pending_.size() % kBlockPayload) ++nblk;
     if (!nblk) return true;
-    std::vector<std::vector<uint8_t>> comp(nblk);
+    std::vector<Bytes> comp(nblk);
     std::atomic<bool> ok{true};
     parallel_for(nblk, threads_, [&](size_t i) {
         const size_t off = i * kBlockPayload;
         const size_t len = std::min(kBlockPayload, pending_.size() - off);
-        std::vector<uint8_t>& c = comp[i];
+        Bytes& c = comp[i];
         c.resize(18 + compressBound((uLong)len) + 8);
-        z_stream zs{};
-        if (deflateInit2(&zs, level_, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { ok = false; return; }
+        // one deflate stream per thread and level for the life of the thread: deflateInit2 allocates and clears ~260 KB per call
+        static thread_local TlDeflate tl;
+        if (!tl.init || tl.level != level_) {
+            if (tl.init) deflateEnd(&tl.zs);
+            tl.zs = z_stream{};
+            tl.init = false;
+            if (deflateInit2(&tl.zs, level_, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { ok = false; return; }
+            tl.init = true;
+            tl.level = level_;
+        } else if (deflateReset(&tl.zs) != Z_OK) { ok = false; return; }
+        z_stream& zs = tl.zs;
         zs.next_in = const_cast<Bytef*>(pending_.data() + off);
         zs.avail_in = (uInt)len;
         zs.next_out = c.data() + 18;
         zs.avail_out = (uInt)(c.size() - 18 - 8);
         const int rc = deflate(&zs, Z_FINISH);
         const size_t clen = zs.total_out;
-        deflateEnd(&zs);
         if (rc != Z_STREAM_END || 18 + clen + 8 > 65536) { ok = false; return; }
         static const uint8_t hdr[12] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0};
         memcpy(c.data(), hdr, 12);

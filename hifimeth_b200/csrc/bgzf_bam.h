@@ -15,6 +15,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 namespace hm {
@@ -22,15 +23,33 @@ namespace hm {
 // Runs fn(i) for i in [0, n) on up to `threads` threads (inline when n or threads is small).
 void parallel_for(size_t n, int threads, const std::function<void(size_t)>& fn);
 
+// Byte buffers that are resized and then overwritten completely (inflated slabs, compressed input, assembled output): a plain
+// std::vector zero-fills on resize, which at 16 - 150 MB per buffer was a serial pass of its own in the reader and worker threads.
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+    template <class U> struct rebind { using other = NoInitAlloc<U>; };
+    NoInitAlloc() = default;
+    template <class U> NoInitAlloc(const NoInitAlloc<U>&) {}
+    template <class U, class... A> void construct(U* p, A&&... a)
+    {
+        if constexpr (sizeof...(A) == 0) ::new (static_cast<void*>(p)) U;  // default-initialised: no fill
+        else ::new (static_cast<void*>(p)) U(std::forward<A>(a)...);
+    }
+};
+using Bytes = std::vector<uint8_t, NoInitAlloc<uint8_t>>;
+
 // One inflated stretch of the input.  Record bodies handed out by BamReader point into `data`, or -- for a record that
 // straddles two slabs -- into one of the `extra` buffers of the slab it ends in; both stay valid while the slab is alive.
 struct Slab {
-    std::vector<uint8_t> data;
+    Bytes data;
     std::deque<std::vector<uint8_t>> extra;
 };
 
-// Sequential BGZF inflater with read-ahead: a background thread reads compressed slabs, inflates their blocks on `threads`
-// threads and queues the results, so that inflation overlaps whatever the consumer does with the previous slab.
+// Sequential BGZF inflater with read-ahead, three stages deep: an I/O thread reads compressed slabs and cuts them at block
+// boundaries; two driver threads inflate a slab each (its blocks spread over the shared thread pool, one z_stream per pool thread
+// re-used with inflateReset); the consumer takes the inflated slabs in file order.  Reading, the serial parts of one slab and the
+// inflation of the next overlap -- one thread doing all three in turn delivered 1.6 GB/s of inflated bytes on 32 cores, enough
+// for two B200s, not for four.
 class BgzfReader {
 public:
     ~BgzfReader();
@@ -40,19 +59,31 @@ public:
     void close();
 
 private:
-    void run();
-    bool inflate_more(std::vector<uint8_t>& out, std::string& err);
+    struct Blk { size_t off, size, isize, dst; };
+    struct RawSlab {
+        Bytes raw;                 // whole BGZF blocks
+        std::vector<Blk> blks;
+        size_t total = 0;          // inflated bytes
+        uint64_t seq = 0;
+    };
+    void io_loop();
+    void driver_loop();
+    bool read_raw(RawSlab& rs, std::string& err);   // false at end of file or on error (err set)
+    void fail(const std::string& err);
     FILE* f_ = nullptr;
     int threads_ = 1;
     size_t slab_bytes_ = 0;     // compressed bytes read per slab
-    std::vector<uint8_t> raw_;  // compressed bytes not yet consumed
+    Bytes carry_;               // tail of the last read: an incomplete block
     bool eof_ = false;
-    std::thread worker_;
+    std::thread io_;
+    std::vector<std::thread> drivers_;
     std::mutex m_;
     std::condition_variable cv_;
-    std::deque<std::shared_ptr<Slab>> ready_;
-    bool done_ = false, stop_ = false;
-    std::string worker_err_;
+    std::deque<RawSlab> raw_q_;                              // I/O thread -> drivers
+    std::deque<std::pair<uint64_t, std::shared_ptr<Slab>>> done_;  // drivers -> consumer (any order, few entries)
+    uint64_t next_seq_ = 0, n_slabs_ = 0;                   // next slab the consumer takes; slabs the file holds (valid once io_done_)
+    bool io_done_ = false, stop_ = false;
+    std::string err_;
 };
 
 class BgzfWriter {
@@ -66,7 +97,7 @@ private:
     bool flush(bool all, std::string& err);
     FILE* f_ = nullptr;
     int threads_ = 1, level_ = 6;
-    std::vector<uint8_t> pending_;
+    Bytes pending_;
 };
 
 struct BamHeader {

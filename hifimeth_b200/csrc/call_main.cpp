@@ -167,7 +167,7 @@ struct RawBatch {
 // The records of one batch after the engine: assembled output bodies, ready to be written in order.
 struct OutBatch {
     uint64_t seq = 0;
-    std::vector<uint8_t> obuf;
+    hm::Bytes obuf;  // overwritten completely: no zero fill (bgzf_bam.h)
     std::vector<size_t> ooff, olen;
 };
 
