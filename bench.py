@@ -361,7 +361,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch.jit GPU library baseline")
     ap.add_argument("--no-queue", action="store_true", help="skip the one-process host-work-queue run (hifimeth-b200 call)")
-    ap.add_argument("--queue-reads", type=int, default=int(os.environ.get("HM_QUEUE_READS", "12000")), help="20 kb reads per GPU in the queue run")
+    ap.add_argument("--queue-reads", type=int, default=int(os.environ.get("HM_QUEUE_READS", "24000")), help="20 kb reads per GPU in the queue run")
     ap.add_argument("--queue-level", type=int, default=6, help="BGZF level of the queue run's output (htslib's default is 6)")
     ap.add_argument("--cnn-mode", type=int, default=int(os.environ.get("HM_CNN_MODE", "0")))
     args = ap.parse_args()

@@ -348,6 +348,13 @@ struct TlDeflate {
 
 BgzfWriter::~BgzfWriter()
 {
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        end_ = true;
+        q_.clear();
+        cv_.notify_all();
+    }
+    if (bg_.joinable()) bg_.join();
     if (f_) fclose(f_);
 }
 
@@ -358,41 +365,102 @@ bool BgzfWriter::open(const char* path, int threads, int level, std::string& err
     threads_ = std::max(threads, 1);
     level_ = level;
     pending_.clear();
+    q_.clear();
+    bg_err_.clear();
+    end_ = false;
+    bg_ = std::thread(&BgzfWriter::bg_loop, this);
     return true;
 }
 
+// The caller only appends; whole chunks of kWriteBatch blocks go to a background thread that deflates them (blocks spread over the
+// shared pool) and writes them out, so that record assembly, the copy into `pending_`, deflate and the file write overlap.  With
+// deflate in the caller the one writer thread was busy 2.3 of 2.5 s of a 4-GPU run and set its pace.
 bool BgzfWriter::write(const void* data, size_t n, std::string& err)
 {
     const uint8_t* p = static_cast<const uint8_t*>(data);
     pending_.insert(pending_.end(), p, p + n);
-    if (pending_.size() >= kWriteBatch * kBlockPayload) return flush(false, err);
+    if (pending_.size() >= kWriteBatch * kBlockPayload) return hand_over(false, err);
     return true;
 }
 
-bool BgzfWriter::flush(bool all, std::string& err)
+bool BgzfWriter::hand_over(bool all, std::string& err)
 {
-    size_t nblk = pending_.size() / kBlockPayload;
-    if (all && pending_.size() % kBlockPayload) ++nblk;
+    const size_t nblk = pending_.size() / kBlockPayload;
+    const size_t take = all ? pending_.size() : nblk * kBlockPayload;
+    if (take) {
+        Bytes chunk;
+        if (take == pending_.size()) chunk.swap(pending_);
+        else {
+            chunk.assign(pending_.begin(), pending_.begin() + take);
+            pending_.erase(pending_.begin(), pending_.begin() + take);
+        }
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return q_.size() < 2 || !bg_err_.empty(); });
+        if (bg_err_.empty()) {
+            q_.push_back(std::move(chunk));
+            cv_.notify_all();
+        }
+    }
+    std::lock_guard<std::mutex> lk(m_);
+    if (!bg_err_.empty()) { err = bg_err_; return false; }
+    return true;
+}
+
+void BgzfWriter::bg_loop()
+{
+    for (;;) {
+        Bytes chunk;
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            cv_.wait(lk, [&] { return !q_.empty() || end_; });
+            if (q_.empty()) return;
+            chunk = std::move(q_.front());
+            q_.pop_front();
+            cv_.notify_all();
+        }
+        std::string err;
+        bool ok = false;
+        try {
+            ok = deflate_chunk(chunk, err);
+        } catch (const std::exception& e) {
+            err = std::string("BGZF writer: ") + e.what();
+        } catch (...) {
+            err = "BGZF writer: unknown exception";
+        }
+        if (!ok) {
+            std::lock_guard<std::mutex> lk(m_);
+            bg_err_ = err.empty() ? std::string("deflate failed") : err;
+            q_.clear();
+            cv_.notify_all();
+            return;
+        }
+    }
+}
+
+bool BgzfWriter::deflate_chunk(const Bytes& in, std::string& err)
+{
+    const size_t nblk = (in.size() + kBlockPayload - 1) / kBlockPayload;
     if (!nblk) return true;
     std::vector<Bytes> comp(nblk);
     std::atomic<bool> ok{true};
+    const int level = level_;
     parallel_for(nblk, threads_, [&](size_t i) {
         const size_t off = i * kBlockPayload;
-        const size_t len = std::min(kBlockPayload, pending_.size() - off);
+        const size_t len = std::min(kBlockPayload, in.size() - off);
         Bytes& c = comp[i];
         c.resize(18 + compressBound((uLong)len) + 8);
         // one deflate stream per thread and level for the life of the thread: deflateInit2 allocates and clears ~260 KB per call
         static thread_local TlDeflate tl;
-        if (!tl.init || tl.level != level_) {
+        if (!tl.init || tl.level != level) {
             if (tl.init) deflateEnd(&tl.zs);
             tl.zs = z_stream{};
             tl.init = false;
-            if (deflateInit2(&tl.zs, level_, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { ok = false; return; }
+            if (deflateInit2(&tl.zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { ok = false; return; }
             tl.init = true;
-            tl.level = level_;
+            tl.level = level;
         } else if (deflateReset(&tl.zs) != Z_OK) { ok = false; return; }
         z_stream& zs = tl.zs;
-        zs.next_in = const_cast<Bytef*>(pending_.data() + off);
+        zs.next_in = const_cast<Bytef*>(in.data() + off);
         zs.avail_in = (uInt)len;
         zs.next_out = c.data() + 18;
         zs.avail_out = (uInt)(c.size() - 18 - 8);
@@ -404,22 +472,27 @@ bool BgzfWriter::flush(bool all, std::string& err)
         c[12] = 'B'; c[13] = 'C';
         wr16(c.data() + 14, 2);
         wr16(c.data() + 16, (uint32_t)(18 + clen + 8 - 1));
-        wr32(c.data() + 18 + clen, (uint32_t)crc32(crc32(0L, Z_NULL, 0), pending_.data() + off, (uInt)len));
+        wr32(c.data() + 18 + clen, (uint32_t)crc32(crc32(0L, Z_NULL, 0), in.data() + off, (uInt)len));
         wr32(c.data() + 18 + clen + 4, (uint32_t)len);
         c.resize(18 + clen + 8);
     });
     if (!ok) { err = "deflate failed"; return false; }
     for (auto& c : comp)
         if (fwrite(c.data(), 1, c.size(), f_) != c.size()) { err = "write error"; return false; }
-    const size_t used = std::min(pending_.size(), nblk * kBlockPayload);
-    pending_.erase(pending_.begin(), pending_.begin() + used);
     return true;
 }
 
 bool BgzfWriter::close(std::string& err)
 {
     if (!f_) return true;
-    bool ok = flush(true, err);
+    bool ok = hand_over(true, err);
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        end_ = true;
+        cv_.notify_all();
+    }
+    if (bg_.joinable()) bg_.join();
+    if (ok && !bg_err_.empty()) { err = bg_err_; ok = false; }
     static const uint8_t eof_marker[28] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (ok && fwrite(eof_marker, 1, 28, f_) != 28) { err = "write error"; ok = false; }
     if (fclose(f_) != 0 && ok) { err = "close error"; ok = false; }

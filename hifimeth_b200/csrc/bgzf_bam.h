@@ -94,10 +94,18 @@ public:
     bool close(std::string& err);  // flushes, writes the BGZF end-of-file marker
 
 private:
-    bool flush(bool all, std::string& err);
+    bool hand_over(bool all, std::string& err);   // whole blocks (all: everything) of pending_ -> the background thread
+    void bg_loop();
+    bool deflate_chunk(const Bytes& in, std::string& err);
     FILE* f_ = nullptr;
     int threads_ = 1, level_ = 6;
     Bytes pending_;
+    std::thread bg_;             // deflates and writes the chunks in order
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<Bytes> q_;
+    bool end_ = false;
+    std::string bg_err_;
 };
 
 struct BamHeader {
