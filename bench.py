@@ -61,7 +61,12 @@ class ClockSampler:
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t_mark = index, [], None, None
+
+    def mark(self):
+        """The timed region starts now: only samples taken from here on count (nvidia-smi needs seconds to start on an 8-GPU box,
+        so it is launched before the warm-up steps)."""
+        self.t_mark = time.perf_counter()
 
     def start(self):
         try:
@@ -73,11 +78,16 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
+        timed = [r for t, r in self.rows if self.t_mark is None or t >= self.t_mark]
+        window = "timed region"
+        if not timed:  # a timed region shorter than one sampling period: the warm-up steps ran the same kernels
+            timed, window = [r for _, r in self.rows], "warm-up + timed region"
+        self.rows = timed
         sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
         mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         reasons = set()
@@ -85,7 +95,8 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
+                "window": window}
 
 
 def physical_cores() -> int:
@@ -433,12 +444,13 @@ def main():
 
     # ---- kernel-only: inputs resident in HBM -------------------------------------------------------------------------------------
     flags = hme.HM_SUBMIT_SKIP_H2D | hme.HM_SUBMIT_SKIP_D2H
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         eng.submit(0, n, flags)
         eng.collect(0, copy=False)
-    sampler = ClockSampler(local)
-    sampler.start()
     barrier()
+    sampler.mark()
     dev_ms = top_ms = exec_flops = 0.0
     launches = top_launches = 0
     stage_ms = np.zeros(4)
