@@ -7,7 +7,8 @@ import sys
 import numpy as np
 import pytest
 
-from hifimeth_b200 import shard, synth
+from hifimeth_b200 import synth
+import shard_model as shard
 
 from conftest import ROOT
 
