@@ -720,7 +720,7 @@ int tensor_model_build(TensorModelHandle& m, const CnnModel& host)
             c.gather_shift = c1 ? h.terms[0].shift : 0;
             c.w_rank_bytes = rank_bytes;
             c.wait_op = (int)i;
-            for (int q = 0; q < kChainMaxWait; ++q) c.mma_wait[q] = -1;
+            c.mma_wait = 0;
             it.out_map = h.out;
             // a ring slot holds the step's weight tiles (cout x 64 bytes for this CTA) in front of the 16 KiB slab of a streamed term
             if ((uint32_t)h.cout * 64u > (h.head ? kChainSlotBytes : kChainWBytes)) { ok = false; break; }
@@ -746,9 +746,9 @@ int tensor_model_build(TensorModelHandle& m, const CnnModel& host)
             int nw = 0;
             auto add_wait = [&](int j) {
                 if (j < 0) return true;
-                for (int q = 0; q < nw; ++q) if (c.mma_wait[q] == j) return true;
+                for (int q = 0; q < nw; ++q) if (((c.mma_wait >> (8 * q)) & 0xffu) == (uint32_t)j + 1u) return true;
                 if (nw == kChainMaxWait) return false;
-                c.mma_wait[nw++] = j;
+                c.mma_wait |= ((uint32_t)j + 1u) << (8 * nw++);
                 return true;
             };
             for (size_t k = 0; k < h.terms.size() && ok; ++k) {

@@ -46,6 +46,11 @@ constexpr uint32_t kChainSlabBytes = 16384;    // 8 planes: {hi, lo} x 4 channel
 constexpr uint32_t kChainSlotBytes = 24576;    // weights first, slab behind them; a step without slab may use all of it (head: 16 KiB)
 constexpr int kChainMaxSteps = 192;            // table of the steps of one tile round (124 for the shipped models); last entry = count
 constexpr int kChainMaxWait = 4;
+// clock64 stamps (HM_CHAIN_STAMPS=1 at run time) are compiled in only with -DHM_CHAIN_STAMPS_BUILD=1 (tools/build_variant.py): even
+// predicated off they cost the single MMA-issuing thread instructions on its critical loop
+#ifndef HM_CHAIN_STAMPS_BUILD
+#define HM_CHAIN_STAMPS_BUILD 0
+#endif
 
 struct ChainTerm {
     const uint8_t* src;   // streamed term: plane 0 (hi, g = 0), row 0 of the compact source map; resident term: nullptr
@@ -68,7 +73,8 @@ struct ChainOp {
     int32_t gather;         // 1: conv1 form (F1, G1): term 0 is gathered from the X map -- a ring step holds 4 TAPS (= 2 K-steps of two
                             // 8-feature taps) of the 128 sites' windows, rows site_rows[site] + gather_shift + tap; cin = 8 * padded taps
     int32_t gather_shift;
-    int32_t mma_wait[kChainMaxWait];  // the first MMA waits for the epilogues of these ops; -1 = unused
+    uint32_t mma_wait;      // the first MMA waits for the epilogues of up to four ops: one byte each, 1 + op index, 0 = unused
+    uint32_t pad_[3];
 };
 
 struct ChainProgram {
@@ -242,12 +248,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) si
                     const uint32_t idesc = umma::make_idesc_bf16_m256((uint32_t)op.n);
                     const uint32_t b_desc = (uint32_t)umma::make_desc(0, nh * 16u, 128);
                     const uint32_t b_tile16 = (nh * 32u) >> 4;  // the {hi} or the {lo} tile of one stage
-                    const bool sto = prog.dbg && pair == 0 && it == 2 && lane == 0;
+                    const bool sto = HM_CHAIN_STAMPS_BUILD && prog.dbg && pair == 0 && it == 2 && lane == 0;
                     if (sto) prog.dbg[320 + 2 * oi] = clock64();
                     // resident inputs written and accumulator columns drained by earlier epilogues (both CTAs)
-                    #pragma unroll
-                    for (int q = 0; q < kChainMaxWait; ++q)
-                        if (op.mma_wait[q] >= 0) umma::mbar_wait(&res_ready[op.mma_wait[q]], it & 1u);
+                    for (uint32_t w = op.mma_wait; w; w >>= 8) umma::mbar_wait(&res_ready[(w & 0xffu) - 1u], it & 1u);
                     umma::tc_fence_after();
                     if (sto) prog.dbg[321 + 2 * oi] = clock64();
                     const uint32_t d_addr = tmem_base + op.acc_col;
@@ -255,7 +259,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) si
                     for (uint32_t S = 0; S < n_spairs; ++S) {
                         for (uint32_t k = 0; k < n_terms; ++k, ++step) {
                             const uint32_t slot = step % (uint32_t)kChainSlots, phase = (step / (uint32_t)kChainSlots) & 1u;
-                            const bool st = prog.dbg && pair == 0 && it == 2 && lane == 0 && mstep < 124u;
+                            const bool st = HM_CHAIN_STAMPS_BUILD && prog.dbg && pair == 0 && it == 2 && lane == 0 && mstep < 124u;
                             if (st) prog.dbg[2 * mstep] = clock64();
                             if (!ready) umma::mbar_wait(&full[slot], phase);
                             {
@@ -312,7 +316,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) si
             for (int oi = 0; oi < n_ops; ++oi) {
                 const ChainOp& op = s_ops[oi];
                 const int n = op.n;
-                const bool st = prog.dbg && pair == 0 && it == 2 && rank == 0 && warp == (uint32_t)kProducerWarps + 1u && lane == 0;
+                const bool st = HM_CHAIN_STAMPS_BUILD && prog.dbg && pair == 0 && it == 2 && rank == 0 && warp == (uint32_t)kProducerWarps + 1u && lane == 0;
                 if (st) prog.dbg[256 + 3 * oi] = clock64();
                 umma::mbar_wait(&acc_full[op.wait_op], it & 1u);
                 if (st) prog.dbg[256 + 3 * oi + 1] = clock64();
