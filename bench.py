@@ -556,6 +556,12 @@ def main():
         if not args.no_queue and args.cnn_mode == 0:
             q = queue_bench(world, args.queue_reads, level=args.queue_level)
             line["queue"] = q
+            if world >= 4 and "value" in q and not os.environ.get("HM_QUEUE_NO_LEVEL1"):
+                # below ~8 host cores per GPU zlib sets the pace: the same run with the output at BGZF level 1 shows how much of the
+                # host budget the level-6 deflate takes (the reference writes through htslib's default, level 6)
+                q1 = queue_bench(world, args.queue_reads, level=1)
+                line["queue_level1"] = {k: q1[k] for k in ("value", "wall_s", "sites", "out_bam_bytes", "steady_sites_per_s", "limiter", "phase_s_summed_per_role",
+                                                           "timeline_s", "cmd", "error") if k in q1}
             line["kernel_scaling"] = {"value": line["value"], "unit": "sites/s", "what": "N ranks, N resident batches, device time, max over ranks"}
             if world > 1 and "value" in q:
                 # for N > 1 the end-to-end number IS the product's one-process queue path (BAM in -> mod BAM out)
