@@ -238,69 +238,97 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) si
             const uint32_t desc_hi = (uint32_t)(umma::make_desc(0, 0, 128) >> 32);
             const uint32_t ring16 = umma::smem_u32(s_ring) >> 4;
             const uint32_t a_desc = (uint32_t)umma::make_desc(0, kChainPlaneBytes, 128);  // K-adjacent core matrices one plane apart
+            // Everything the issue loop needs from an op sits in registers, and the NEXT op's values are fetched while the current
+            // op's steps issue: read from the op table at the op boundary they cost the one issuing thread a chain of shared-memory
+            // round trips there, on top of a load per step for the term's kind.
+            struct OpVals {
+                uint32_t n_spairs, n_terms, idesc, b_desc, b_tile16, acc_col, mma_wait, stream_mask;
+                uint32_t a_hi[kMaxTerms], a_lo[kMaxTerms];
+            };
+            auto load_op = [&](int oi) {
+                const ChainOp& op = s_ops[oi];
+                OpVals v;
+                const uint32_t nh = (uint32_t)op.n >> 1;
+                v.n_spairs = (uint32_t)op.cin >> 5;
+                v.n_terms = (uint32_t)op.n_terms;
+                v.idesc = umma::make_idesc_bf16_m256((uint32_t)op.n);
+                v.b_desc = (uint32_t)umma::make_desc(0, nh * 16u, 128);
+                v.b_tile16 = (nh * 32u) >> 4;  // the {hi} or the {lo} tile of one stage
+                v.acc_col = op.acc_col;
+                v.mma_wait = op.mma_wait;
+                v.stream_mask = 0;
+                #pragma unroll
+                for (int k = 0; k < kMaxTerms; ++k) {
+                    if (op.term[k].src != nullptr) v.stream_mask |= 1u << k;
+                    v.a_hi[k] = tmem_base + op.term[k].a_hi_col;
+                    v.a_lo[k] = tmem_base + op.term[k].a_lo_col;
+                }
+                return v;
+            };
             uint32_t step = 0, it = 0, mstep = 0;
             bool ready = false;  // the NEXT step's slot is probed before this step's MMAs are issued: hides the barrier round trip
+            OpVals cur = load_op(0);
             for (uint32_t t2 = pair; 2 * t2 < prog.n_tiles; t2 += n_pairs, ++it) {
                 for (int oi = 0; oi < n_ops; ++oi) {
-                    const ChainOp& op = s_ops[oi];
-                    const uint32_t n_spairs = (uint32_t)op.cin >> 5, n_terms = (uint32_t)op.n_terms;
-                    const uint32_t nh = (uint32_t)op.n >> 1;
-                    const uint32_t idesc = umma::make_idesc_bf16_m256((uint32_t)op.n);
-                    const uint32_t b_desc = (uint32_t)umma::make_desc(0, nh * 16u, 128);
-                    const uint32_t b_tile16 = (nh * 32u) >> 4;  // the {hi} or the {lo} tile of one stage
+                    OpVals nxt = cur;
                     const bool sto = HM_CHAIN_STAMPS_BUILD && prog.dbg && pair == 0 && it == 2 && lane == 0;
                     if (sto) prog.dbg[320 + 2 * oi] = clock64();
                     // resident inputs written and accumulator columns drained by earlier epilogues (both CTAs)
-                    for (uint32_t w = op.mma_wait; w; w >>= 8) umma::mbar_wait(&res_ready[(w & 0xffu) - 1u], it & 1u);
+                    for (uint32_t w = cur.mma_wait; w; w >>= 8) umma::mbar_wait(&res_ready[(w & 0xffu) - 1u], it & 1u);
                     umma::tc_fence_after();
                     if (sto) prog.dbg[321 + 2 * oi] = clock64();
-                    const uint32_t d_addr = tmem_base + op.acc_col;
-                    uint32_t acc = 0;
-                    for (uint32_t S = 0; S < n_spairs; ++S) {
-                        for (uint32_t k = 0; k < n_terms; ++k, ++step) {
-                            const uint32_t slot = step % (uint32_t)kChainSlots, phase = (step / (uint32_t)kChainSlots) & 1u;
-                            const bool st = HM_CHAIN_STAMPS_BUILD && prog.dbg && pair == 0 && it == 2 && lane == 0 && mstep < 124u;
-                            if (st) prog.dbg[2 * mstep] = clock64();
-                            if (!ready) umma::mbar_wait(&full[slot], phase);
-                            {
-                                const uint32_t ns = step + 1u;
-                                ready = umma::mbar_test_wait(&full[ns % (uint32_t)kChainSlots], (ns / (uint32_t)kChainSlots) & 1u);
-                            }
-                            if (st) {
-                                prog.dbg[2 * mstep + 1] = clock64();
-                                ++mstep;
-                            }
-                            umma::tc_fence_after();
-                            if (umma::elect_one()) {
-                                const uint32_t sb16 = ring16 + slot * (kChainSlotBytes >> 4);
-                                const uint32_t b0 = b_desc + sb16;
-                                if (op.term[k].src != nullptr) {
-                                    const uint32_t a0 = a_desc + sb16 + (kChainWBytes >> 4);
-                                    #pragma unroll
-                                    for (uint32_t s = 0; s < 2; ++s) {
-                                        const uint32_t a_h = a0 + s * ((2u * kChainPlaneBytes) >> 4), a_l = a_h + ((4u * kChainPlaneBytes) >> 4);
-                                        const uint32_t b_h = b0 + s * 2u * b_tile16, b_l = b_h + b_tile16;
-                                        umma::mma2_bf16_w(d_addr, a_h, b_h, desc_hi, idesc, s ? 1u : acc);
-                                        umma::mma2_bf16_w(d_addr, a_l, b_h, desc_hi, idesc, 1);
-                                        umma::mma2_bf16_w(d_addr, a_h, b_l, desc_hi, idesc, 1);
-                                    }
-                                } else {
-                                    const uint32_t a0 = tmem_base + op.term[k].a_hi_col + 16u * S, l0 = tmem_base + op.term[k].a_lo_col + 16u * S;
-                                    #pragma unroll
-                                    for (uint32_t s = 0; s < 2; ++s) {
-                                        const uint32_t b_h = b0 + s * 2u * b_tile16, b_l = b_h + b_tile16;
-                                        umma::mma2_ts_bf16_w(d_addr, a0 + 8u * s, b_h, desc_hi, idesc, s ? 1u : acc);
-                                        umma::mma2_ts_bf16_w(d_addr, l0 + 8u * s, b_h, desc_hi, idesc, 1);
-                                        umma::mma2_ts_bf16_w(d_addr, a0 + 8u * s, b_l, desc_hi, idesc, 1);
-                                    }
-                                }
-                                // the op's last step releases its slot through acc_full (see the producers)
-                                umma::mma2_commit_mc((S + 1 == n_spairs && k + 1 == n_terms) ? &acc_full[oi] : &empty[slot]);
-                            }
-                            acc = 1;
-                            __syncwarp();
+                    const uint32_t d_addr = tmem_base + cur.acc_col;
+                    const uint32_t n_steps = cur.n_spairs * cur.n_terms;
+                    uint32_t acc = 0, S = 0, k = 0;
+                    for (uint32_t q = 0; q < n_steps; ++q, ++step) {
+                        const uint32_t slot = step % (uint32_t)kChainSlots, phase = (step / (uint32_t)kChainSlots) & 1u;
+                        const bool st = HM_CHAIN_STAMPS_BUILD && prog.dbg && pair == 0 && it == 2 && lane == 0 && mstep < 124u;
+                        if (st) prog.dbg[2 * mstep] = clock64();
+                        if (!ready) umma::mbar_wait(&full[slot], phase);
+                        {
+                            const uint32_t ns = step + 1u;
+                            ready = umma::mbar_test_wait(&full[ns % (uint32_t)kChainSlots], (ns / (uint32_t)kChainSlots) & 1u);
                         }
+                        if (st) {
+                            prog.dbg[2 * mstep + 1] = clock64();
+                            ++mstep;
+                        }
+                        umma::tc_fence_after();
+                        const bool stream = (cur.stream_mask >> k) & 1u;
+                        const uint32_t ah = k == 0 ? cur.a_hi[0] : k == 1 ? cur.a_hi[1] : cur.a_hi[2];
+                        const uint32_t al = k == 0 ? cur.a_lo[0] : k == 1 ? cur.a_lo[1] : cur.a_lo[2];
+                        if (umma::elect_one()) {
+                            const uint32_t sb16 = ring16 + slot * (kChainSlotBytes >> 4);
+                            const uint32_t b0 = cur.b_desc + sb16;
+                            if (stream) {
+                                const uint32_t a0 = a_desc + sb16 + (kChainWBytes >> 4);
+                                #pragma unroll
+                                for (uint32_t s = 0; s < 2; ++s) {
+                                    const uint32_t a_h = a0 + s * ((2u * kChainPlaneBytes) >> 4), a_l = a_h + ((4u * kChainPlaneBytes) >> 4);
+                                    const uint32_t b_h = b0 + s * 2u * cur.b_tile16, b_l = b_h + cur.b_tile16;
+                                    umma::mma2_bf16_w(d_addr, a_h, b_h, desc_hi, cur.idesc, s ? 1u : acc);
+                                    umma::mma2_bf16_w(d_addr, a_l, b_h, desc_hi, cur.idesc, 1);
+                                    umma::mma2_bf16_w(d_addr, a_h, b_l, desc_hi, cur.idesc, 1);
+                                }
+                            } else {
+                                const uint32_t a0 = ah + 16u * S, l0 = al + 16u * S;
+                                #pragma unroll
+                                for (uint32_t s = 0; s < 2; ++s) {
+                                    const uint32_t b_h = b0 + s * 2u * cur.b_tile16, b_l = b_h + cur.b_tile16;
+                                    umma::mma2_ts_bf16_w(d_addr, a0 + 8u * s, b_h, desc_hi, cur.idesc, s ? 1u : acc);
+                                    umma::mma2_ts_bf16_w(d_addr, l0 + 8u * s, b_h, desc_hi, cur.idesc, 1);
+                                    umma::mma2_ts_bf16_w(d_addr, a0 + 8u * s, b_l, desc_hi, cur.idesc, 1);
+                                }
+                            }
+                            // the op's last step releases its slot through acc_full (see the producers)
+                            umma::mma2_commit_mc(q + 1 == n_steps ? &acc_full[oi] : &empty[slot]);
+                        }
+                        acc = 1;
+                        __syncwarp();
+                        if (q == 0) nxt = load_op(oi + 1 == n_ops ? 0 : oi + 1);  // in flight under this op's remaining steps
+                        if (++k == cur.n_terms) { k = 0; ++S; }
                     }
+                    cur = nxt;
                 }
             }
         }
