@@ -940,6 +940,9 @@ DenseOp patch_op(const DevOp& d, const TensorWorkspaceImpl& s, uint32_t n_tiles,
 
 long long* g_f12_dbg = nullptr;
 long long* g_chain_dbg = nullptr;
+long long* g_g2_dbg = nullptr;
+int g_g2_which = -1;  // HM_G2_STAMPS=<k>: stamp the k-th dense_gemm2 launch of every batch (0 = first)
+int g_g2_count = 0;
 
 // conv1 + conv2 of `rows` dense rows in one launch (dense_fused12_kernel): tiles of 124 output rows, CTA pairs.
 int launch_fused12(const DevOp& d1, const DevOp& d2, TensorWorkspaceImpl& s, uint32_t rows, int sm_count, cudaStream_t stream)
@@ -985,7 +988,19 @@ int launch_op(const DevOp& d, TensorWorkspaceImpl& s, uint32_t n_tiles, float* l
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    if (d.two_cta) return cudaLaunchKernelEx(&cfg, dense_gemm2_kernel, p) == cudaSuccess ? 0 : -1;
+    if (d.two_cta) {
+        // HM_G2_STAMPS=<k>: pair 0 of the k-th CTA-pair launch of the batch stamps tiles 16 .. 47 (needs the stamps build)
+        static const char* g2 = getenv("HM_G2_STAMPS");
+        if (g2) {
+            if (!g_g2_dbg) cudaMalloc((void**)&g_g2_dbg, 512 * sizeof(long long));
+            if (g_g2_count++ == atoi(g2)) {
+                cudaMemsetAsync(g_g2_dbg, 0, 512 * sizeof(long long), stream);
+                p.dbg = g_g2_dbg;
+                g_g2_which = p.n;
+            }
+        }
+        return cudaLaunchKernelEx(&cfg, dense_gemm2_kernel, p) == cudaSuccess ? 0 : -1;
+    }
     return cudaLaunchKernelEx(&cfg, dense_gemm_kernel, p) == cudaSuccess ? 0 : -1;
 }
 
@@ -1276,6 +1291,20 @@ int tensor_batch_run(const TensorModelHandle* models, uint32_t ctx_mask, TensorW
             fprintf(stderr, "%2d:", t);
             for (int k = 0; k < 16; ++k) fprintf(stderr, " %7lld%s", h[16 * t + k] ? h[16 * t + k] - t0 : -1, (k == 2 || k == 10 || k == 11 || k == 14) ? " |" : "");
             fprintf(stderr, "\n");
+        }
+    }
+    if (g_g2_dbg) {  // HM_G2_STAMPS: where pair 0 of one dense_gemm2 launch spent tiles 16 .. 47
+        cudaStreamSynchronize(stream);
+        g_g2_count = 0;
+        std::vector<long long> h(512);
+        cudaMemcpy(h.data(), g_g2_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "dense_gemm2 stamps (N = %d), per tile: MMA warp [wait acc buffer | wait ring stages | tile period] epilogue warp [wait acc | store | period] "
+                        "producer warp 0 [wait slot]\n", g_g2_which);
+        for (int t = 1; t < 32 && h[16 * t]; ++t) {
+            const long long* d = h.data() + 16 * t;
+            const long long* q = d - 16;
+            fprintf(stderr, " %2d: mma [%5lld | %5lld | %5lld]  epi [%5lld | %5lld | %5lld]  prod [%5lld]\n", 16 + t, d[1] - d[0], d[2], d[0] - q[0], d[5] - d[4],
+                    d[6] - d[5], d[6] - q[6], d[8]);
         }
     }
     if (g_chain_dbg) {  // HM_CHAIN_STAMPS: ring timeline of pair 0 of the last chain launch (cycles; each SM has its own clock)

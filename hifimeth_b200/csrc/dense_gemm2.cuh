@@ -14,6 +14,14 @@
 
 namespace hm {
 
+// clock64 stamps of pair 0 (HM_G2_STAMPS=1 at run time) are compiled in only with -DHM_G2_STAMPS_BUILD=1 (tools/build_variant.py):
+// per tile 16 .. 47 of the launch, dbg[16 * (it - 16) + k]: MMA warp k = 0 before / 1 after the wait for the accumulator buffer,
+// 2 cycles spent waiting for ring stages, 3 last stage issued; epilogue warp 0 of the leader: 4 before / 5 after the wait for the
+// accumulator, 6 tile stored; producer warp 0 of the leader: 8 cycles spent waiting for its ring slot during the tile.
+#ifndef HM_G2_STAMPS_BUILD
+#define HM_G2_STAMPS_BUILD 0
+#endif
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) dense_gemm2_kernel(const __grid_constant__ DenseOp op)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -77,7 +85,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) de
             for (int st = 0; st < op.n_stages; ++st, ++stage_no) {
                 if (stage_no % n_prod != warp) continue;
                 const uint32_t slot = stage_no % (uint32_t)op.ring, phase = (stage_no / (uint32_t)op.ring) & 1u;
+                const uint32_t pit = (t2 - pair) / n_pairs;
+                const bool pst = HM_G2_STAMPS_BUILD && op.dbg && pair == 0 && rank == 0 && warp == 0 && lane == 0 && pit >= 16u && pit < 48u;
+                const long long pt0 = pst ? clock64() : 0;
                 umma::mbar_wait(&empty[slot], phase ^ 1u);
+                if (pst) op.dbg[16 * (pit - 16u) + 8] += clock64() - pt0;
                 uint8_t* stage = s_ring + (size_t)slot * op.stage_bytes;
                 if (lane == 0) umma::mbar_arrive_expect_tx(&full[slot], stage_tx);
                 __syncwarp();
@@ -117,12 +129,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) de
             uint32_t slot = 0, phase = 0, it = 0;
             for (uint32_t t2 = pair; 2 * t2 < op.n_tiles; t2 += n_pairs, ++it) {
                 const uint32_t buf = it & 1u, use = it >> 1;
+                const bool mst = HM_G2_STAMPS_BUILD && op.dbg && pair == 0 && lane == 0 && it >= 16u && it < 48u;
+                long long* md = op.dbg + 16 * ((int)it - 16);
+                if (mst) md[0] = clock64();
                 umma::mbar_wait(&t_empty[buf], (use & 1u) ^ 1u);
+                if (mst) md[1] = clock64();
                 umma::tc_fence_after();
                 const uint32_t d_addr = tmem_base + buf * acc_stride;
                 uint32_t acc = 0, b_cur = b_base;
                 for (int st = 0; st < n_stages; ++st) {
+                    const long long mt0 = mst ? clock64() : 0;
                     umma::mbar_wait(&full[slot], phase);
+                    if (mst) md[2] += clock64() - mt0;
                     umma::tc_fence_after();
                     if (umma::elect_one()) {
                         const uint32_t sa = ring16 + slot * stage16;
@@ -145,6 +163,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) de
                     if (++slot == (uint32_t)ring) { slot = 0; phase ^= 1u; }
                 }
                 if (umma::elect_one()) umma::mma2_commit_mc(&t_full[buf]);
+                if (mst) md[3] = clock64();
                 __syncwarp();
             }
         } else {
@@ -172,12 +191,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) de
             #pragma unroll
             for (int k = 0; k < kMaxScatter; ++k) msc[k] = msc_next[k];
             if (2 * (t2 + n_pairs) < op.n_tiles) scatter_rows(op, (unsigned long long)(2 * (t2 + n_pairs) + rank) * kTileRows + m, msc_next);
+            const bool est = HM_G2_STAMPS_BUILD && op.dbg && pair == 0 && rank == 0 && warp == (uint32_t)kProducerWarps + 1u && lane == 0 && it >= 16u && it < 48u;
+            if (est) op.dbg[16 * ((int)it - 16) + 4] = clock64();
             umma::mbar_wait(&t_full[buf], use & 1u);
+            if (est) op.dbg[16 * ((int)it - 16) + 5] = clock64();
             umma::tc_fence_after();
             const uint32_t t_addr = tmem_base + (lane_grp << 16) + buf * acc_stride;
             epilogue_map_row(op, t_addr, row, half, s_bias, msc, false);
             umma::tc_fence_before();
             __syncwarp();
+            if (est) op.dbg[16 * ((int)it - 16) + 6] = clock64();
             if (lane == 0) {
                 if (rank == 0) umma::mbar_arrive(&t_empty[buf]);
                 else umma::mbar_arrive_cluster(umma::mapa(umma::smem_u32(&t_empty[buf]), 0));
