@@ -556,3 +556,29 @@ def test_chain_kernel_and_op_by_op_compact_ops_agree(lib_built, tmp_path):
     assert int(a["launches"]) < int(b["launches"])  # one chain launch per context instead of 17 compact ops
     assert np.abs(a["logits"] - b["logits"]).max() < 2e-4
     assert np.abs(a["ml"].astype(int) - b["ml"].astype(int)).max() <= 1
+
+
+def test_repeated_engines_and_pipelined_slots_are_deterministic(lib_built):
+    """Engines created and destroyed in a row, two staging slots in flight at a time (the way the `call` driver and bench.py's
+    e2e loop use them): every batch succeeds and every run returns the same bytes.  tools/stress_engine.py is the long form
+    (200 engines x 4 full-size batches on one B200: no failure, one digest)."""
+    import hashlib
+
+    batch, _ = synth.make_reads(60, (4000, 15000), seed=99, flag_rev_every=4)
+    ref = None
+    for _ in range(6):
+        eng = hme.Engine(n_slots=2, max_reads=64, max_bases=batch.n_bases + 1024)
+        try:
+            digests = []
+            for i in range(4):
+                n = eng.stage(i & 1, batch)
+                eng.submit(i & 1, n)
+                if i:
+                    r = eng.collect((i & 1) ^ 1)
+                    digests.append(hashlib.sha1(r.ml.tobytes() + r.qoff.tobytes() + r.call_off.tobytes()).hexdigest())
+            r = eng.collect(1)
+            digests.append(hashlib.sha1(r.ml.tobytes() + r.qoff.tobytes() + r.call_off.tobytes()).hexdigest())
+        finally:
+            eng.close()
+        ref = ref or digests[0]
+        assert digests == [ref] * 4
