@@ -1,4 +1,4 @@
-// site_chain.cuh -- the compact (per-site) part of the dilated dense plan in ONE kernel: F2..F6, G2..G6, T7_0..3, T8_0..1 and the
+// site_chain.cuh -- the compact (per-site) part of the dilated dense plan in ONE kernel: F1..F6, G1..G6, T7_0..3, T8_0..1 and the
 // FC head of a tile of sites, with every intermediate map kept ON CHIP IN TENSOR MEMORY.
 //
 // Launched op by op (round 1) the compact chain moved ~23 KB of HBM traffic per site -- every op wrote its 256..512 B/site map and
@@ -15,8 +15,10 @@
 //              commit latency in BOTH the producer warps and the MMA warp (clock64 stamps, HM_CHAIN_STAMPS) -- 30 ms per step against
 //              24 ms op by op.  With the maps in TMEM all of shared memory is ring.
 //   streamed   through a ring of 9 slots of 24 KiB, one slot per (op, PAIR of 16-channel stages, term): the term's weight tiles (hi, lo;
-//              this CTA's half of N; from L2 -- the whole model is 1 MB) and, for terms that read a scatter copy of a dense map or
-//              F1 / G1, the 8 activation planes of the two stages (16 KiB, HBM -> shared, 1-D bulk copies); 6 MMAs per hand-over
+//              this CTA's half of N; from L2 -- the whole model is 1 MB) and, for terms that read a scatter copy of a dense map,
+//              the 8 activation planes of the two stages (16 KiB, HBM -> shared, 1-D bulk copies); 6 MMAs per hand-over.  The
+//              conv1-form ops F1 / G1 open the chain: their steps hold 4 taps of the sites' windows, gathered from the X map with
+//              one 16-byte cp.async per (site, tap, hi / lo) through the site-row index
 //   MMA warp   (leader CTA) per slot and stage the split-precision triple hi*hi + lo*hi + hi*lo, M = 256; waits for the epilogues an
 //              op depends on (mbarrier) before its first MMA, so F and G ops alternate: MMA(G_l) runs under epilogue(F_l).  Resident
 //              operands also run faster: N = 96 / 64 take 48 / 46 cycles per MMA from TMEM against 64 from shared memory
@@ -30,8 +32,8 @@
 // MMAs still read the columns its packed output goes to; the epilogue warps of a CTA meet at a named barrier after the head, because
 // the next round's F2 / G2 outputs go where the head's accumulator was.
 //
-// HBM traffic per site: the scatter copies and F1 / G1 read once (~7.5 KB) and 9 B of logits + ML byte written.  conv1-form ops (F1, G1:
-// gathered from the X map) stay separate launches of dense_gemm_kernel.
+// HBM traffic per site: the scatter copies (6.5 KB) and the site's X rows read once, 9 B of logits + ML byte written.  No other
+// launch belongs to the compact part of the plan.
 #pragma once
 #include "dense_gemm2.cuh"
 #include "postprocess.cuh"
