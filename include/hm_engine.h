@@ -28,6 +28,10 @@
  * Threading: one feeder thread per slot may call acquire/submit/collect for that slot; different slots
  * may be driven from different threads.  Each slot owns a CUDA stream; H2D, kernels and D2H of different
  * slots overlap.  Buffers handed out by acquire/collect stay valid until the next acquire of the slot.
+ * hm_batch_submit is NOT fully asynchronous: it returns after the decode and scan kernels of the batch have run (tens of
+ * microseconds of device time) -- the host cuts the CNN stage's sub-batches from the per-read site counts the scan produces --
+ * and with the CNN stage enqueued; everything after that overlaps the caller.  Two slots per device (what the `call` driver and
+ * bench.py use) keep the device busy across that hand-over.
  */
 #ifndef HM_ENGINE_H
 #define HM_ENGINE_H
