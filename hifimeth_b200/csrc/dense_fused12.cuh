@@ -50,7 +50,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
     extern __shared__ __align__(128) uint8_t smem[];
     const DenseOp& c1 = f.c1;
     const DenseOp& c2 = f.c2;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the warp index through a shuffle: ptxas then knows it is warp-uniform, role branches become uniform branches and the MMA
+    // issuer's loop counters, descriptors and barrier addresses can stay in uniform registers (cutlass::canonical_warp_idx_sync)
+    const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const uint32_t rank = umma::cluster_ctarank();
     const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
     constexpr int kStages = 8;  // = c2.n_stages: the A ring holds exactly one Y1 tile, slot = stage
@@ -177,10 +179,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
                 if (umma::elect_one()) {
                     const uint32_t d_addr = tmem_base + (j & 1u) * 128u;
                     uint32_t sa = xring16 + slot * xstage16, bq = b1_base, acc = 0;
-                    for (int q = 0; q < ksteps; ++q, sa += aq16) {
-                        umma::mma2_bf16_w(d_addr, x_hi + sa, bq, desc_hi, idesc, acc);
-                        umma::mma2_bf16_w(d_addr, x_lo + sa, bq, desc_hi, idesc, 1);
-                        umma::mma2_bf16_w(d_addr, x_hi + sa, bq + b_step, desc_hi, idesc, 1);
+                    for (int q = 0; q < ksteps; ++q, sa += aq16) {  // one asm statement per triple (umma::mma2_stage3_bf16 has the reason)
+                        umma::mma2_triple_bf16(d_addr, x_hi + sa, x_lo + sa, bq, b_step, desc_hi, idesc, acc);
                         bq += 2 * b_step;
                         acc = 1;
                     }
@@ -206,14 +206,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF12Threads, 1) dens
                     if (lane == 0) stamp(it, 3 + st);
                     if (umma::elect_one()) {
                         const uint32_t sa = ring16 + (uint32_t)st * stage16;
-                        uint32_t bq = b_cur;
-                        #pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            umma::mma2_bf16_w(d_addr, a_hi[k] + sa, bq, desc_hi, idesc, (st | k) ? 1u : 0u);
-                            umma::mma2_bf16_w(d_addr, a_lo[k] + sa, bq, desc_hi, idesc, 1);
-                            umma::mma2_bf16_w(d_addr, a_hi[k] + sa, bq + b_step, desc_hi, idesc, 1);
-                            bq += 2 * b_step;
-                        }
+                        umma::mma2_stage3_bf16(d_addr, a_hi[0] + sa, a_lo[0] + sa, a_hi[1] + sa, a_lo[1] + sa, a_hi[2] + sa, a_lo[2] + sa, b_cur, b_step, desc_hi,
+                                               idesc, st ? 1u : 0u);
                         // epilogue-1 refills the ring one 32-channel chunk (two stages) at a time: one release per chunk
                         if (st & 1) umma::mma2_commit_mc(&empty[st]);
                     }

@@ -212,7 +212,9 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_gemm_kernel_t(const __
 {
     const uint32_t variant = kDbg ? op.variant : 0u;  // experiment switches compile away in the product instantiation
     extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the warp index through a shuffle: ptxas then knows it is warp-uniform, role branches become uniform branches and the MMA
+    // issuer's loop counters, descriptors and barrier addresses can stay in uniform registers (cutlass::canonical_warp_idx_sync)
+    const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     uint8_t* s_w = smem;
     uint8_t* s_ring = smem + ((op.w_bytes + 127u) & ~127u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + (size_t)op.ring * op.stage_bytes);

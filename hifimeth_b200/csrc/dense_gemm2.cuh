@@ -25,7 +25,9 @@ namespace hm {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) dense_gemm2_kernel(const __grid_constant__ DenseOp op)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the warp index through a shuffle: ptxas then knows it is warp-uniform, role branches become uniform branches and the MMA
+    // issuer's loop counters, descriptors and barrier addresses can stay in uniform registers (cutlass::canonical_warp_idx_sync)
+    const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const uint32_t rank = umma::cluster_ctarank();
     const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
     uint8_t* s_w = smem;
@@ -142,7 +144,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) de
                     umma::mbar_wait(&full[slot], phase);
                     if (mst) md[2] += clock64() - mt0;
                     umma::tc_fence_after();
-                    if (umma::elect_one()) {
+                    if (n_terms == 3) {
+                        // all nine MMAs of the stage in one asm statement: see umma::mma2_stage3_bf16
+                        const uint32_t sa = ring16 + slot * stage16;
+                        if (umma::elect_one()) {
+                            umma::mma2_stage3_bf16(d_addr, a_hi[0] + sa, a_lo[0] + sa, a_hi[1] + sa, a_lo[1] + sa, a_hi[2] + sa, a_lo[2] + sa, b_cur, b_step,
+                                                   desc_hi, idesc, acc);
+                            umma::mma2_commit_mc(&empty[slot]);
+                        }
+                    } else if (umma::elect_one()) {
                         const uint32_t sa = ring16 + slot * stage16;
                         uint32_t bq = b_cur, a0 = acc;
                         #pragma unroll

@@ -103,7 +103,9 @@ inline size_t chain_smem_bytes()
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) site_chain_kernel(const __grid_constant__ ChainProgram prog)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the warp index through a shuffle: ptxas then knows it is warp-uniform, role branches become uniform branches and the MMA
+    // issuer's loop counters, descriptors and barrier addresses can stay in uniform registers (cutlass::canonical_warp_idx_sync)
+    const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const uint32_t rank = umma::cluster_ctarank();
     const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
     uint8_t* s_ring = smem;                                  // [9][24 KiB]
@@ -302,25 +304,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1) si
                         if (umma::elect_one()) {
                             const uint32_t sb16 = ring16 + slot * (kChainSlotBytes >> 4);
                             const uint32_t b0 = cur.b_desc + sb16;
+                            // six MMAs in one asm statement: the operands cross into uniform registers once (umma::mma2_stage3_bf16)
                             if (stream) {
                                 const uint32_t a0 = a_desc + sb16 + (kChainWBytes >> 4);
-                                #pragma unroll
-                                for (uint32_t s = 0; s < 2; ++s) {
-                                    const uint32_t a_h = a0 + s * ((2u * kChainPlaneBytes) >> 4), a_l = a_h + ((4u * kChainPlaneBytes) >> 4);
-                                    const uint32_t b_h = b0 + s * 2u * cur.b_tile16, b_l = b_h + cur.b_tile16;
-                                    umma::mma2_bf16_w(d_addr, a_h, b_h, desc_hi, cur.idesc, s ? 1u : acc);
-                                    umma::mma2_bf16_w(d_addr, a_l, b_h, desc_hi, cur.idesc, 1);
-                                    umma::mma2_bf16_w(d_addr, a_h, b_l, desc_hi, cur.idesc, 1);
-                                }
+                                umma::mma2_step6_bf16(d_addr, a0, a0 + ((4u * kChainPlaneBytes) >> 4), (2u * kChainPlaneBytes) >> 4, b0, cur.b_tile16, desc_hi,
+                                                      cur.idesc, acc);
                             } else {
-                                const uint32_t a0 = ah + 16u * S, l0 = al + 16u * S;
-                                #pragma unroll
-                                for (uint32_t s = 0; s < 2; ++s) {
-                                    const uint32_t b_h = b0 + s * 2u * cur.b_tile16, b_l = b_h + cur.b_tile16;
-                                    umma::mma2_ts_bf16_w(d_addr, a0 + 8u * s, b_h, desc_hi, cur.idesc, s ? 1u : acc);
-                                    umma::mma2_ts_bf16_w(d_addr, l0 + 8u * s, b_h, desc_hi, cur.idesc, 1);
-                                    umma::mma2_ts_bf16_w(d_addr, a0 + 8u * s, b_l, desc_hi, cur.idesc, 1);
-                                }
+                                umma::mma2_step6_ts_bf16(d_addr, ah + 16u * S, al + 16u * S, b0, cur.b_tile16, desc_hi, cur.idesc, acc);
                             }
                             // the op's last step releases its slot through acc_full (see the producers)
                             umma::mma2_commit_mc(q + 1 == n_steps ? &acc_full[oi] : &empty[slot]);

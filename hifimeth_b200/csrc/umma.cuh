@@ -185,6 +185,126 @@ __device__ __forceinline__ void mma2_ts_bf16_w(uint32_t tmem_d, uint32_t tmem_a,
         ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
+// The nine MMAs of one ring stage of a three-term op (three taps x {hi*hi, lo*hi, hi*lo}) as ONE asm statement.  The thread that
+// issues the MMAs is the kernels' real limit: measured in situ they run at 70 - 92 cycles each against 64 in a tight loop, and
+// tools/mma_contention_probe.cu reproduces it -- operands recomputed in vector registers in front of every MMA (one integer op + one
+// register-to-uniform move each, what nine separate asm statements compile to) cost 95 cycles per MMA, 129 with epilogue warps
+// competing for the scheduler.  Here the inputs cross into uniform registers once per stage.
+// a_h / a_l: low descriptor words of the three taps' hi and lo views; b0: low word of the stage's first weight tile, tiles
+// {hi, lo} per term b_step apart; acc = 0 overwrites the accumulator with the first product.
+__device__ __forceinline__ void mma2_stage3_bf16(uint32_t tmem_d, uint32_t ah0, uint32_t al0, uint32_t ah1, uint32_t al1, uint32_t ah2, uint32_t al2,
+                                                 uint32_t b0, uint32_t b_step, uint32_t desc_hi, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, t;\n\t.reg .b64 da, dl, db, dc;\n\t.reg .b32 bb;\n\t"
+        "setp.ne.b32 p, %11, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "mov.b64 da, {%1, %9};\n\t"
+        "mov.b64 dl, {%2, %9};\n\t"
+        "mov.b64 db, {%7, %9};\n\t"
+        "add.u32 bb, %7, %8;\n\t"
+        "mov.b64 dc, {bb, %9};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %10, p;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], dl, db, %10, t;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, dc, %10, t;\n\t"
+        "mov.b64 da, {%3, %9};\n\t"
+        "mov.b64 dl, {%4, %9};\n\t"
+        "add.u32 bb, bb, %8;\n\t"
+        "mov.b64 db, {bb, %9};\n\t"
+        "add.u32 bb, bb, %8;\n\t"
+        "mov.b64 dc, {bb, %9};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %10, t;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], dl, db, %10, t;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, dc, %10, t;\n\t"
+        "mov.b64 da, {%5, %9};\n\t"
+        "mov.b64 dl, {%6, %9};\n\t"
+        "add.u32 bb, bb, %8;\n\t"
+        "mov.b64 db, {bb, %9};\n\t"
+        "add.u32 bb, bb, %8;\n\t"
+        "mov.b64 dc, {bb, %9};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %10, t;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], dl, db, %10, t;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, dc, %10, t;\n\t}"
+        ::"r"(tmem_d), "r"(ah0), "r"(al0), "r"(ah1), "r"(al1), "r"(ah2), "r"(al2), "r"(b0), "r"(b_step), "r"(desc_hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// One split-precision triple (a_h b0, a_l b0, a_h (b0 + b_step)) as one asm statement (conv1-form k-steps of the fused kernel).
+__device__ __forceinline__ void mma2_triple_bf16(uint32_t tmem_d, uint32_t a_h, uint32_t a_l, uint32_t b0, uint32_t b_step, uint32_t desc_hi, uint32_t idesc,
+                                                 uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, t;\n\t.reg .b64 da, dl, db, dc;\n\t.reg .b32 bb;\n\t"
+        "setp.ne.b32 p, %7, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 dl, {%2, %5};\n\t"
+        "mov.b64 db, {%3, %5};\n\t"
+        "add.u32 bb, %3, %4;\n\t"
+        "mov.b64 dc, {bb, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %6, p;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], dl, db, %6, t;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, dc, %6, t;\n\t}"
+        ::"r"(tmem_d), "r"(a_h), "r"(a_l), "r"(b0), "r"(b_step), "r"(desc_hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// The six MMAs of one ring step of the chain kernel (two 16-channel stages of one term) as one asm statement; operand A in shared
+// memory (stage 1's views a_step further) ...
+__device__ __forceinline__ void mma2_step6_bf16(uint32_t tmem_d, uint32_t a_h, uint32_t a_l, uint32_t a_step, uint32_t b0, uint32_t b_tile, uint32_t desc_hi,
+                                                uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, t;\n\t.reg .b64 da, dl, db, dc;\n\t.reg .b32 bb, ah, al;\n\t"
+        "setp.ne.b32 p, %8, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "mov.b64 da, {%1, %6};\n\t"
+        "mov.b64 dl, {%2, %6};\n\t"
+        "mov.b64 db, {%4, %6};\n\t"
+        "add.u32 bb, %4, %5;\n\t"
+        "mov.b64 dc, {bb, %6};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %7, p;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], dl, db, %7, t;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, dc, %7, t;\n\t"
+        "add.u32 ah, %1, %3;\n\t"
+        "add.u32 al, %2, %3;\n\t"
+        "mov.b64 da, {ah, %6};\n\t"
+        "mov.b64 dl, {al, %6};\n\t"
+        "add.u32 bb, bb, %5;\n\t"
+        "mov.b64 db, {bb, %6};\n\t"
+        "add.u32 bb, bb, %5;\n\t"
+        "mov.b64 dc, {bb, %6};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %7, t;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], dl, db, %7, t;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, dc, %7, t;\n\t}"
+        ::"r"(tmem_d), "r"(a_h), "r"(a_l), "r"(a_step), "r"(b0), "r"(b_tile), "r"(desc_hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// ... or in tensor memory (t_h / t_l: TMEM addresses of the hi and lo halves of the packed map; stage 1 is 8 columns further).
+__device__ __forceinline__ void mma2_step6_ts_bf16(uint32_t tmem_d, uint32_t t_h, uint32_t t_l, uint32_t b0, uint32_t b_tile, uint32_t desc_hi, uint32_t idesc,
+                                                   uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, t;\n\t.reg .b64 db, dc;\n\t.reg .b32 bb, ah, al, z;\n\t"
+        "setp.ne.b32 p, %7, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "mov.b32 z, 0;\n\t"
+        "mov.b64 db, {%3, %5};\n\t"
+        "add.u32 bb, %3, %4;\n\t"
+        "mov.b64 dc, {bb, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %6, {z, z, z, z, z, z, z, z}, p;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%2], db, %6, {z, z, z, z, z, z, z, z}, t;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], dc, %6, {z, z, z, z, z, z, z, z}, t;\n\t"
+        "add.u32 ah, %1, 8;\n\t"
+        "add.u32 al, %2, 8;\n\t"
+        "add.u32 bb, bb, %4;\n\t"
+        "mov.b64 db, {bb, %5};\n\t"
+        "add.u32 bb, bb, %4;\n\t"
+        "mov.b64 dc, {bb, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [ah], db, %6, {z, z, z, z, z, z, z, z}, t;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [al], db, %6, {z, z, z, z, z, z, z, z}, t;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [ah], dc, %6, {z, z, z, z, z, z, z, z}, t;\n\t}"
+        ::"r"(tmem_d), "r"(t_h), "r"(t_l), "r"(b0), "r"(b_tile), "r"(desc_hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
 __host__ __device__ constexpr uint32_t make_idesc_bf16_m256(uint32_t n)
 {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((256u >> 4) << 24);
