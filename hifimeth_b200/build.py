@@ -10,7 +10,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libhm_engine.so"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["engine.cu", "cnn_tensor.cu", "onnx_weights.cpp", "host_record.cpp", "bgzf_bam.cpp", "call_main.cpp"]
+SOURCES = ["engine.cu", "cnn_tensor.cu", "onnx_weights.cpp", "host_record.cpp", "bgzf_bam.cpp", "fast_deflate.cpp", "call_main.cpp"]
 EXE = PKG / "bin" / "hifimeth-b200"
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]

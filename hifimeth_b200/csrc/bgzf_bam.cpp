@@ -2,6 +2,7 @@
 #include <functional>
 
 #include "bgzf_bam.h"
+#include "fast_deflate.h"
 
 #include <algorithm>
 #include <atomic>
@@ -140,6 +141,12 @@ void parallel_for(size_t n, int threads, const std::function<void(size_t)>& fn)
 
 // ---- BgzfReader ----------------------------------------------------------------------------------------------------------
 namespace {
+// HM_ZLIB_ONLY=1: every block through zlib (A/B of the codecs in fast_deflate.h; tools/bam_copy_bench.py)
+bool use_zlib_only()
+{
+    static const bool v = [] { const char* e = getenv("HM_ZLIB_ONLY"); return e && *e && *e != '0'; }();
+    return v;
+}
 constexpr size_t kRawAhead = 2;     // compressed slabs queued between the I/O thread and the drivers
 constexpr int kInflateDrivers = 2;  // slabs being inflated at the same time
 
@@ -289,6 +296,15 @@ void BgzfReader::driver_loop()
             parallel_for(rs.blks.size(), threads_, [&](size_t i) {
                 const Blk& b = rs.blks[i];
                 if (!b.isize) return;
+                {
+                    // own inflater first (fast_deflate.h); whatever it does not accept goes to zlib below, which has the last word
+                    const uint8_t* q = rs.raw.data() + b.off;
+                    const size_t xl = rd16(q + 10);
+                    if (!use_zlib_only() && hm_inflate_fast(q + 12 + xl, b.size - 12 - xl - 8, out + b.dst, b.isize)) {
+                        if (crc32(crc32(0L, Z_NULL, 0), out + b.dst, (uInt)b.isize) != rd32(q + b.size - 8)) ok = false;
+                        return;
+                    }
+                }
                 static thread_local TlInflate tl;
                 if (!tl.init) {
                     if (inflateInit2(&tl.zs, -15) != Z_OK) { ok = false; return; }
@@ -448,14 +464,23 @@ bool BgzfWriter::deflate_chunk(const Bytes& in, std::string& err)
         const size_t off = i * kBlockPayload;
         const size_t len = std::min(kBlockPayload, in.size() - off);
         Bytes& c = comp[i];
-        c.resize(18 + compressBound((uLong)len) + 8);
+        c.resize(18 + std::max<size_t>(compressBound((uLong)len), hm_deflate_rle_bound(len)) + 8);
+        size_t clen = 0;
+        if (level == 1 && !use_zlib_only()) {
+            // level 1 = run-length + Huffman, one dynamic block per BGZF block (fast_deflate.h): HiFi records are kinetics codes,
+            // packed bases and qualities -- noisy bytes in which zlib's level-1 matcher finds only short, poor matches.  On such
+            // records this is several times faster than zlib level 1 and its output is smaller than level 6's
+            clen = hm_deflate_rle(in.data() + off, len, c.data() + 18, c.size() - 18 - 8);
+            if (!clen) { ok = false; return; }
+        } else {
         // one deflate stream per thread and level for the life of the thread: deflateInit2 allocates and clears ~260 KB per call
         static thread_local TlDeflate tl;
         if (!tl.init || tl.level != level) {
             if (tl.init) deflateEnd(&tl.zs);
             tl.zs = z_stream{};
             tl.init = false;
-            if (deflateInit2(&tl.zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { ok = false; return; }
+            // (HM_ZLIB_ONLY=1 and level 1: zlib's own run-length strategy, the closest zlib has to hm_deflate_rle)
+            if (deflateInit2(&tl.zs, level, Z_DEFLATED, -15, 8, level == 1 ? Z_RLE : Z_DEFAULT_STRATEGY) != Z_OK) { ok = false; return; }
             tl.init = true;
             tl.level = level;
         } else if (deflateReset(&tl.zs) != Z_OK) { ok = false; return; }
@@ -465,8 +490,10 @@ bool BgzfWriter::deflate_chunk(const Bytes& in, std::string& err)
         zs.next_out = c.data() + 18;
         zs.avail_out = (uInt)(c.size() - 18 - 8);
         const int rc = deflate(&zs, Z_FINISH);
-        const size_t clen = zs.total_out;
-        if (rc != Z_STREAM_END || 18 + clen + 8 > 65536) { ok = false; return; }
+        clen = zs.total_out;
+        if (rc != Z_STREAM_END) { ok = false; return; }
+        }
+        if (18 + clen + 8 > 65536) { ok = false; return; }
         static const uint8_t hdr[12] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0};
         memcpy(c.data(), hdr, 12);
         c[12] = 'B'; c[13] = 'C';

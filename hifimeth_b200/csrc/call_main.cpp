@@ -36,6 +36,7 @@
 
 #include "../../include/hm_engine.h"
 #include "bgzf_bam.h"
+#include "fast_deflate.h"
 
 namespace {
 
@@ -634,6 +635,18 @@ static int call_main_impl(int argc, char** argv)
 }
 
 // Round trip of the BAM codec alone (tests): read every record of `in_path`, write it unchanged to `out_path`.
+extern "C" size_t hm_deflate_block(const uint8_t* in, size_t n, uint8_t* out, size_t cap)
+{
+    if ((!in && n) || !out) return 0;
+    return hm::hm_deflate_rle(in, n, out, cap);
+}
+
+extern "C" int hm_inflate_block(const uint8_t* in, size_t n_in, uint8_t* out, size_t n_out)
+{
+    if (!in || (!out && n_out)) return 0;
+    return hm::hm_inflate_fast(in, n_in, out, n_out) ? 1 : 0;
+}
+
 extern "C" int hm_bam_copy(const char* in_path, const char* out_path, int threads, int level)
 {
     try {

@@ -220,6 +220,11 @@ void hm_call_fast_exit(int on);
 /* Reads every record of a BAM file and writes it unchanged (block-parallel BGZF inflate / deflate); returns the number of
  * records or a negative hm_status.  Test hook for the codec. */
 int hm_bam_copy(const char* in_path, const char* out_path, int threads, int level);
+/* The raw-DEFLATE block codec behind level 1 of the writer and behind the reader (hifimeth_b200/csrc/fast_deflate.h), one BGZF
+ * payload at a time.  Test hooks: hm_deflate_block compresses in[0, n) (n <= 65535; cap >= n + 64) and returns the compressed size
+ * (0 on a bad argument); hm_inflate_block returns 1 if in[0, n_in) is a complete DEFLATE stream of exactly n_out bytes, else 0. */
+size_t hm_deflate_block(const uint8_t* in, size_t n, uint8_t* out, size_t cap);
+int hm_inflate_block(const uint8_t* in, size_t n_in, uint8_t* out, size_t n_out);
 
 /* ---- validation hooks (parity tests; need cfg.keep_debug = 1, call after hm_batch_collect) ------------ */
 

@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--extra", default="", help="extra CLI arguments, space separated")
     ap.add_argument("--warm", action="store_true", help="hold a CUDA context on every device while the CLI runs (what nvidia-persistenced "
                     "does on a production box: without it a fresh process pays the GPU's re-initialisation, ~2 s per device here)")
+    ap.add_argument("--sweep", default="", help="comma separated CORES[:ENV=VAL[:ENV=VAL]] -- one run per entry on the same BAM, pinned to "
+                    "that many host cores with taskset (-t CORES): the host-bound regime of a many-GPU box on one GPU.  One JSON line each")
     a = ap.parse_args()
     hmbuild.build()
     tmp = Path(tempfile.mkdtemp(prefix="hm_cli_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None))
@@ -58,6 +60,43 @@ def main():
         for i in range(torch.cuda.device_count()):
             torch.zeros(1, device=f"cuda:{i}")
         torch.cuda.synchronize()
+    if a.sweep:
+        for spec in a.sweep.split(","):
+            parts = spec.split(":")
+            cores = int(parts[0])
+            env = dict(os.environ)
+            env.update(dict(kv.split("=", 1) for kv in parts[1:]))
+            c = ["taskset", "-c", f"0-{cores - 1}", str(exe), "call", "--level", str(a.level), "-t", str(cores)]
+            if a.devices:
+                c += ["--devices", a.devices]
+            c += a.extra.split() + [str(src), str(dst)]
+            best = None
+            for _ in range(a.repeat):
+                t0 = time.time()
+                r = subprocess.run(c, capture_output=True, text=True, env=env)
+                wall = time.time() - t0
+                if r.returncode != 0:
+                    sys.stderr.write(r.stderr)
+                    raise SystemExit(r.returncode)
+                if best is None or wall < best[0]:
+                    best = (wall, r.stderr)
+            wall, log = best
+            sites = sum(int(x) for x in re.search(r"CpG (\d+), CHG (\d+), CHH (\d+)", log).groups())
+            tl = re.search(r"engines ready ([\d.]+), input inflated ([\d.]+), last batch collected ([\d.]+), engines destroyed ([\d.]+), output closed ([\d.]+)", log)
+            ph = re.search(r"read\+inflate ([\d.]+), engine create ([\d.]+), pack ([\d.]+), submit ([\d.]+), collect\(wait\) ([\d.]+), assemble ([\d.]+), write\+deflate ([\d.]+)", log)
+            out = {"cores": cores, "env": parts[1:], "reads": a.reads, "read_len": a.len, "level": a.level, "wall_s": round(wall, 3), "sites": sites,
+                   "sites_per_s": sites / wall, "out_bam_bytes": dst.stat().st_size, "in_bam_bytes": in_bytes}
+            if tl:
+                ready, inflated, collected, destroyed, closed = (float(x) for x in tl.groups())
+                out["timeline_s"] = {"engines_ready": ready, "input_inflated": inflated, "last_batch_collected": collected, "output_closed": closed}
+                out["steady_sites_per_s"] = sites / max(closed - ready, 1e-9)
+            if ph:
+                out["phase_s"] = dict(zip(("read_inflate", "engine_create", "pack", "submit", "collect_wait", "assemble", "write_deflate"), (float(x) for x in ph.groups())))
+            print(json.dumps(out), flush=True)
+        for p in (src, dst):
+            p.unlink(missing_ok=True)
+        tmp.rmdir()
+        return
     best = None
     for _ in range(a.repeat):
         t0 = time.time()
