@@ -43,9 +43,10 @@ namespace {
 struct Options {
     std::string model_dir, in_path, out_path, hist_path;
     int min_read_len = 1000, site_batch = 32, reads_per_batch = 10000, keep_kinetics = 0, threads = 0, ctx_mask = 7;
-    int level = 1;   // BGZF level of the output.  htslib's default (what the reference writes) is 6; measured on synthetic HiFi records: level 1
-                     // costs 3.7 % more bytes and a third of the deflate time -- with 8 host cores per GPU the queue runs at 96 % of the
-                     // device rate at level 1 and at 55 % at level 6
+    int level = 1;   // BGZF level of the output.  Level 1 = the engine's own run-length + Huffman block coder (fast_deflate.h); 2 .. 9 and 0
+                     // = zlib.  htslib's default (what the reference writes) is 6: on synthetic HiFi records that is 1.9 % LARGER than
+                     // level 1 here and takes ~8 x the deflate time -- with 8 host cores per GPU the queue ran at 55 % of the device
+                     // rate at zlib level 6
     std::vector<int> devices;   // one worker (engine) per entry; an ordinal may repeat
     long long max_bases = 0;    // 0 = chosen from the input size
 };
@@ -76,7 +77,7 @@ void usage(const char* prog, const char* cmd)
                     "  -t <Integer>  Number of CPU threads used for BAM inflate/deflate and record assembly\n"
                     "  --devices <list>  CUDA devices, comma separated; batches are dealt to one worker per entry. Default = 0\n"
                     "  --max-bases <Integer>  Bases per batch. Default: from the input size, 2 Mi .. 24 Mi\n"
-                    "  --level <Integer>  BGZF compression level of the output (6 = htslib's default: ~4 % smaller files, 3 x the deflate time). Default = 1\n"
+                    "  --level <Integer>  BGZF compression level of the output: 1 = run-length + Huffman (built in, fastest), 0 and 2-9 = zlib (6 = htslib's default). Default = 1\n"
                     "  --hist <File>  Write the per-context histograms of the ML bytes (the input of pileup's threshold rule) as TSV\n",
             default_model_dir().c_str());
 }
