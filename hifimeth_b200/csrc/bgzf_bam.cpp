@@ -141,6 +141,7 @@ void parallel_for(size_t n, int threads, const std::function<void(size_t)>& fn)
 
 // ---- BgzfReader ----------------------------------------------------------------------------------------------------------
 namespace {
+std::atomic<uint64_t> g_inflate_fallbacks{0};
 // HM_ZLIB_ONLY=1: every block through zlib (A/B of the codecs in fast_deflate.h; tools/bam_copy_bench.py)
 bool use_zlib_only()
 {
@@ -158,6 +159,8 @@ struct TlInflate {
     ~TlInflate() { if (init) inflateEnd(&zs); }
 };
 }  // namespace
+
+uint64_t bgzf_inflate_fallbacks() { return g_inflate_fallbacks.load(std::memory_order_relaxed); }
 
 BgzfReader::~BgzfReader() { close(); }
 void BgzfReader::close()
@@ -301,7 +304,7 @@ void BgzfReader::driver_loop()
                     const uint8_t* q = rs.raw.data() + b.off;
                     const size_t xl = rd16(q + 10);
                     if (!use_zlib_only() && hm_inflate_fast(q + 12 + xl, b.size - 12 - xl - 8, out + b.dst, b.isize)) {
-                        if (crc32(crc32(0L, Z_NULL, 0), out + b.dst, (uInt)b.isize) != rd32(q + b.size - 8)) ok = false;
+                        if (hm_crc32(0, out + b.dst, b.isize) != rd32(q + b.size - 8)) ok = false;
                         return;
                     }
                 }
@@ -319,8 +322,9 @@ void BgzfReader::driver_loop()
                 zs.avail_out = (uInt)b.isize;
                 const int rc = inflate(&zs, Z_FINISH);
                 if (rc != Z_STREAM_END || zs.total_out != b.isize ||
-                    crc32(crc32(0L, Z_NULL, 0), out + b.dst, (uInt)b.isize) != rd32(p + b.size - 8))
+                    hm_crc32(0, out + b.dst, b.isize) != rd32(p + b.size - 8))
                     ok = false;
+                else if (!use_zlib_only()) g_inflate_fallbacks.fetch_add(1, std::memory_order_relaxed);
             });
             if (!ok) { fail("BGZF block failed to inflate or its CRC does not match"); return; }
             std::lock_guard<std::mutex> lk(m_);
@@ -499,7 +503,7 @@ bool BgzfWriter::deflate_chunk(const Bytes& in, std::string& err)
         c[12] = 'B'; c[13] = 'C';
         wr16(c.data() + 14, 2);
         wr16(c.data() + 16, (uint32_t)(18 + clen + 8 - 1));
-        wr32(c.data() + 18 + clen, (uint32_t)crc32(crc32(0L, Z_NULL, 0), in.data() + off, (uInt)len));
+        wr32(c.data() + 18 + clen, hm_crc32(0, in.data() + off, len));
         wr32(c.data() + 18 + clen + 4, (uint32_t)len);
         c.resize(18 + clen + 8);
     });

@@ -38,6 +38,10 @@ struct NoInitAlloc : std::allocator<T> {
 };
 using Bytes = std::vector<uint8_t, NoInitAlloc<uint8_t>>;
 
+// BGZF blocks the built-in inflater (fast_deflate.h) did not accept and zlib then read correctly, since the start of the process.
+// Zero on well-formed input; anything else is a defect of the built-in inflater worth reporting (the data is still right).
+uint64_t bgzf_inflate_fallbacks();
+
 // One inflated stretch of the input.  Record bodies handed out by BamReader point into `data`, or -- for a record that
 // straddles two slabs -- into one of the `extra` buffers of the slab it ends in; both stay valid while the slab is alive.
 struct Slab {

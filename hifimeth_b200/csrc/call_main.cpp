@@ -605,6 +605,9 @@ static int call_main_impl(int argc, char** argv)
                     "collect(wait) %.2f, assemble %.2f, write+deflate %.2f; %llu batches of <= %lld bases on %d worker(s), %d host threads\n",
             S.us_read / 1e6, S.us_create / 1e6, S.us_pack / 1e6, S.us_submit / 1e6, S.us_collect / 1e6, S.us_assemble / 1e6, S.us_write / 1e6,
             (unsigned long long)S.n_batches.load(), opt.max_bases, n_workers, opt.threads);
+    if (hm::bgzf_inflate_fallbacks())
+        fprintf(stderr, "[hifimeth-b200] note: %llu BGZF block(s) were not accepted by the built-in inflater and were read by zlib instead (output unaffected)\n",
+                (unsigned long long)hm::bgzf_inflate_fallbacks());
     fprintf(stderr, "[hifimeth-b200] timeline (s since start): engines ready %.2f, input inflated %.2f, last batch collected %.2f, engines "
                     "destroyed %.2f, output closed %.2f\n",
             S.at_ready / 1e6, S.at_input_done / 1e6, S.at_last_collect / 1e6, S.at_destroyed / 1e6, secs);
@@ -647,6 +650,8 @@ extern "C" int hm_inflate_block(const uint8_t* in, size_t n_in, uint8_t* out, si
     if (!in || (!out && n_out)) return 0;
     return hm::hm_inflate_fast(in, n_in, out, n_out) ? 1 : 0;
 }
+
+extern "C" uint32_t hm_crc32_bytes(uint32_t crc, const uint8_t* data, size_t n) { return (!data && n) ? crc : hm::hm_crc32(crc, data, n); }
 
 extern "C" int hm_bam_copy(const char* in_path, const char* out_path, int threads, int level)
 {

@@ -5,6 +5,11 @@
 #include <algorithm>
 #include <cstring>
 
+#include <zlib.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
 namespace hm {
 namespace {
 
@@ -566,6 +571,63 @@ bool hm_inflate_fast(const uint8_t* in, size_t n_in, uint8_t* out, size_t n_out)
         if (bfinal) break;
     }
     return br.inside() && op == out_end;
+}
+
+// ---- CRC-32 ---------------------------------------------------------------------------------------------------------------
+#if defined(__x86_64__)
+namespace {
+// Folds data[0, n) (n a multiple of 16, n >= 64) into 16 bytes that continue to the same CRC: x^k mod P constants of the
+// reflected polynomial for k = 4*128 +- 32 (four lanes in flight) and 128 +- 32 (one lane).
+__attribute__((target("pclmul,sse4.1")))
+void crc32_fold(uint32_t raw_state, const uint8_t* data, size_t n, uint8_t out[16])
+{
+    const __m128i k1k2 = _mm_set_epi64x(0x1c6e41596ll, 0x154442bd4ll);
+    const __m128i k3k4 = _mm_set_epi64x(0x0ccaa009ell, 0x1751997d0ll);
+    const __m128i* p = reinterpret_cast<const __m128i*>(data);
+    __m128i x1 = _mm_xor_si128(_mm_loadu_si128(p), _mm_cvtsi32_si128((int)raw_state));
+    __m128i x2 = _mm_loadu_si128(p + 1), x3 = _mm_loadu_si128(p + 2), x4 = _mm_loadu_si128(p + 3);
+    p += 4;
+    n -= 64;
+    while (n >= 64) {
+        const __m128i l1 = _mm_clmulepi64_si128(x1, k1k2, 0x00), l2 = _mm_clmulepi64_si128(x2, k1k2, 0x00);
+        const __m128i l3 = _mm_clmulepi64_si128(x3, k1k2, 0x00), l4 = _mm_clmulepi64_si128(x4, k1k2, 0x00);
+        x1 = _mm_xor_si128(_mm_xor_si128(_mm_clmulepi64_si128(x1, k1k2, 0x11), l1), _mm_loadu_si128(p));
+        x2 = _mm_xor_si128(_mm_xor_si128(_mm_clmulepi64_si128(x2, k1k2, 0x11), l2), _mm_loadu_si128(p + 1));
+        x3 = _mm_xor_si128(_mm_xor_si128(_mm_clmulepi64_si128(x3, k1k2, 0x11), l3), _mm_loadu_si128(p + 2));
+        x4 = _mm_xor_si128(_mm_xor_si128(_mm_clmulepi64_si128(x4, k1k2, 0x11), l4), _mm_loadu_si128(p + 3));
+        p += 4;
+        n -= 64;
+    }
+#define HM_FOLD1(a, next) _mm_xor_si128(_mm_xor_si128(_mm_clmulepi64_si128(a, k3k4, 0x11), _mm_clmulepi64_si128(a, k3k4, 0x00)), next)
+    x1 = HM_FOLD1(x1, x2);
+    x1 = HM_FOLD1(x1, x3);
+    x1 = HM_FOLD1(x1, x4);
+    while (n >= 16) {
+        x1 = HM_FOLD1(x1, _mm_loadu_si128(p));
+        ++p;
+        n -= 16;
+    }
+#undef HM_FOLD1
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(out), x1);
+}
+}  // namespace
+#endif
+
+uint32_t hm_crc32(uint32_t crc, const uint8_t* data, size_t n)
+{
+#if defined(__x86_64__)
+    static const bool have = __builtin_cpu_supports("pclmul") && __builtin_cpu_supports("sse4.1");
+    if (have && n >= 128) {
+        const size_t bulk = n & ~(size_t)15;
+        uint8_t rem[16];
+        crc32_fold(~crc, data, bulk, rem);
+        // the 16 folded bytes stand for everything read so far: their CRC from the all-zero state, then the tail
+        uint32_t c = (uint32_t)crc32(0xffffffffu, rem, 16);
+        if (n > bulk) c = (uint32_t)crc32(c, data + bulk, (uInt)(n - bulk));
+        return c;
+    }
+#endif
+    return (uint32_t)crc32(crc, data, (uInt)n);
 }
 
 }  // namespace hm

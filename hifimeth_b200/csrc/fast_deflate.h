@@ -27,4 +27,9 @@ size_t hm_deflate_rle(const uint8_t* in, size_t n, uint8_t* out, size_t cap);
 // block inside the input and produces exactly n_out bytes.  Never reads outside in[0, n_in) or writes outside out[0, n_out).
 bool hm_inflate_fast(const uint8_t* in, size_t n_in, uint8_t* out, size_t n_out);
 
+// CRC-32 of the gzip trailer (reflected 0x04C11DB7), continuing from `crc` like zlib's crc32().  On x86-64 with PCLMULQDQ the bulk is
+// folded 64 bytes per iteration with carry-less multiplies (Gopal et al., "Fast CRC Computation for Generic Polynomials Using
+// PCLMULQDQ Instruction", Intel 2009); the last 16-byte remainder and the tail go through zlib's table code.  Elsewhere: zlib.
+uint32_t hm_crc32(uint32_t crc, const uint8_t* data, size_t n);
+
 }  // namespace hm

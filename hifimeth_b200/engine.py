@@ -63,7 +63,7 @@ class hm_timing(C.Structure):
 
 ABI_SYMBOLS = ["hm_engine_create", "hm_engine_destroy", "hm_last_error", "hm_version", "hm_batch_acquire", "hm_batch_submit",
                "hm_batch_collect", "hm_batch_timing", "hm_model_weights", "hm_codev1_encode", "hm_codev1_decode", "hm_pack_record", "hm_pack_records",
-               "hm_mod_record_bound", "hm_build_mod_record", "hm_build_mod_record_mm", "hm_parse_mod_record", "hm_ml_threshold", "hm_call_main", "hm_call_fast_exit", "hm_bam_copy", "hm_deflate_block", "hm_inflate_block", "hm_debug_dump_decode", "hm_debug_dump_ctx",
+               "hm_mod_record_bound", "hm_build_mod_record", "hm_build_mod_record_mm", "hm_parse_mod_record", "hm_ml_threshold", "hm_call_main", "hm_call_fast_exit", "hm_bam_copy", "hm_deflate_block", "hm_inflate_block", "hm_crc32_bytes", "hm_debug_dump_decode", "hm_debug_dump_ctx",
                "hm_debug_dump_features", "hm_debug_dump_logits", "hm_debug_dump_xmap", "hm_debug_dump_acts", "hm_debug_dense_op", "hm_debug_last_op_ms", "hm_microbench"]
 
 _lib = None
@@ -110,6 +110,8 @@ def load_library() -> C.CDLL:
     L.hm_deflate_block.restype = C.c_size_t
     L.hm_inflate_block.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
     L.hm_inflate_block.restype = C.c_int
+    L.hm_crc32_bytes.argtypes = [C.c_uint32, C.c_void_p, C.c_size_t]
+    L.hm_crc32_bytes.restype = C.c_uint32
     L.hm_debug_dump_decode.argtypes = [C.c_void_p, C.c_int, _u16p, _u16p, _u16p, _u16p, _u8p, _u8p]
     L.hm_debug_dump_ctx.argtypes = [C.c_void_p, C.c_int, _u8p]
     L.hm_debug_dump_features.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, _f32p]

@@ -225,6 +225,8 @@ int hm_bam_copy(const char* in_path, const char* out_path, int threads, int leve
  * (0 on a bad argument); hm_inflate_block returns 1 if in[0, n_in) is a complete DEFLATE stream of exactly n_out bytes, else 0. */
 size_t hm_deflate_block(const uint8_t* in, size_t n, uint8_t* out, size_t cap);
 int hm_inflate_block(const uint8_t* in, size_t n_in, uint8_t* out, size_t n_out);
+/* CRC-32 of BGZF trailers as the reader / writer compute it (carry-less-multiply folding on x86-64); same contract as zlib's crc32(). */
+uint32_t hm_crc32_bytes(uint32_t crc, const uint8_t* data, size_t n);
 
 /* ---- validation hooks (parity tests; need cfg.keep_debug = 1, call after hm_batch_collect) ------------ */
 

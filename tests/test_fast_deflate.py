@@ -150,3 +150,19 @@ def test_inflate_block_survives_bit_flips(lib):
                 ref_ok = False
             if ok:
                 assert ref_ok and back == ref
+
+
+def test_crc32_matches_zlib_for_every_length_alignment_and_start_value(lib):
+    rng = np.random.default_rng(21)
+    data = rng.integers(0, 256, 70000, dtype=np.uint8).tobytes()
+    buf = C.create_string_buffer(data, len(data))
+    base = C.addressof(buf)
+    for n in list(range(0, 300)) + [511, 512, 513, 4095, 4096, 4097, 0xff00, 65535, 70000 - 3]:
+        for off in (0, 1, 3):
+            for start in (0, 0x12345678, 0xffffffff):
+                assert lib.hm_crc32_bytes(start, base + off, n) == zlib.crc32(data[off:off + n], start), (n, off, start)
+    # continuing a CRC piecewise is the same as one call
+    c = 0
+    for lo, hi in ((0, 1000), (1000, 1017), (1017, 40000), (40000, 70000)):
+        c = lib.hm_crc32_bytes(c, base + lo, hi - lo)
+    assert c == zlib.crc32(data)
