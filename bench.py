@@ -69,7 +69,38 @@ class ClockSampler:
         self.t_mark = time.perf_counter()
 
     def start(self):
+        """In-process NVML polling (50 ms) when nvidia_ml_py is importable: it answers from the first poll, where a fresh nvidia-smi
+        needed longer than a whole 8-GPU bench run before its first line.  nvidia-smi -lms otherwise."""
         try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            reasons_fn(h)
+            self.nvml_stop = threading.Event()
+
+            def poll():
+                # NVML reason bits: 0x4 sw_power_cap, 0x8 hw_slowdown, 0x20 sw_thermal_slowdown, 0x40 hw_thermal_slowdown
+                while not self.nvml_stop.is_set():
+                    try:
+                        sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        r = int(reasons_fn(h))
+                        act = lambda bit: "Active" if r & bit else "Not Active"
+                        self.rows.append((time.perf_counter(), [str(sm), str(mx), "", act(0x8), act(0x40), act(0x20), act(0x4)]))
+                    except Exception:
+                        pass
+                    self.nvml_stop.wait(0.05)
+
+            threading.Thread(target=poll, daemon=True).start()
+            self.source = "nvml"
+            return
+        except Exception:
+            self.nvml_stop = None
+        try:
+            self.source = "nvidia-smi"
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
@@ -81,6 +112,8 @@ class ClockSampler:
             self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
+        if getattr(self, "nvml_stop", None) is not None:
+            self.nvml_stop.set()
         if self.proc:
             self.proc.terminate()
         timed = [r for t, r in self.rows if self.t_mark is None or t >= self.t_mark]
@@ -96,7 +129,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
-                "window": window}
+                "window": window, "source": getattr(self, "source", None)}
 
 
 def physical_cores() -> int:

@@ -14,6 +14,8 @@
 #include <cstring>
 #include <thread>
 
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <zlib.h>
 
 namespace hm {
@@ -174,6 +176,9 @@ void BgzfReader::close()
     for (auto& d : drivers_)
         if (d.joinable()) d.join();
     drivers_.clear();
+    if (map_) munmap(const_cast<uint8_t*>(map_), map_size_);
+    map_ = nullptr;
+    map_size_ = map_pos_ = 0;
     if (f_) fclose(f_);
     f_ = nullptr;
     raw_q_.clear();
@@ -189,6 +194,21 @@ bool BgzfReader::open(const char* path, int threads, std::string& err)
     slab_bytes_ = kReadSlab;
     if (const char* e = getenv("HM_BGZF_SLAB")) slab_bytes_ = std::max<size_t>(1024, (size_t)atoll(e));  // tests: force records to straddle slabs
     carry_.clear();
+    // A regular file is mapped instead of read: fread() is one more copy of every compressed byte on ONE thread -- 14 GB for the
+    // 8-GPU bench input, seconds of a run whose GPUs need 2.7 s.  Pipes and HM_NO_MMAP=1 keep the fread path.
+    {
+        struct stat sb;
+        const char* no = getenv("HM_NO_MMAP");
+        if (!(no && *no && *no != '0') && fstat(fileno(f_), &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
+            void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fileno(f_), 0);
+            if (m != MAP_FAILED) {
+                map_ = static_cast<const uint8_t*>(m);
+                map_size_ = (size_t)sb.st_size;
+                map_pos_ = 0;
+                madvise(m, map_size_, MADV_SEQUENTIAL);
+            }
+        }
+    }
     eof_ = io_done_ = stop_ = false;
     next_seq_ = n_slabs_ = 0;
     err_.clear();
@@ -247,6 +267,34 @@ bool BgzfReader::read_raw(RawSlab& rs, std::string& err)
     }
 }
 
+// The mapped form of read_raw: a slab is a run of whole blocks of the mapping, nothing is copied.
+bool BgzfReader::read_raw_mapped(RawSlab& rs, std::string& err)
+{
+    for (;;) {
+        rs.blks.clear();
+        rs.total = 0;
+        if (map_pos_ >= map_size_) return false;
+        const uint8_t* base = map_ + map_pos_;
+        const size_t avail = map_size_ - map_pos_;
+        size_t off = 0;
+        while (off < avail && off < slab_bytes_) {
+            bool bad;
+            const size_t bs = bgzf_block_size(base + off, avail - off, bad);
+            if (bad) { err = "not a BGZF block (is the input a BAM file?)"; return false; }
+            if (!bs || off + bs > avail) { err = "truncated BGZF block at end of file"; return false; }
+            if (bs < 12 + (size_t)rd16(base + off + 10) + 2 + 8) { err = "corrupt BGZF block (BSIZE smaller than its own header and trailer)"; return false; }
+            const size_t isize = rd32(base + off + bs - 4);
+            if (isize > 65536) { err = "corrupt BGZF block (ISIZE above 64 KiB)"; return false; }
+            rs.blks.push_back({off, bs, isize, rs.total});
+            rs.total += isize;
+            off += bs;
+        }
+        rs.base = base;
+        map_pos_ += off;
+        if (rs.total) return true;  // else only empty blocks (EOF markers): look for more
+    }
+}
+
 void BgzfReader::io_loop()
 {
     uint64_t seq = 0;
@@ -254,7 +302,7 @@ void BgzfReader::io_loop()
         for (;;) {
             RawSlab rs;
             std::string err;
-            if (!read_raw(rs, err)) {
+            if (!(map_ ? read_raw_mapped(rs, err) : read_raw(rs, err))) {
                 if (!err.empty()) { fail(err); return; }
                 break;
             }
@@ -301,7 +349,7 @@ void BgzfReader::driver_loop()
                 if (!b.isize) return;
                 {
                     // own inflater first (fast_deflate.h); whatever it does not accept goes to zlib below, which has the last word
-                    const uint8_t* q = rs.raw.data() + b.off;
+                    const uint8_t* q = (rs.base ? rs.base : rs.raw.data()) + b.off;
                     const size_t xl = rd16(q + 10);
                     if (!use_zlib_only() && hm_inflate_fast(q + 12 + xl, b.size - 12 - xl - 8, out + b.dst, b.isize)) {
                         if (hm_crc32(0, out + b.dst, b.isize) != rd32(q + b.size - 8)) ok = false;
@@ -313,7 +361,7 @@ void BgzfReader::driver_loop()
                     if (inflateInit2(&tl.zs, -15) != Z_OK) { ok = false; return; }
                     tl.init = true;
                 } else if (inflateReset(&tl.zs) != Z_OK) { ok = false; return; }
-                const uint8_t* p = rs.raw.data() + b.off;
+                const uint8_t* p = (rs.base ? rs.base : rs.raw.data()) + b.off;
                 const size_t xlen = rd16(p + 10);
                 z_stream& zs = tl.zs;
                 zs.next_in = const_cast<Bytef*>(p + 12 + xlen);
@@ -375,6 +423,13 @@ BgzfWriter::~BgzfWriter()
         cv_.notify_all();
     }
     if (bg_.joinable()) bg_.join();
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        io_end_ = true;
+        wq_.clear();
+        cv_.notify_all();
+    }
+    if (io_.joinable()) io_.join();
     if (f_) fclose(f_);
 }
 
@@ -387,8 +442,10 @@ bool BgzfWriter::open(const char* path, int threads, int level, std::string& err
     pending_.clear();
     q_.clear();
     bg_err_.clear();
-    end_ = false;
+    wq_.clear();
+    end_ = io_end_ = false;
     bg_ = std::thread(&BgzfWriter::bg_loop, this);
+    io_ = std::thread(&BgzfWriter::io_loop, this);
     return true;
 }
 
@@ -400,6 +457,18 @@ bool BgzfWriter::write(const void* data, size_t n, std::string& err)
     const uint8_t* p = static_cast<const uint8_t*>(data);
     pending_.insert(pending_.end(), p, p + n);
     if (pending_.size() >= kWriteBatch * kBlockPayload) return hand_over(false, err);
+    return true;
+}
+
+bool BgzfWriter::write_owned(Bytes&& piece, std::string& err)
+{
+    if (!hand_over(true, err)) return false;  // what write() collected so far goes first
+    if (piece.empty()) return true;
+    std::unique_lock<std::mutex> lk(m_);
+    cv_.wait(lk, [&] { return q_.size() < 2 || !bg_err_.empty(); });
+    if (!bg_err_.empty()) { err = bg_err_; return false; }
+    q_.push_back(std::move(piece));
+    cv_.notify_all();
     return true;
 }
 
@@ -508,9 +577,37 @@ bool BgzfWriter::deflate_chunk(const Bytes& in, std::string& err)
         c.resize(18 + clen + 8);
     });
     if (!ok) { err = "deflate failed"; return false; }
-    for (auto& c : comp)
-        if (fwrite(c.data(), 1, c.size(), f_) != c.size()) { err = "write error"; return false; }
+    // to the file-write stage (at most two chunks ahead of it)
+    std::unique_lock<std::mutex> lk(m_);
+    cv_.wait(lk, [&] { return wq_.size() < 2 || !bg_err_.empty(); });
+    if (!bg_err_.empty()) { err = bg_err_; return false; }
+    wq_.push_back(std::move(comp));
+    cv_.notify_all();
     return true;
+}
+
+void BgzfWriter::io_loop()
+{
+    for (;;) {
+        std::vector<Bytes> comp;
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            cv_.wait(lk, [&] { return !wq_.empty() || io_end_; });
+            if (wq_.empty()) return;
+            comp = std::move(wq_.front());
+            wq_.pop_front();
+            cv_.notify_all();
+        }
+        for (auto& c : comp)
+            if (fwrite(c.data(), 1, c.size(), f_) != c.size()) {
+                std::lock_guard<std::mutex> lk(m_);
+                if (bg_err_.empty()) bg_err_ = "write error";
+                q_.clear();
+                wq_.clear();
+                cv_.notify_all();
+                return;
+            }
+    }
 }
 
 bool BgzfWriter::close(std::string& err)
@@ -523,6 +620,12 @@ bool BgzfWriter::close(std::string& err)
         cv_.notify_all();
     }
     if (bg_.joinable()) bg_.join();
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        io_end_ = true;
+        cv_.notify_all();
+    }
+    if (io_.joinable()) io_.join();
     if (ok && !bg_err_.empty()) { err = bg_err_; ok = false; }
     static const uint8_t eof_marker[28] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (ok && fwrite(eof_marker, 1, 28, f_) != 28) { err = "write error"; ok = false; }

@@ -65,6 +65,7 @@ public:
 private:
     struct Blk { size_t off, size, isize, dst; };
     struct RawSlab {
+        const uint8_t* base = nullptr;  // mapped input: the blocks lie here; otherwise in raw
         Bytes raw;                 // whole BGZF blocks
         std::vector<Blk> blks;
         size_t total = 0;          // inflated bytes
@@ -73,6 +74,9 @@ private:
     void io_loop();
     void driver_loop();
     bool read_raw(RawSlab& rs, std::string& err);   // false at end of file or on error (err set)
+    bool read_raw_mapped(RawSlab& rs, std::string& err);
+    const uint8_t* map_ = nullptr;  // regular files are mapped: the pool threads inflate straight from the page cache
+    size_t map_size_ = 0, map_pos_ = 0;
     void fail(const std::string& err);
     FILE* f_ = nullptr;
     int threads_ = 1;
@@ -95,11 +99,15 @@ public:
     ~BgzfWriter();
     bool open(const char* path, int threads, int level, std::string& err);
     bool write(const void* data, size_t n, std::string& err);
+    // A finished piece of the stream, taken over without a copy: what was written before goes out first (closing its last block
+    // short), then the piece becomes deflate work of its own.
+    bool write_owned(Bytes&& piece, std::string& err);
     bool close(std::string& err);  // flushes, writes the BGZF end-of-file marker
 
 private:
     bool hand_over(bool all, std::string& err);   // whole blocks (all: everything) of pending_ -> the background thread
     void bg_loop();
+    void io_loop();              // writes the deflated chunks to the file, in order, while the next chunk is being deflated
     bool deflate_chunk(const Bytes& in, std::string& err);
     FILE* f_ = nullptr;
     int threads_ = 1, level_ = 6;
@@ -110,6 +118,9 @@ private:
     std::deque<Bytes> q_;
     bool end_ = false;
     std::string bg_err_;
+    std::thread io_;
+    std::deque<std::vector<Bytes>> wq_;   // deflated chunks (one Bytes per BGZF block) waiting for the file write
+    bool io_end_ = false;
 };
 
 struct BamHeader {
@@ -138,6 +149,8 @@ class BamWriter {
 public:
     bool open(const char* path, int threads, int level, const BamHeader& hdr, std::string& err);
     bool write_record(const uint8_t* body, size_t len, std::string& err);
+    // records already in stream form (block_size + body each), handed over without a copy
+    bool write_chunk(Bytes&& records, std::string& err) { return z_.write_owned(std::move(records), err); }
     bool close(std::string& err);
 
 private:

@@ -171,8 +171,8 @@ struct RawBatch {
 // The records of one batch after the engine: assembled output bodies, ready to be written in order.
 struct OutBatch {
     uint64_t seq = 0;
-    hm::Bytes obuf;  // overwritten completely: no zero fill (bgzf_bam.h)
-    std::vector<size_t> ooff, olen;
+    hm::Bytes obuf;  // the batch's records as they go into the BAM stream: block_size + body, one after the other (no zero fill: bgzf_bam.h)
+    std::vector<size_t> ooff, olen;  // assembly only: bounded slot and final length of every record
 };
 
 // Bounded multi-producer / multi-consumer queue; close() wakes everybody (pop then drains what is left).
@@ -420,14 +420,14 @@ void gpu_worker_body(Shared& S, int device, int threads)
                 nc = calls.call_off[r + 1] - calls.call_off[r];
                 text = calls.mm_off[r + 1] - calls.mm_off[r];
             }
-            ob.ooff[i + 1] = ob.ooff[i] + f.raw.entries[i].len + 64 + nc + text;
+            ob.ooff[i + 1] = ob.ooff[i] + 4 + f.raw.entries[i].len + 64 + nc + text;  // 4: the record's block_size field
         }
         ob.obuf.resize(ob.ooff.back());
         std::atomic<int> bad{-1};
         hm::parallel_for(n, threads, [&](size_t i) {
             const Entry& e = f.raw.entries[i];
             const uint8_t* body = e.body;
-            uint8_t* dst = ob.obuf.data() + ob.ooff[i];
+            uint8_t* dst = ob.obuf.data() + ob.ooff[i] + 4;
             const int32_t ri = f.read_index[i];
             int rc;
             if (ri < 0) {
@@ -446,6 +446,23 @@ void gpu_worker_body(Shared& S, int device, int threads)
             if (rc != 0) bad = (int)i;
         });
         if (bad >= 0) { S.fail("cannot assemble output record " + std::to_string(bad.load()) + " of batch " + std::to_string(ob.seq)); return false; }
+        // Close the gaps between the bounded slots, here on the worker: the one writer thread used to copy every record into the
+        // BGZF writer's buffer (and that buffer once more into deflate chunks) -- two serial passes over the whole output, 5 GB at
+        // 8 GPUs.  The batch now reaches the writer as one finished piece of the BAM stream (BamWriter::write_chunk).
+        {
+            size_t w_off = 0;
+            uint8_t* base = ob.obuf.data();
+            for (size_t i = 0; i < n; ++i) {
+                const size_t len = ob.olen[i];
+                const uint32_t l32 = (uint32_t)len;
+                if (w_off != ob.ooff[i]) memmove(base + w_off + 4, base + ob.ooff[i] + 4, len);
+                memcpy(base + w_off, &l32, 4);  // little-endian host (x86-64 / aarch64)
+                w_off += 4 + len;
+            }
+            ob.obuf.resize(w_off);
+            ob.ooff.clear();
+            ob.olen.clear();
+        }
         f.raw = RawBatch{};
         f.live = false;
         S.us_assemble += w.lap_us();
@@ -498,8 +515,7 @@ void writer_body(Shared& S, hm::BamWriter& out)
         OutBatch b;
         if (!S.outbox.take(seq, b)) break;
         sw.lap_us();
-        for (size_t i = 0; i < b.olen.size(); ++i)
-            if (!out.write_record(b.obuf.data() + b.ooff[i], b.olen[i], err)) { S.fail(S.opt.out_path + ": " + err); return; }
+        if (!out.write_chunk(std::move(b.obuf), err)) { S.fail(S.opt.out_path + ": " + err); return; }
         S.us_write += sw.lap_us();
     }
 }
@@ -660,15 +676,33 @@ extern "C" int hm_bam_copy(const char* in_path, const char* out_path, int thread
     hm::BamReader in;
     hm::BamHeader hdr;
     if (!in.open(in_path, threads, hdr, err)) return HM_ERR_FORMAT;
-    hm::BamWriter out;
-    if (!out.open(out_path, threads, level, hdr, err)) return HM_ERR_ARG;
     const uint8_t* body;
     size_t len;
     long long n = 0;
+    if (level < 0 || !out_path) {  // reader only: inflate, frame, count
+        while (in.next(body, len, err)) ++n;
+        return err.empty() ? (int)std::min<long long>(n, 0x7fffffff) : HM_ERR_FORMAT;
+    }
+    hm::BamWriter out;
+    const bool pieces = level >= 100;  // 100 + level: hand the records over in finished pieces, as `call` does (BamWriter::write_chunk)
+    if (pieces) level -= 100;
+    if (!out.open(out_path, threads, level, hdr, err)) return HM_ERR_ARG;
+    hm::Bytes piece;
     while (in.next(body, len, err)) {
-        if (!out.write_record(body, len, err)) return HM_ERR_ARG;
+        if (pieces) {
+            const uint32_t l32 = (uint32_t)len;
+            const size_t at = piece.size();
+            piece.resize(at + 4 + len);
+            memcpy(piece.data() + at, &l32, 4);
+            memcpy(piece.data() + at + 4, body, len);
+            if (piece.size() >= (n % 3 ? (size_t)32 << 20 : (size_t)100000)) {  // large and small pieces alternate
+                if (!out.write_chunk(std::move(piece), err)) return HM_ERR_ARG;
+                piece = hm::Bytes();
+            }
+        } else if (!out.write_record(body, len, err)) return HM_ERR_ARG;
         ++n;
     }
+    if (pieces && !piece.empty() && !out.write_chunk(std::move(piece), err)) return HM_ERR_ARG;
     if (!err.empty()) return HM_ERR_FORMAT;
     if (!out.close(err)) return HM_ERR_ARG;
     return (int)std::min<long long>(n, 0x7fffffff);

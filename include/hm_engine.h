@@ -218,7 +218,8 @@ int hm_call_main(int argc, char** argv);
  * threads -- for executables that leave through _exit() right after (hifimeth_b200/csrc/main.cpp).  Default: join. */
 void hm_call_fast_exit(int on);
 /* Reads every record of a BAM file and writes it unchanged (block-parallel BGZF inflate / deflate); returns the number of
- * records or a negative hm_status.  Test hook for the codec. */
+ * records or a negative hm_status.  level < 0 (or out_path NULL): read and count only; 100 + level: the writer gets
+ * the records in finished pieces (the hand-over `call` uses) instead of one by one.  Test hook for the codec. */
 int hm_bam_copy(const char* in_path, const char* out_path, int threads, int level);
 /* The raw-DEFLATE block codec behind level 1 of the writer and behind the reader (hifimeth_b200/csrc/fast_deflate.h), one BGZF
  * payload at a time.  Test hooks: hm_deflate_block compresses in[0, n) (n <= 65535; cap >= n + 64) and returns the compressed size

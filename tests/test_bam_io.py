@@ -176,3 +176,26 @@ def test_reader_and_writer_pipelines_keep_file_order(lib_built, tmp_path, monkey
     for rep in range(4):
         assert lib.hm_bam_copy(str(src).encode(), str(dst).encode(), 8, 1 + rep % 2) == len(bodies)
         assert synth.read_bam(dst)[2] == bodies
+
+
+def test_reader_paths_and_piecewise_writer_agree(lib_built, tmp_path, monkeypatch):
+    """The mapped and the fread input paths, the read-only mode, and the writer fed with finished pieces of the stream (what `call`
+    hands over: large and small pieces, each closing its last BGZF block short) all give the same records."""
+    _, reads = synth.make_reads(60, (300, 12000), seed=17, flag_rev_every=4)
+    bodies = [synth.record_body(r) for r in reads]
+    src, dst = tmp_path / "in.bam", tmp_path / "out.bam"
+    synth.write_bam(src, bodies, level=6, block=40000)
+    lib = hme.load_library()
+    for no_mmap in ("0", "1"):
+        monkeypatch.setenv("HM_NO_MMAP", no_mmap)
+        assert lib.hm_bam_copy(str(src).encode(), None, 3, -1) == len(bodies)          # read only
+        for level in (101, 106, 1):
+            assert lib.hm_bam_copy(str(src).encode(), str(dst).encode(), 3, level) == len(bodies)
+            text, refs, got = synth.read_bam(dst)
+            assert got == bodies and text == synth.read_bam(src)[0]
+            assert dst.read_bytes()[-28:-12] == bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0])
+    # a mapped file that ends inside a block is an error on this path too
+    cut = tmp_path / "cut.bam"
+    cut.write_bytes(src.read_bytes()[:-40])
+    monkeypatch.setenv("HM_NO_MMAP", "0")
+    assert lib.hm_bam_copy(str(cut).encode(), None, 2, -1) < 0
