@@ -199,3 +199,21 @@ def test_reader_paths_and_piecewise_writer_agree(lib_built, tmp_path, monkeypatc
     cut.write_bytes(src.read_bytes()[:-40])
     monkeypatch.setenv("HM_NO_MMAP", "0")
     assert lib.hm_bam_copy(str(cut).encode(), None, 2, -1) < 0
+
+
+def test_zlib_only_switch_gives_the_same_records(lib_built, tmp_path):
+    """HM_ZLIB_ONLY=1 (read once per process, hence the subprocess): every block through zlib -- the path that also arbitrates
+    blocks the built-in inflater rejects.  Same records, and a level-1 file any inflater reads."""
+    import os
+    import subprocess
+    import sys
+
+    _, reads = synth.make_reads(30, (300, 9000), seed=23)
+    bodies = [synth.record_body(r) for r in reads]
+    src, dst = tmp_path / "in.bam", tmp_path / "out.bam"
+    synth.write_bam(src, bodies, level=6)
+    code = ("import sys; from hifimeth_b200 import engine as e; L = e.load_library(); "
+            f"sys.exit(0 if L.hm_bam_copy({str(src)!r}.encode(), {str(dst)!r}.encode(), 3, 1) == {len(bodies)} else 1)")
+    env = dict(os.environ, HM_ZLIB_ONLY="1", PYTHONPATH=str(hme.PKG.parent))
+    assert subprocess.run([sys.executable, "-c", code], env=env).returncode == 0
+    assert synth.read_bam(dst)[2] == bodies
