@@ -456,14 +456,17 @@ int hm_engine_create(const hm_config* cfg, hm_engine** out)
     *out = nullptr;
     if (cfg->n_slots < 1 || cfg->n_slots > 4 || cfg->max_reads == 0 || cfg->max_bases == 0 || cfg->max_bases >= 0x7fffffffu)
         return fail(nullptr, HM_ERR_ARG, "hm_engine_create: bad capacities (slots %d, reads %u, bases %u)", cfg->n_slots, cfg->max_reads, cfg->max_bases);
+    const auto t_enter = std::chrono::steady_clock::now();
     int ndev = 0;
     cudaError_t st = cudaGetDeviceCount(&ndev);
+    const auto t_count = std::chrono::steady_clock::now();
     if (st != cudaSuccess || ndev == 0)
         return fail(nullptr, HM_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU fallback", st == cudaSuccess ? "device count 0" : cudaGetErrorString(st));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, HM_ERR_ARG, "device %d out of range (0..%d)", cfg->device, ndev - 1);
     cudaDeviceProp prop;
     if ((st = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) return fail(nullptr, HM_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(st));
     if (prop.major != 10) return fail(nullptr, HM_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+    const auto t_prop = std::chrono::steady_clock::now();
     if ((st = cudaSetDevice(cfg->device)) != cudaSuccess) return fail(nullptr, HM_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(st));
 
     // HM_VERBOSE=1: wall-clock of the creation stages on stderr (context, models + plan lowering, slot allocation)
@@ -513,8 +516,9 @@ int hm_engine_create(const hm_config* cfg, hm_engine** out)
             if ((rc = alloc_slot(e, s))) break;
     }
     if (verbose)
-        fprintf(stderr, "[hm_engine_create] device %d: context %.3f s, models + plan %.3f s, %d slot(s) %.3f s\n", cfg->device, secs(t0, t1), secs(t1, t2),
-                e->n_slots, secs(t2, now()));
+        fprintf(stderr, "[hm_engine_create] device %d: runtime start (cudaGetDeviceCount) %.3f s, cudaGetDeviceProperties %.3f s, cudaSetDevice %.3f s, "
+                        "context (cudaFree(0)) %.3f s, models + plan %.3f s, %d slot(s) %.3f s\n",
+                cfg->device, secs(t_enter, t_count), secs(t_count, t_prop), secs(t_prop, t0), secs(t0, t1), secs(t1, t2), e->n_slots, secs(t2, now()));
     if (rc != HM_OK) {
         fail(nullptr, rc, "%s", e->err.c_str());
         hm_engine_destroy(e);
