@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <memory>
 
 #include <zlib.h>
 #if defined(__x86_64__)
@@ -426,8 +427,9 @@ struct BitReader {
 
 bool hm_inflate_fast(const uint8_t* in, size_t n_in, uint8_t* out, size_t n_out)
 {
-    static thread_local DecScratch* T = nullptr;
-    if (!T) T = new DecScratch;  // one per pool thread for the life of the process
+    static thread_local std::unique_ptr<DecScratch> scratch;  // 43 KB of tables, one per pool thread for the life of the thread
+    if (!scratch) scratch.reset(new DecScratch);
+    DecScratch* const T = scratch.get();
     BitReader br(in, n_in);
     uint8_t* op = out;
     uint8_t* const out_end = out + n_out;
